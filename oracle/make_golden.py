@@ -1,0 +1,83 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt from the UNMODIFIED reference head.
+
+Run in the authoring container (needs /root/reference):  python -m oracle.make_golden
+Inputs and weights are pure functions of seeds (openpsg_b200/synth.py), so only the reference's
+intermediates are stored, sub-sampled to keep the fixtures small.
+"""
+from __future__ import annotations
+
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+from openpsg_b200 import synth
+from oracle import ref_shims
+
+GOLDEN_DIR = Path(__file__).resolve().parent.parent / "tests" / "golden"
+WEIGHT_SEED = 0
+LLM_FEATURE_SIZE = synth.OPT_TINY["hidden_size"]
+
+
+def build_reference_head(max_object_num=80):
+    cls = ref_shims.load_reference_head_class(synth.OPT_TINY)
+    head = cls(llm_feature_size=LLM_FEATURE_SIZE, max_object_num=max_object_num)
+    synth.init_parameters(head, WEIGHT_SEED)
+    return head
+
+
+def _summarise(rec: dict, keep_pairs) -> dict:
+    kw = rec["qformer_kwargs"]
+    out33 = rec["qformer"][:, :33]
+    g = {
+        "image_tokens": rec["image_tokens"][0].clone(),
+        "input_ids": kw["input_ids"].clone(),
+        "attention_mask": kw["attention_mask"].clone(),
+        "pair_masks": kw["encoder_attention_mask"][:, 0, :].clone(),     # bool [B, L]
+        "keep_pairs": torch.tensor(keep_pairs),
+        "qformer_out_keep": out33[keep_pairs].clone(),                     # [K,33,768]
+        "cls_feature": out33[:, 0].clone(),                                # [B,768]
+        "exist_logits": rec["exist_logits"][:, 0].clone(),
+        "terminal_error": rec.get("terminal_error"),
+    }
+    gens = rec["generate"]
+    g["selected_embeds0"] = gens[0]["inputs_embeds"][0].clone() if gens else None
+    g["llm_masks"] = torch.stack([x["attention_mask"][0] for x in gens]) if gens else None
+    g["sequences"] = [x["sequences"][0].clone() for x in gens]
+    g["scores_first2"] = [x["scores"].clone() for x in gens[:2]]
+    g["lang_proj_first2"] = [x.clone() for x in rec.get("lang_proj", [])[:2]]
+    # the reference's own selection: recompute exactly as v4:236-237 from its probabilities
+    prob = torch.sigmoid(rec["exist_logits"])
+    g["selected"] = prob.squeeze(1).topk(prob.shape[0]).indices.tolist()[:20]
+    return g
+
+
+def main(argv=None):
+    if not ref_shims.reference_available():
+        print("reference not present; golden fixtures can only be generated in the authoring container")
+        return 1
+    GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
+    head = build_reference_head()
+    cases = {
+        "cfg1": (synth.make_image_inputs(synth.WORKLOADS["cfg1"], 0), list(range(0, 64, 4))),
+        "stress": (synth.make_stress_inputs(), [0, 6, 8, 13, 20, 27, 34, 41, 42, 47, 48]),
+        "cfg2": (synth.make_image_inputs(synth.WORKLOADS["cfg2"], 0), [0, 41, 399, 777, 1234, 1599]),
+    }
+    for name, (inputs, keep) in cases.items():
+        t = time.time()
+        rec = ref_shims.run_reference(head, inputs)
+        g = _summarise(rec, keep)
+        if name == "cfg2":   # 1600x768 fp32 cls rows would be 4.9 MB; the logits pin them
+            g["cls_feature"] = g["cls_feature"][keep].clone()
+            g["pair_masks"] = g["pair_masks"][keep].clone()
+            g["input_ids_keep"] = g.pop("input_ids")[keep].clone()
+            g["attention_mask_keep"] = g.pop("attention_mask")[keep].clone()
+            g["image_tokens"] = g["image_tokens"][::16].clone()
+        torch.save(g, GOLDEN_DIR / f"{name}.pt")
+        print(f"{name}: {time.time() - t:.1f}s  ->  {(GOLDEN_DIR / (name + '.pt')).stat().st_size / 1e6:.2f} MB")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
