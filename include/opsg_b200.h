@@ -1,0 +1,153 @@
+/* libopsg_b200 — C ABI of the B200 (sm_100a) relation-head hot path.
+ *
+ * Drop-in boundary for OpenPSG's RelationTransformerHeadV4 inference path
+ * (reference: kings_sgg/models/relation_heads/relation_transformer_head_v4.py:107-358).  The reference is
+ * pure Python calling PyTorch / HuggingFace eager ops, so "the FFI for this path" is the set of eager
+ * calls the head makes; each entry point below names the reference call sites it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - opsg_bf16 is a raw bfloat16 (uint16_t storage); matrices are row-major with explicit leading dims
+ *     in ELEMENTS; bf16 matrices consumed by the tensor-core kernels need 16-byte aligned bases and
+ *     leading dimensions that are multiples of 8 elements (TMA requirement);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, nothing synchronises the host;
+ *   - no allocation happens inside the library (split-K workspaces etc. are caller-provided);
+ *   - return value: 0 = OPSG_OK, negative = error; opsg_last_error_string() describes the last error of
+ *     the calling thread.  There is no CPU fallback: on a machine without an sm_100 device every compute
+ *     entry point returns OPSG_E_NO_DEVICE.
+ */
+#ifndef OPSG_B200_H_
+#define OPSG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t opsg_bf16;
+
+enum {
+  OPSG_OK = 0,
+  OPSG_E_INVALID = -1,     /* bad argument (shape, alignment, null pointer) */
+  OPSG_E_CUDA = -2,        /* CUDA runtime / driver error; see opsg_last_error_string() */
+  OPSG_E_NO_DEVICE = -3,   /* no CUDA device, or device is not compute capability 10.x */
+  OPSG_E_UNSUPPORTED = -4  /* valid request outside the implemented envelope (e.g. L > 256) */
+};
+
+enum { OPSG_ACT_NONE = 0, OPSG_ACT_GELU = 1, OPSG_ACT_RELU = 2 };
+enum { OPSG_OUT_BF16 = 0, OPSG_OUT_F32 = 1, OPSG_OUT_F32_ATOMIC = 2 };
+
+int opsg_version(void);
+const char* opsg_last_error_string(void);
+/* 0 when the current device can run the kernels (compute capability 10.x), else OPSG_E_NO_DEVICE. */
+int opsg_device_check(void);
+int opsg_num_sms(void);
+
+/* ---- a3 / K2: panoptic map -> per-object token bitmasks ------------------------------------------
+ * Replaces v4:416-429 (F.interpolate(nearest) -> F.pad(0) -> F.interpolate(nearest) -> `== object_id`).
+ * pan: int32 [pan_h, pan_w]; obj_ids: int32 [num_objects]; bits_out: uint32 [num_objects, words],
+ * bit (l % 32) of word (l / 32) is set iff token l = ty * tok_w + tx belongs to the object.
+ * words >= ceil(tok_h*tok_w / 32); unused high bits are written as zero.  The N^2 `logical_or` pair masks
+ * of v4:430-433 are never materialised: consumers OR two rows of bits_out.  Bit-exact. */
+int opsg_pair_mask_bits(const int32_t* pan, int pan_h, int pan_w, int img_h, int img_w, int pad_h, int pad_w,
+                        int tok_h, int tok_w, const int32_t* obj_ids, int num_objects, uint32_t* bits_out,
+                        int words, void* stream);
+
+/* ---- a3 / K1: PatchEmbed operand layout -----------------------------------------------------------
+ * Replaces the input side of timm PatchEmbed's Conv2d(k=s=patch) at v4:410: feat fp32 [C, h, w] ->
+ * bf16 [L, C*patch*patch] (L = (h/patch)*(w/patch), row-major tokens, K order (c, py, px) = the conv
+ * weight's own layout), so the projection is one opsg_gemm_bf16 against weight.reshape(C_out, -1). */
+int opsg_patch_im2col(const float* feat, int channels, int h, int w, int patch, opsg_bf16* out, void* stream);
+
+/* ---- K3 / K6 / K9 / K10c: D = act(A . W^T + bias + residual) on tcgen05 tensor cores ----------------
+ * Replaces every nn.Linear on the path (HF modeling_instructblip.py:499-501,504,548,598,606; v4:208,294;
+ * OPT q/k/v/out/fc1/fc2/lm_head).  A: bf16 [M, K] (lda), W: bf16 [N, K] (ldw) = nn.Linear.weight,
+ * D: [M, N] (ldd) bf16 or fp32 per out_mode.  bias: fp32 [N] (or [M] when bias_along_m != 0), may be NULL.
+ * residual: bf16 [M, N] (ldr) added before the activation's output is stored, may be NULL.
+ * k_splits > 1 requires out_mode == OPSG_OUT_F32_ATOMIC: each split atomically adds its partial product
+ * into D (caller pre-initialises D, e.g. with the bias); bias/residual/act must then be NULL/NONE. */
+int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M, int N, int K,
+                   const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, int out_mode,
+                   int k_splits, void* stream);
+
+/* fp32 [rows, cols] (ld_in) -> bf16 (ld_out); init_rows_f32 broadcasts a row vector (bias) into [rows, cols]. */
+int opsg_cast_f32_bf16(const float* in, int ld_in, opsg_bf16* out, int ld_out, int rows, int cols, void* stream);
+int opsg_init_rows_f32(float* out, int ld_out, const float* row, int rows, int cols, void* stream);
+
+/* ---- a4 / K7: Q-Former embeddings -----------------------------------------------------------------
+ * Replaces InstructBlipQFormerEmbeddings.forward (HF :753-782) for B pair queries.
+ * query: fp32 [n_query, d] (= cat(rel_cls_query, relation_query), v4:155-157); input_ids int32 [B, T];
+ * word_emb/pos_emb fp32 tables; h_out bf16 [B*n_query + B*T, d]: row p*n_query+q = LN(query[q]),
+ * row B*n_query + p*T + t = LN(word_emb[ids[p,t]] + pos_emb[t]). */
+int opsg_qformer_embed_ln(const float* query, int n_query, const int32_t* input_ids, int B, int T,
+                          const float* word_emb, int vocab, const float* pos_emb, const float* gamma,
+                          const float* beta, float eps, int d, opsg_bf16* h_out, void* stream);
+
+/* y = LayerNorm(x) * gamma + beta over the last dim; x,y bf16 [rows, cols] (same ld = cols). */
+int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const float* beta, float eps, opsg_bf16* y,
+                        int rows, int cols, void* stream);
+
+/* ---- a5 / K4: Q-Former self-attention core --------------------------------------------------------
+ * Replaces the score/softmax/context part of InstructBlipQFormerMultiHeadAttention.forward (HF :504-536)
+ * for B pair queries whose rows live in the split layout of opsg_qformer_embed_ln.  qkv: bf16 [R, 3*d]
+ * (q | k | v, heads of head_dim inside each); text_mask int32 [B, T] (0 = padded key: the reference's
+ * -10000 additive bias underflows to weight exactly 0); ctx_out bf16 [R_out, d].  Queries: the n_query
+ * query rows of every pair and, if text_queries != 0, the T text rows too. */
+int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_mask, int B, int n_query, int T, int num_heads,
+                         int head_dim, int text_queries, opsg_bf16* ctx_out, void* stream);
+
+/* ---- a6 / K5: pair-query x image-feature masked cross-attention (the north-star kernel) ------------
+ * Replaces the score/softmax/context part of the cross-attention MHA (HF :499-536) as called with
+ * encoder_hidden_states = image tokens expanded to N^2 copies and encoder_attention_mask = pair masks
+ * (v4:168-170,183-184).  q: bf16 [B*n_query, d] (row p*n_query + r), k: bf16 [L, d] (ld_k),
+ * vt: bf16 [d, ld_vt] = V transposed (row h*head_dim + e, col = key), both projected ONCE per image;
+ * bits: uint32 [N, words] from opsg_pair_mask_bits; pair_index int32 [B] or NULL (p -> pair p);
+ * pair p = (i, j) = (pair / N, pair % N) attends keys where bits[i] | bits[j]; masked keys get the
+ * reference's finfo.min bias (weight exactly 0; an all-masked pair attends uniformly to all L keys).
+ * ctx_out: bf16 [B*n_query, d].  Requires head_dim == 64, L <= 256. */
+int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
+                     const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
+                     int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream);
+
+/* ---- a8 / K8: relation-existence filter -----------------------------------------------------------
+ * Replaces v4:206-209 (Linear(768,1) + sigmoid on out[:,0]) and v4:236-237 (topk(B).indices[:k]).
+ * x: bf16 rows of length d with row stride ld_x elements (out[:,0] = every n_query-th row);
+ * w fp32 [d], b fp32 [1]; logits_out/probs_out fp32 [B]; mask_out uint8 [B] = prob > threshold decided
+ * in logit space; topk_out int32 [k] = indices of the k largest logits, ties -> lower index,
+ * descending.  k <= B, B <= 65536. */
+int opsg_exist_filter_topk(const opsg_bf16* x, int ld_x, int B, int d, const float* w, const float* b,
+                           float threshold, int k, float* logits_out, float* probs_out, uint8_t* mask_out,
+                           int32_t* topk_out, void* stream);
+
+/* ---- a11 / K11: mask mean-pool + pair gather ------------------------------------------------------
+ * Replaces detectors/openseed_relation.py:454-468 (obj = sum(feat*mask)/(sum(mask)+1e-8)) and :502-527
+ * (pair = cat(obj[i], obj[j])).  feat fp32 [C, h, w]; label int32 [h, w] = object slot (0..N-1) owning
+ * the pixel or -1; count_scratch fp32 [N] (caller-provided workspace); obj_out fp32 [N, C];
+ * pair_out fp32 [N*N, 2C] (may be NULL). */
+int opsg_mask_pool_pairs(const float* feat, int channels, int h, int w, const int32_t* label, int num_objects,
+                         float* count_scratch, float* obj_out, float* pair_out, void* stream);
+
+/* ---- a9-a10 / K9-K10: LLM prefix assembly, attention, greedy step ---------------------------------
+ * opsg_gather_rows_bf16: out[r] = src[idx[r]] for contiguous row blocks (pair_feature[si], v4:294).
+ * opsg_embed_gather: out[r] = table[ids[r]] (+ pos_table[pos[r]] if given), bf16 out (v4:296; OPT :64-70).
+ * opsg_llm_attn: causal multi-head attention over a static KV cache; q bf16 [nseq*q_len, H*hd],
+ *   k/v cache bf16 [nseq, max_ctx, H*hd]; key_mask uint8 [nseq, max_ctx] (0 = padded key); query t of a
+ *   sequence sits at absolute position q_pos0 + t and sees keys <= its position (HF OPT :75-101).
+ * opsg_argmax_rows: greedy token = argmax over fp32 logits rows (ties -> lower index). */
+int opsg_gather_rows_bf16(const opsg_bf16* src, int row_elems, const int32_t* idx, int n_rows, opsg_bf16* out,
+                          void* stream);
+int opsg_embed_gather(const opsg_bf16* table, int d, const int32_t* ids, const opsg_bf16* pos_table,
+                      const int32_t* pos, int n_rows, opsg_bf16* out, int ld_out, void* stream);
+int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_cache, const opsg_bf16* v_cache, int max_ctx,
+                  const uint8_t* key_mask, int nseq, int q_len, int q_pos0, int num_heads, int head_dim, float scale,
+                  opsg_bf16* out, int ld_out, void* stream);
+int opsg_kv_append(const opsg_bf16* qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model, opsg_bf16* k_cache,
+                   opsg_bf16* v_cache, int max_ctx, void* stream);
+int opsg_argmax_rows(const float* logits, int ld, int rows, int cols, int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPSG_B200_H_ */

@@ -1,0 +1,305 @@
+// K4 / K10a / K10b — small-sequence multi-head attention (Q-Former self-attention over S = 33 + T <= 64 rows per
+// pair; OPT prefill / decode attention over a static KV cache, context <= 128).
+//
+// These problems are tiny and independent (B * heads of them, <= 64 x 128 scores each): one CTA per
+// (sequence, head), whole K / V^T / Q tile in shared memory, register-resident FlashAttention-2 style softmax
+// on warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  They carry ~1% of the path's FLOPs; the big
+// tensor-core work (GEMMs, pair cross-attention) is on tcgen05 — packing several sequences per 128-row tcgen05
+// tile with a block-diagonal mask is the planned upgrade for this kernel.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace opsg {
+
+struct SmallAttnParams {
+  int mode;                       // 0 = Q-Former split layout, 1 = LLM static KV cache
+  // mode 0
+  const __nv_bfloat16* qkv;       // [R, 3*d_model]
+  const int32_t* text_mask;       // [B, T]
+  int B, n_query, T, text_queries;
+  // mode 1
+  const __nv_bfloat16* q;         // [nseq*q_len, ld_q]
+  const __nv_bfloat16* k_cache;   // [nseq, max_ctx, d_model]
+  const __nv_bfloat16* v_cache;
+  const uint8_t* key_mask;        // [nseq, max_ctx]
+  int ld_q, max_ctx, q_len, q_pos0;
+  // common
+  __nv_bfloat16* out;
+  int ld_out, num_heads, d_model;
+  float scale_log2e;
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// HD = head dim (multiple of 16), NK = padded key capacity (multiple of 16), 4 warps x 16 query rows per pass.
+template <int HD, int NK>
+__global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p) {
+  constexpr int QS = HD + 8;      // padded row strides (elements) -> conflict-free fragment loads
+  constexpr int KS = HD + 8;
+  constexpr int VS = NK + 8;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_dyn);      // [64][QS]
+  __nv_bfloat16* sK = sQ + 64 * QS;                                     // [NK][KS]
+  __nv_bfloat16* sVt = sK + NK * KS;                                    // [HD][VS]
+  uint8_t* sValid = reinterpret_cast<uint8_t*>(sVt + HD * VS);          // [NK]
+
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  int n_keys, n_q;
+  if (p.mode == 0) { n_keys = p.n_query + p.T; n_q = p.text_queries ? n_keys : p.n_query; }
+  else             { n_keys = p.q_pos0 + p.q_len; n_q = p.q_len; }
+
+  auto qformer_row = [&](int i) -> size_t {
+    return i < p.n_query ? static_cast<size_t>(seq) * p.n_query + i
+                         : static_cast<size_t>(p.B) * p.n_query + static_cast<size_t>(seq) * p.T + (i - p.n_query);
+  };
+
+  // ---- stage K, V^T and key validity -------------------------------------------------------------
+  constexpr int VEC = HD / 8;
+  for (int idx = threadIdx.x; idx < NK * VEC; idx += blockDim.x) {
+    const int key = idx / VEC, v8 = idx % VEC;
+    uint4 ku = make_uint4(0, 0, 0, 0), vu = make_uint4(0, 0, 0, 0);
+    if (key < n_keys) {
+      if (p.mode == 0) {
+        const __nv_bfloat16* base = p.qkv + qformer_row(key) * (3 * p.d_model) + head * HD + v8 * 8;
+        ku = __ldg(reinterpret_cast<const uint4*>(base + p.d_model));
+        vu = __ldg(reinterpret_cast<const uint4*>(base + 2 * p.d_model));
+      } else {
+        const size_t off = (static_cast<size_t>(seq) * p.max_ctx + key) * p.d_model + head * HD + v8 * 8;
+        ku = __ldg(reinterpret_cast<const uint4*>(p.k_cache + off));
+        vu = __ldg(reinterpret_cast<const uint4*>(p.v_cache + off));
+      }
+    }
+    *reinterpret_cast<uint4*>(sK + key * KS + v8 * 8) = ku;
+    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vu);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sVt[(v8 * 8 + e) * VS + key] = ve[e];
+  }
+  for (int key = threadIdx.x; key < NK; key += blockDim.x) {
+    bool ok = key < n_keys;
+    if (ok) {
+      if (p.mode == 0) ok = key < p.n_query || p.text_mask[static_cast<size_t>(seq) * p.T + (key - p.n_query)] != 0;
+      else ok = p.key_mask[static_cast<size_t>(seq) * p.max_ctx + key] != 0;
+    }
+    sValid[key] = ok ? 1 : 0;
+  }
+
+  for (int q0 = 0; q0 < n_q; q0 += 64) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * VEC; idx += blockDim.x) {
+      const int r = idx / VEC, v8 = idx % VEC;
+      const int qi = q0 + r;
+      uint4 qu = make_uint4(0, 0, 0, 0);
+      if (qi < n_q) {
+        if (p.mode == 0) qu = __ldg(reinterpret_cast<const uint4*>(p.qkv + qformer_row(qi) * (3 * p.d_model) + head * HD + v8 * 8));
+        else qu = __ldg(reinterpret_cast<const uint4*>(p.q + (static_cast<size_t>(seq) * p.q_len + qi) * p.ld_q + head * HD + v8 * 8));
+      }
+      *reinterpret_cast<uint4*>(sQ + r * QS + v8 * 8) = qu;
+    }
+    __syncthreads();
+    if (q0 + warp * 16 >= n_q) continue;   // warp-uniform; no further block-wide barriers below in this pass
+
+    // ---- S = Q K^T ---------------------------------------------------------------------------------
+    float s[NK / 8][4];
+#pragma unroll
+    for (int n = 0; n < NK / 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+    const __nv_bfloat16* qw = sQ + (warp * 16) * QS;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(qw + g * QS + kk * 16 + 2 * t);
+      a[1] = *reinterpret_cast<const uint32_t*>(qw + (g + 8) * QS + kk * 16 + 2 * t);
+      a[2] = *reinterpret_cast<const uint32_t*>(qw + g * QS + kk * 16 + 8 + 2 * t);
+      a[3] = *reinterpret_cast<const uint32_t*>(qw + (g + 8) * QS + kk * 16 + 8 + 2 * t);
+#pragma unroll
+      for (int n = 0; n < NK / 8; ++n) {
+        const __nv_bfloat16* kr = sK + (n * 8 + g) * KS + kk * 16 + 2 * t;
+        mma_bf16_16816(s[n], a, *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+      }
+    }
+    // ---- mask + softmax (rows g and g+8 of this warp's 16) -------------------------------------------
+    const int qi0 = q0 + warp * 16 + g, qi1 = qi0 + 8;
+    const int lim0 = (p.mode == 1) ? p.q_pos0 + qi0 : 0x7fffffff;   // causal: key <= absolute query position
+    const int lim1 = (p.mode == 1) ? p.q_pos0 + qi1 : 0x7fffffff;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NK / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = n * 8 + 2 * t + e;
+        const bool ok = sValid[key] != 0;
+        if (!(ok && key <= lim0)) s[n][e] = -INFINITY;
+        if (!(ok && key <= lim1)) s[n][2 + e] = -INFINITY;
+        m0 = fmaxf(m0, s[n][e]);
+        m1 = fmaxf(m1, s[n][2 + e]);
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    if (m0 == -INFINITY) m0 = 0.f;
+    if (m1 == -INFINITY) m1 = 0.f;
+    const float ms0 = m0 * p.scale_log2e, ms1 = m1 * p.scale_log2e;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NK / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[n][e] = ex2f(fmaf(s[n][e], p.scale_log2e, -ms0));
+        s[n][2 + e] = ex2f(fmaf(s[n][2 + e], p.scale_log2e, -ms1));
+        l0 += s[n][e];
+        l1 += s[n][2 + e];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // ---- O = P V --------------------------------------------------------------------------------------
+    float o[HD / 8][4];
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < NK / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n) {
+        const __nv_bfloat16* vr = sVt + (n * 8 + g) * VS + kk * 16 + 2 * t;
+        mma_bf16_16816(o[n], a, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+      }
+    }
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    auto out_row = [&](int qi) -> __nv_bfloat16* {
+      const size_t row = (p.mode == 0) ? qformer_row(qi) : static_cast<size_t>(seq) * p.q_len + qi;
+      return p.out + row * p.ld_out + head * HD;
+    };
+    if (qi0 < n_q) {
+      __nv_bfloat16* d = out_row(qi0);
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n)
+        *reinterpret_cast<uint32_t*>(d + n * 8 + 2 * t) = pack_bf16x2(o[n][0] * inv0, o[n][1] * inv0);
+    }
+    if (qi1 < n_q) {
+      __nv_bfloat16* d = out_row(qi1);
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n)
+        *reinterpret_cast<uint32_t*>(d + n * 8 + 2 * t) = pack_bf16x2(o[n][2] * inv1, o[n][3] * inv1);
+    }
+  }
+}
+
+template <int HD, int NK>
+static int launch_small_attn(const SmallAttnParams& p, int nseq, cudaStream_t st) {
+  constexpr int smem = (64 * (HD + 8) + NK * (HD + 8) + HD * (NK + 8)) * 2 + NK;
+  static bool configured = false;
+  if (!configured) {
+    int rc = check_cuda(cudaFuncSetAttribute(small_attn_kernel<HD, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                        "cudaFuncSetAttribute(small_attn)");
+    if (rc) return rc;
+    configured = true;
+  }
+  small_attn_kernel<HD, NK><<<dim3(nseq, p.num_heads), 128, smem, st>>>(p);
+  OPSG_CHECK_LAUNCH("small_attn_kernel");
+  return OPSG_OK;
+}
+
+template <int HD>
+static int dispatch_nk(const SmallAttnParams& p, int nseq, int n_keys, cudaStream_t st) {
+  if (n_keys <= 64) return launch_small_attn<HD, 64>(p, nseq, st);
+  if (n_keys <= 128) return launch_small_attn<HD, 128>(p, nseq, st);
+  return set_error(OPSG_E_UNSUPPORTED, "small attention: %d keys > 128 unsupported", n_keys);
+}
+
+static int dispatch_hd(const SmallAttnParams& p, int nseq, int n_keys, int head_dim, cudaStream_t st) {
+  switch (head_dim) {
+    case 64: return dispatch_nk<64>(p, nseq, n_keys, st);
+    case 80: return dispatch_nk<80>(p, nseq, n_keys, st);
+    case 128: return dispatch_nk<128>(p, nseq, n_keys, st);
+    default: return set_error(OPSG_E_UNSUPPORTED, "small attention: head_dim %d unsupported (64, 80, 128)", head_dim);
+  }
+}
+
+__global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model,
+                                 __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int max_ctx) {
+  const int vec = d_model / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(nseq) * q_len * vec) return;
+  const int c = static_cast<int>(idx % vec);
+  const long long r = idx / vec;
+  const int t = static_cast<int>(r % q_len), s = static_cast<int>(r / q_len);
+  const __nv_bfloat16* src = qkv + static_cast<size_t>(r) * ld_qkv + c * 8;
+  const size_t dst = (static_cast<size_t>(s) * max_ctx + pos0 + t) * d_model + c * 8;
+  *reinterpret_cast<uint4*>(k_cache + dst) = __ldg(reinterpret_cast<const uint4*>(src + d_model));
+  *reinterpret_cast<uint4*>(v_cache + dst) = __ldg(reinterpret_cast<const uint4*>(src + 2 * d_model));
+}
+
+}  // namespace opsg
+
+using namespace opsg;
+
+extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_mask, int B, int n_query, int T, int num_heads,
+                                    int head_dim, int text_queries, opsg_bf16* ctx_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(qkv && ctx_out && (T == 0 || text_mask), "self_attn_small: null pointer");
+  OPSG_CHECK_ARG(B > 0 && n_query > 0 && T >= 0 && num_heads > 0, "self_attn_small: bad shape");
+  SmallAttnParams p{};
+  p.mode = 0;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.text_mask = text_mask;
+  p.B = B; p.n_query = n_query; p.T = T; p.text_queries = text_queries;
+  p.out = reinterpret_cast<__nv_bfloat16*>(ctx_out);
+  p.num_heads = num_heads; p.d_model = num_heads * head_dim; p.ld_out = p.d_model;
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+  return dispatch_hd(p, B, n_query + T, head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_cache, const opsg_bf16* v_cache, int max_ctx,
+                             const uint8_t* key_mask, int nseq, int q_len, int q_pos0, int num_heads, int head_dim,
+                             float scale, opsg_bf16* out, int ld_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(q && k_cache && v_cache && key_mask && out, "llm_attn: null pointer");
+  OPSG_CHECK_ARG(nseq > 0 && q_len > 0 && q_pos0 >= 0 && q_pos0 + q_len <= max_ctx, "llm_attn: bad shape");
+  OPSG_CHECK_ARG(ld_q % 8 == 0 && ld_out % 2 == 0, "llm_attn: bad leading dims");
+  SmallAttnParams p{};
+  p.mode = 1;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q);
+  p.k_cache = reinterpret_cast<const __nv_bfloat16*>(k_cache);
+  p.v_cache = reinterpret_cast<const __nv_bfloat16*>(v_cache);
+  p.key_mask = key_mask;
+  p.ld_q = ld_q; p.max_ctx = max_ctx; p.q_len = q_len; p.q_pos0 = q_pos0;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out; p.num_heads = num_heads; p.d_model = num_heads * head_dim;
+  p.scale_log2e = 1.4426950408889634f * scale;
+  return dispatch_hd(p, nseq, q_pos0 + q_len, head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int opsg_kv_append(const opsg_bf16* qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model, opsg_bf16* k_cache,
+                              opsg_bf16* v_cache, int max_ctx, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(qkv && k_cache && v_cache, "kv_append: null pointer");
+  OPSG_CHECK_ARG(nseq > 0 && q_len > 0 && pos0 >= 0 && pos0 + q_len <= max_ctx && d_model % 8 == 0 && ld_qkv % 8 == 0,
+                 "kv_append: bad shape");
+  const long long total = static_cast<long long>(nseq) * q_len * (d_model / 8);
+  kv_append_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv, nseq, q_len, pos0, d_model,
+      reinterpret_cast<__nv_bfloat16*>(k_cache), reinterpret_cast<__nv_bfloat16*>(v_cache), max_ctx);
+  OPSG_CHECK_LAUNCH("kv_append_kernel");
+  return OPSG_OK;
+}

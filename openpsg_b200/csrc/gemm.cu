@@ -1,0 +1,311 @@
+// K3/K6/K9/K10c — D = act(A . W^T + bias + residual), bf16 operands, fp32 accumulation in TMEM.
+//
+// Persistent warp-specialised tcgen05 kernel (one CTA per SM, cta_group::1):
+//   warp 0 (1 thread)  TMA producer : A tile [128 x 64] + W tile [BN x 64] per stage, 128B swizzle
+//   warp 1 (1 thread)  MMA issuer   : 4 x tcgen05.mma 128 x BN x 16 per stage, accumulator in TMEM
+//   warp 2             TMEM allocator (2 accumulator stages x BN columns)
+//   warps 4-7          epilogue     : tcgen05.ld 32x32b (thread = row), bias/residual/act, 16B stores
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static tile
+// scheduler (tile = blockIdx.x + i * gridDim.x, N fastest so the CTAs resident at one time share A tiles
+// through L2).  Out-of-bounds rows/cols/K are zero-filled by TMA and predicated away in the epilogue.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace opsg {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
+constexpr int kGemmThreads = 256;
+
+struct GemmParams {
+  void* D;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int M, N, K;
+  int ldd, ldr;
+  int bias_along_m;
+  int act;
+  int out_mode;
+  int k_splits;
+  int m_tiles, n_tiles;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // +1024 for manual alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * S::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int kb_total = (p.K + kBK - 1) / kBK;
+  const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
+
+  if (threadIdx.x == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int m_t = rest % p.m_tiles;
+      const int split = rest / p.m_tiles;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+        tma_load_2d(smem_a + stage * S::kABytes, &tmA, &full_bar[stage], kb * kBK, m_t * kBM);
+        tma_load_2d(smem_b + stage * S::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_t * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = (tile / p.n_tiles) / p.m_tiles;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
+        const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          umma_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                  (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&tmem_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int m_t = rest % p.m_tiles;
+      const int split = rest / p.m_tiles;
+      const bool has_k = split * kb_per_split < kb_total;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_t * kBM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const float bias_m = (p.bias && p.bias_along_m && row_ok) ? p.bias[row] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_t * BN + c * 32;
+        if (row_ok && col0 < p.N && has_k) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          const bool full = (col0 + 32 <= p.N);
+          if (p.bias) {
+            if (p.bias_along_m) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += bias_m;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+            }
+          }
+          if (p.residual) {
+            const __nv_bfloat16* r = p.residual + static_cast<size_t>(row) * p.ldr + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(r) + j);
+                f[j * 8 + 0] += bf16_lo(u.x); f[j * 8 + 1] += bf16_hi(u.x);
+                f[j * 8 + 2] += bf16_lo(u.y); f[j * 8 + 3] += bf16_hi(u.y);
+                f[j * 8 + 4] += bf16_lo(u.z); f[j * 8 + 5] += bf16_hi(u.z);
+                f[j * 8 + 6] += bf16_lo(u.w); f[j * 8 + 7] += bf16_hi(u.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) f[j] += __bfloat162float(r[j]);
+            }
+          }
+          if (p.act == OPSG_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          } else if (p.act == OPSG_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_mode == OPSG_OUT_BF16) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+                u.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+                u.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+                u.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+                reinterpret_cast<uint4*>(d)[j] = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) d[j] = __float2bfloat16(f[j]);
+            }
+          } else if (p.out_mode == OPSG_OUT_F32) {
+            float* d = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(d)[j] = make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) d[j] = f[j];
+            }
+          } else {  // OPSG_OUT_F32_ATOMIC (split-K)
+            float* d = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(d + j, f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = check_cuda(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             S::kTotal), "cudaFuncSetAttribute(gemm)");
+    if (rc) return rc;
+    configured = true;
+  }
+  p.n_tiles = (p.N + BN - 1) / BN;
+  p.m_tiles = (p.M + kBM - 1) / kBM;
+  const int total = p.m_tiles * p.n_tiles * p.k_splits;
+  const int grid = total < opsg_num_sms() ? total : opsg_num_sms();
+  gemm_bf16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  OPSG_CHECK_LAUNCH("gemm_bf16_kernel");
+  return OPSG_OK;
+}
+
+}  // namespace opsg
+
+using namespace opsg;
+
+extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M, int N,
+                              int K, const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act,
+                              int out_mode, int k_splits, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(A && W && D, "gemm: null pointer");
+  OPSG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  OPSG_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "gemm: leading dimension too small");
+  OPSG_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 elements (TMA)");
+  OPSG_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm: A/W must be 16-byte aligned");
+  OPSG_CHECK_ARG(out_mode >= OPSG_OUT_BF16 && out_mode <= OPSG_OUT_F32_ATOMIC, "gemm: bad out_mode");
+  OPSG_CHECK_ARG(k_splits >= 1, "gemm: k_splits must be >= 1");
+  if (k_splits > 1)
+    OPSG_CHECK_ARG(out_mode == OPSG_OUT_F32_ATOMIC && !bias && !residual && act == OPSG_ACT_NONE,
+                   "gemm: split-K needs OPSG_OUT_F32_ATOMIC and no bias/residual/act");
+  OPSG_CHECK_ARG(!residual || ldr >= N, "gemm: ldr too small");
+
+  // tile width: wide tiles for big problems, narrower ones when the grid would not fill the machine
+  const int m_tiles = (M + kBM - 1) / kBM;
+  int bn = 256;
+  const int sms = opsg_num_sms();
+  while (bn > 32 && (N <= bn / 2 || m_tiles * ((N + bn - 1) / bn) * k_splits < sms)) bn >>= 1;
+
+  CUtensorMap tmA, tmB;
+  rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, kBK);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.D = D; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.ldr = ldr; p.bias_along_m = bias_along_m; p.act = act;
+  p.out_mode = out_mode; p.k_splits = k_splits; p.m_tiles = 0; p.n_tiles = 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_gemm<256, 4>(tmA, tmB, p, st);
+    case 128: return launch_gemm<128, 6>(tmA, tmB, p, st);
+    case 64: return launch_gemm<64, 8>(tmA, tmB, p, st);
+    default: return launch_gemm<32, 8>(tmA, tmB, p, st);
+  }
+}

@@ -1,0 +1,525 @@
+// HBM-bound integer / byte / elementwise kernels of the relation-head path: pair-mask bits (K2), PatchEmbed
+// operand re-layout (K1 input side), Q-Former embeddings + LayerNorm (K7), LayerNorm, existence filter +
+// exact top-k (K8), mask mean-pool + pair gather (K11), row/embedding gathers, argmax.
+// Coalesced 16-byte accesses, warp-shuffle reductions, no tensor cores (none of this is GEMM-shaped).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace opsg {
+
+static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// K2: pan id map -> object token bitmasks.  One warp per (object, 32-token word).
+// nearest index = min(int(floorf(dst * (float(in) / float(out)))), in - 1)  (ATen legacy 'nearest').
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
+  const float scale = __fdiv_rn(static_cast<float>(in_size), static_cast<float>(out_size));
+  const int src = static_cast<int>(floorf(__fmul_rn(static_cast<float>(dst), scale)));
+  return min(src, in_size - 1);
+}
+
+__global__ void pair_mask_bits_kernel(const int32_t* __restrict__ pan, int pan_h, int pan_w, int img_h, int img_w,
+                                      int pad_h, int pad_w, int tok_h, int tok_w, const int32_t* __restrict__ obj_ids,
+                                      int num_objects, uint32_t* __restrict__ bits, int words) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= num_objects * words) return;
+  const int obj = warp_global / words;
+  const int word = warp_global % words;
+  const int l = word * 32 + lane;
+  const int L = tok_h * tok_w;
+  bool hit = false;
+  if (l < L) {
+    const int ty = l / tok_w, tx = l % tok_w;
+    const int r2 = nearest_src(ty, pad_h, tok_h);   // token row -> padded image row   (v4:422-423)
+    const int c2 = nearest_src(tx, pad_w, tok_w);
+    float value = 0.f;                              // F.pad(value=0)                   (v4:420-421)
+    if (r2 < img_h && c2 < img_w) {
+      const int r1 = nearest_src(r2, pan_h, img_h); // image row -> pan row             (v4:417-418)
+      const int c1 = nearest_src(c2, pan_w, img_w);
+      value = static_cast<float>(pan[static_cast<size_t>(r1) * pan_w + c1]);   // .float() round trip
+    }
+    hit = (value == static_cast<float>(obj_ids[obj]));
+  }
+  const uint32_t w = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) bits[static_cast<size_t>(obj) * words + word] = w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 input side: fp32 [C,h,w] -> bf16 [L, C*p*p], K order (c, py, px).  Thread = 8 consecutive px.
+// ------------------------------------------------------------------------------------------------
+__global__ void patch_im2col_kernel(const float* __restrict__ feat, int C, int h, int w, int patch, int th, int tw,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int x8_per_row = (tw * patch) / 8;
+  const long long total = static_cast<long long>(C) * (th * patch) * x8_per_row;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x8 = static_cast<int>(idx % x8_per_row);
+  const long long t = idx / x8_per_row;
+  const int y = static_cast<int>(t % (th * patch));
+  const int c = static_cast<int>(t / (th * patch));
+  const int x = x8 * 8;
+  const float* src = feat + (static_cast<size_t>(c) * h + y) * w + x;
+  float f[8];
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __ldg(src + j);
+  }
+  const int ty = y / patch, py = y % patch, tx = x / patch, px = x % patch;
+  const size_t K = static_cast<size_t>(C) * patch * patch;
+  __nv_bfloat16* dst = out + (static_cast<size_t>(ty) * tw + tx) * K + (static_cast<size_t>(c) * patch + py) * patch + px;
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out, int ld_out,
+                                     int rows, int cols) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx % cols);
+  out[static_cast<size_t>(r) * ld_out + c] = __float2bfloat16(in[static_cast<size_t>(r) * ld_in + c]);
+}
+
+__global__ void init_rows_f32_kernel(float* __restrict__ out, int ld_out, const float* __restrict__ row, int rows, int cols) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx % cols);
+  out[static_cast<size_t>(r) * ld_out + c] = row ? row[c] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm helpers: one warp per row; row kept in registers (cols <= 32 * 8 * kMaxChunks).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxChunks = 12;   // 12 * 256 = 3072 columns
+
+template <int CHUNKS>
+__device__ __forceinline__ void ln_normalize_store(float (&v)[CHUNKS][8], int cols, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i)
+    if ((i * 32 + lane) * 8 < cols) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  const float mean = warp_sum(s) / cols;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i)
+    if ((i * 32 + lane) * 8 < cols) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
+    if (c0 < cols) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(y + c0) = u;
+    }
+  }
+}
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             __nv_bfloat16* __restrict__ y, int rows, int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + static_cast<size_t>(row) * cols;
+  float v[CHUNKS][8];
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
+    if (c0 < cols) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c0));
+      v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
+      v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
+    }
+  }
+  ln_normalize_store<CHUNKS>(v, cols, gamma, beta, eps, y + static_cast<size_t>(row) * cols);
+}
+
+// K7: row p*nq+q = LN(query[q]); row B*nq + p*T + t = LN(word_emb[ids[p,t]] + pos_emb[t]).  d <= 1024.
+__global__ void __launch_bounds__(256) qformer_embed_ln_kernel(const float* __restrict__ query, int nq,
+                                                               const int32_t* __restrict__ ids, int B, int T,
+                                                               const float* __restrict__ word_emb, int vocab,
+                                                               const float* __restrict__ pos_emb,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float eps, int d, __nv_bfloat16* __restrict__ out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_query_rows = B * nq;
+  if (row >= n_query_rows + B * T) return;
+  const float* src;
+  const float* pos = nullptr;
+  if (row < n_query_rows) {
+    src = query + static_cast<size_t>(row % nq) * d;
+  } else {
+    const int r = row - n_query_rows;
+    int id = ids[r];
+    id = min(max(id, 0), vocab - 1);
+    src = word_emb + static_cast<size_t>(id) * d;
+    pos = pos_emb + static_cast<size_t>(r % T) * d;
+  }
+  float v[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
+    if (c0 < d) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + c0) + 1);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+      if (pos) {
+        const float4 pa = __ldg(reinterpret_cast<const float4*>(pos + c0));
+        const float4 pb = __ldg(reinterpret_cast<const float4*>(pos + c0) + 1);
+        v[i][0] += pa.x; v[i][1] += pa.y; v[i][2] += pa.z; v[i][3] += pa.w;
+        v[i][4] += pb.x; v[i][5] += pb.y; v[i][6] += pb.z; v[i][7] += pb.w;
+      }
+    }
+  }
+  ln_normalize_store<4>(v, d, gamma, beta, eps, out + static_cast<size_t>(row) * d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: existence logits (warp per pair) + exact stable top-k by rank counting.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exist_logits_kernel(const __nv_bfloat16* __restrict__ x, int ld_x, int B, int d,
+                                                           const float* __restrict__ w, const float* __restrict__ b,
+                                                           float logit_threshold, float* __restrict__ logits,
+                                                           float* __restrict__ probs, uint8_t* __restrict__ mask) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ld_x;
+  float acc = 0.f;
+  for (int c0 = lane * 8; c0 < d; c0 += 256) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c0));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + c0) + 1);
+    acc += bf16_lo(u.x) * w0.x + bf16_hi(u.x) * w0.y + bf16_lo(u.y) * w0.z + bf16_hi(u.y) * w0.w +
+           bf16_lo(u.z) * w1.x + bf16_hi(u.z) * w1.y + bf16_lo(u.w) * w1.z + bf16_hi(u.w) * w1.w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float z = acc + b[0];
+    logits[row] = z;
+    if (probs) probs[row] = 1.f / (1.f + expf(-z));
+    if (mask) mask[row] = z > logit_threshold ? 1 : 0;
+  }
+}
+
+// rank(i) = #{j : z_j > z_i or (z_j == z_i and j < i)};  rank < k  ->  topk[rank] = i.
+__global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict__ logits, int B, int k,
+                                                        int32_t* __restrict__ topk) {
+  __shared__ float tile[2048];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float zi = i < B ? logits[i] : 0.f;
+  int rank = 0;
+  for (int j0 = 0; j0 < B; j0 += 2048) {
+    const int n = min(2048, B - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) tile[t] = logits[j0 + t];
+    __syncthreads();
+    if (i < B) {
+      for (int t = 0; t < n; ++t) {
+        const float zj = tile[t];
+        rank += (zj > zi || (zj == zi && (j0 + t) < i)) ? 1 : 0;
+      }
+    }
+  }
+  if (i < B && rank < k) topk[rank] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11: mask mean-pool (single pass over the feature map) + pair gather.
+// Warp = 32 consecutive pixels x all channels; lanes sharing a label are reduced with shuffles and the
+// leader adds into obj_sum[label, c].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_pool_accum_kernel(const float* __restrict__ feat, int C, int hw,
+                                                              const int32_t* __restrict__ label, int N,
+                                                              float* __restrict__ obj_sum, float* __restrict__ count) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c_per_block_y = (C + gridDim.y - 1) / gridDim.y;
+  const int c_begin = blockIdx.y * c_per_block_y;
+  const int c_end = min(C, c_begin + c_per_block_y);
+  const int pix = warp * 32 + lane;
+  if (warp * 32 >= hw) return;
+  int lbl = (pix < hw) ? label[pix] : -1;
+  if (lbl >= N) lbl = -1;
+  // distinct labels inside the warp (typically 1-3 for panoptic regions)
+  uint32_t remaining = __ballot_sync(0xffffffffu, lbl >= 0);
+  while (remaining) {
+    const int leader = __ffs(remaining) - 1;
+    const int cur = __shfl_sync(0xffffffffu, lbl, leader);
+    const uint32_t group = __ballot_sync(0xffffffffu, lbl == cur);
+    remaining &= ~group;
+    if (blockIdx.y == 0 && lane == leader) atomicAdd(count + cur, static_cast<float>(__popc(group)));
+    const bool mine = (lbl == cur);
+    for (int c = c_begin; c < c_end; ++c) {
+      float v = (mine && pix < hw) ? __ldg(feat + static_cast<size_t>(c) * hw + pix) : 0.f;
+      v = warp_sum(v);
+      if (lane == leader) atomicAdd(obj_sum + static_cast<size_t>(cur) * C + c, v);
+    }
+  }
+}
+
+__global__ void mask_pool_normalize_kernel(float* __restrict__ obj, const float* __restrict__ count, int N, int C) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * C) return;
+  obj[idx] = obj[idx] / (count[idx / C] + 1e-8f);
+}
+
+__global__ void pair_concat_kernel(const float* __restrict__ obj, int N, int C, float* __restrict__ pair_out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * N * 2 * C) return;
+  const int col = static_cast<int>(idx % (2 * C));
+  const long long p = idx / (2 * C);
+  const int i = static_cast<int>(p / N), j = static_cast<int>(p % N);
+  pair_out[idx] = col < C ? obj[static_cast<size_t>(i) * C + col] : obj[static_cast<size_t>(j) * C + (col - C)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// gathers / argmax
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_rows_bf16_kernel(const uint4* __restrict__ src, int row_vec, const int32_t* __restrict__ idx, int n_rows,
+                                        uint4* __restrict__ out) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(n_rows) * row_vec) return;
+  const int r = static_cast<int>(t / row_vec), c = static_cast<int>(t % row_vec);
+  out[t] = __ldg(src + static_cast<size_t>(idx[r]) * row_vec + c);
+}
+
+__global__ void embed_gather_kernel(const __nv_bfloat16* __restrict__ table, int d, const int32_t* __restrict__ ids,
+                                    const __nv_bfloat16* __restrict__ pos_table, const int32_t* __restrict__ pos, int n_rows,
+                                    __nv_bfloat16* __restrict__ out, int ld_out) {
+  const int vec = d / 8;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(n_rows) * vec) return;
+  const int r = static_cast<int>(t / vec), c = static_cast<int>(t % vec);
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(table + static_cast<size_t>(ids[r]) * d) + c);
+  if (pos_table) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(pos_table + static_cast<size_t>(pos[r]) * d) + c);
+    u.x = pack_bf16x2(bf16_lo(u.x) + bf16_lo(q.x), bf16_hi(u.x) + bf16_hi(q.x));
+    u.y = pack_bf16x2(bf16_lo(u.y) + bf16_lo(q.y), bf16_hi(u.y) + bf16_hi(q.y));
+    u.z = pack_bf16x2(bf16_lo(u.z) + bf16_lo(q.z), bf16_hi(u.z) + bf16_hi(q.z));
+    u.w = pack_bf16x2(bf16_lo(u.w) + bf16_lo(q.w), bf16_hi(u.w) + bf16_hi(q.w));
+  }
+  *(reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * ld_out) + c) = u;
+}
+
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
+                                                          int32_t* __restrict__ out) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  const int row = blockIdx.x;
+  const float* x = logits + static_cast<size_t>(row) * ld;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = x[c];
+    if (v > best || (v == best && c < best_i)) { best = v; best_i = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = best_i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
+      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < best_i)) { best = s_val[w]; best_i = s_idx[w]; }
+    out[row] = best_i;
+  }
+}
+
+}  // namespace opsg
+
+using namespace opsg;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int opsg_pair_mask_bits(const int32_t* pan, int pan_h, int pan_w, int img_h, int img_w, int pad_h, int pad_w,
+                                   int tok_h, int tok_w, const int32_t* obj_ids, int num_objects, uint32_t* bits_out,
+                                   int words, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(pan && obj_ids && bits_out, "pair_mask_bits: null pointer");
+  OPSG_CHECK_ARG(pan_h > 0 && pan_w > 0 && img_h > 0 && img_w > 0 && tok_h > 0 && tok_w > 0 && num_objects > 0,
+                 "pair_mask_bits: bad shape");
+  OPSG_CHECK_ARG(pad_h >= img_h && pad_w >= img_w, "pair_mask_bits: pad_shape smaller than img_shape");
+  OPSG_CHECK_ARG(words * 32 >= tok_h * tok_w, "pair_mask_bits: words too small for %d tokens", tok_h * tok_w);
+  const long long threads = static_cast<long long>(num_objects) * words * 32;
+  pair_mask_bits_kernel<<<ceil_div(threads, 256), 256, 0, ST(stream)>>>(pan, pan_h, pan_w, img_h, img_w, pad_h, pad_w,
+                                                                        tok_h, tok_w, obj_ids, num_objects, bits_out, words);
+  OPSG_CHECK_LAUNCH("pair_mask_bits_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_patch_im2col(const float* feat, int channels, int h, int w, int patch, opsg_bf16* out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(feat && out, "patch_im2col: null pointer");
+  OPSG_CHECK_ARG(patch > 0 && patch % 8 == 0 && h >= patch && w >= patch, "patch_im2col: patch must be a multiple of 8");
+  const int th = h / patch, tw = w / patch;
+  const long long total = static_cast<long long>(channels) * (th * patch) * ((tw * patch) / 8);
+  patch_im2col_kernel<<<ceil_div(total, 256), 256, 0, ST(stream)>>>(feat, channels, h, w, patch, th, tw,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out));
+  OPSG_CHECK_LAUNCH("patch_im2col_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_cast_f32_bf16(const float* in, int ld_in, opsg_bf16* out, int ld_out, int rows, int cols, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(in && out && rows > 0 && cols > 0, "cast_f32_bf16: bad argument");
+  cast_f32_bf16_kernel<<<ceil_div(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream)>>>(
+      in, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
+  OPSG_CHECK_LAUNCH("cast_f32_bf16_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_init_rows_f32(float* out, int ld_out, const float* row, int rows, int cols, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(out && rows > 0 && cols > 0, "init_rows_f32: bad argument");
+  init_rows_f32_kernel<<<ceil_div(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream)>>>(out, ld_out, row, rows, cols);
+  OPSG_CHECK_LAUNCH("init_rows_f32_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_qformer_embed_ln(const float* query, int n_query, const int32_t* input_ids, int B, int T,
+                                     const float* word_emb, int vocab, const float* pos_emb, const float* gamma,
+                                     const float* beta, float eps, int d, opsg_bf16* h_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(query && word_emb && pos_emb && gamma && beta && h_out, "qformer_embed_ln: null pointer");
+  OPSG_CHECK_ARG(T == 0 || input_ids, "qformer_embed_ln: null input_ids");
+  OPSG_CHECK_ARG(d % 8 == 0 && d <= 1024 && B > 0 && n_query > 0 && T >= 0, "qformer_embed_ln: bad shape (d=%d)", d);
+  const long long rows = static_cast<long long>(B) * (n_query + T);
+  qformer_embed_ln_kernel<<<ceil_div(rows * 32, 256), 256, 0, ST(stream)>>>(query, n_query, input_ids, B, T, word_emb, vocab,
+                                                                           pos_emb, gamma, beta, eps, d,
+                                                                           reinterpret_cast<__nv_bfloat16*>(h_out));
+  OPSG_CHECK_LAUNCH("qformer_embed_ln_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const float* beta, float eps, opsg_bf16* y,
+                                   int rows, int cols, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(x && gamma && beta && y, "layernorm: null pointer");
+  OPSG_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 256 * kMaxChunks, "layernorm: cols=%d unsupported", cols);
+  const int grid = ceil_div(static_cast<long long>(rows) * 32, 256);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  if (cols <= 1024) layernorm_bf16_kernel<4><<<grid, 256, 0, ST(stream)>>>(xp, gamma, beta, eps, yp, rows, cols);
+  else layernorm_bf16_kernel<kMaxChunks><<<grid, 256, 0, ST(stream)>>>(xp, gamma, beta, eps, yp, rows, cols);
+  OPSG_CHECK_LAUNCH("layernorm_bf16_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_exist_filter_topk(const opsg_bf16* x, int ld_x, int B, int d, const float* w, const float* b,
+                                      float threshold, int k, float* logits_out, float* probs_out, uint8_t* mask_out,
+                                      int32_t* topk_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(x && w && b && logits_out, "exist_filter_topk: null pointer");
+  OPSG_CHECK_ARG(B > 0 && B <= 65536 && d % 8 == 0 && ld_x % 8 == 0, "exist_filter_topk: bad shape");
+  OPSG_CHECK_ARG(k >= 0 && k <= B && (k == 0 || topk_out), "exist_filter_topk: bad k");
+  OPSG_CHECK_ARG(threshold > 0.f && threshold < 1.f, "exist_filter_topk: threshold must be in (0,1)");
+  const float logit_thr = logf(threshold / (1.f - threshold));
+  exist_logits_kernel<<<ceil_div(static_cast<long long>(B) * 32, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ld_x, B, d, w, b, logit_thr, logits_out, probs_out, mask_out);
+  OPSG_CHECK_LAUNCH("exist_logits_kernel");
+  if (k > 0) {
+    topk_rank_kernel<<<ceil_div(B, 256), 256, 0, ST(stream)>>>(logits_out, B, k, topk_out);
+    OPSG_CHECK_LAUNCH("topk_rank_kernel");
+  }
+  return OPSG_OK;
+}
+
+extern "C" int opsg_mask_pool_pairs(const float* feat, int channels, int h, int w, const int32_t* label, int num_objects,
+                                    float* count_scratch, float* obj_out, float* pair_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(feat && label && obj_out && count_scratch, "mask_pool_pairs: null pointer");
+  OPSG_CHECK_ARG(channels > 0 && h > 0 && w > 0 && num_objects > 0, "mask_pool_pairs: bad shape");
+  rc = check_cuda(cudaMemsetAsync(obj_out, 0, static_cast<size_t>(num_objects) * channels * sizeof(float), ST(stream)),
+                  "cudaMemsetAsync(obj_out)");
+  if (rc) return rc;
+  rc = check_cuda(cudaMemsetAsync(count_scratch, 0, static_cast<size_t>(num_objects) * sizeof(float), ST(stream)),
+                  "cudaMemsetAsync(count)");
+  if (rc) return rc;
+  const int hw = h * w;
+  const int warps = ceil_div(hw, 32);
+  dim3 grid(ceil_div(static_cast<long long>(warps) * 32, 256), channels >= 64 ? 8 : 1);
+  mask_pool_accum_kernel<<<grid, 256, 0, ST(stream)>>>(feat, channels, hw, label, num_objects, obj_out, count_scratch);
+  OPSG_CHECK_LAUNCH("mask_pool_accum_kernel");
+  mask_pool_normalize_kernel<<<ceil_div(static_cast<long long>(num_objects) * channels, 256), 256, 0, ST(stream)>>>(
+      obj_out, count_scratch, num_objects, channels);
+  OPSG_CHECK_LAUNCH("mask_pool_normalize_kernel");
+  if (pair_out) {
+    const long long total = static_cast<long long>(num_objects) * num_objects * 2 * channels;
+    pair_concat_kernel<<<ceil_div(total, 256), 256, 0, ST(stream)>>>(obj_out, num_objects, channels, pair_out);
+    OPSG_CHECK_LAUNCH("pair_concat_kernel");
+  }
+  return OPSG_OK;
+}
+
+extern "C" int opsg_gather_rows_bf16(const opsg_bf16* src, int row_elems, const int32_t* idx, int n_rows, opsg_bf16* out,
+                                     void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(src && idx && out && n_rows > 0 && row_elems > 0 && row_elems % 8 == 0, "gather_rows: bad argument");
+  const int row_vec = row_elems / 8;
+  gather_rows_bf16_kernel<<<ceil_div(static_cast<long long>(n_rows) * row_vec, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(src), row_vec, idx, n_rows, reinterpret_cast<uint4*>(out));
+  OPSG_CHECK_LAUNCH("gather_rows_bf16_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_embed_gather(const opsg_bf16* table, int d, const int32_t* ids, const opsg_bf16* pos_table,
+                                 const int32_t* pos, int n_rows, opsg_bf16* out, int ld_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(table && ids && out && n_rows > 0 && d % 8 == 0 && ld_out % 8 == 0, "embed_gather: bad argument");
+  OPSG_CHECK_ARG(!pos_table || pos, "embed_gather: pos_table without pos");
+  embed_gather_kernel<<<ceil_div(static_cast<long long>(n_rows) * (d / 8), 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(table), d, ids, reinterpret_cast<const __nv_bfloat16*>(pos_table), pos, n_rows,
+      reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  OPSG_CHECK_LAUNCH("embed_gather_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_argmax_rows(const float* logits, int ld, int rows, int cols, int32_t* out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(logits && out && rows > 0 && cols > 0 && ld >= cols, "argmax_rows: bad argument");
+  argmax_rows_kernel<<<rows, 256, 0, ST(stream)>>>(logits, ld, rows, cols, out);
+  OPSG_CHECK_LAUNCH("argmax_rows_kernel");
+  return OPSG_OK;
+}

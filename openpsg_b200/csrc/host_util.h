@@ -1,0 +1,30 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and TMA tensor-map creation.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/opsg_b200.h"
+
+namespace opsg {
+
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// 2-D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows};
+// 128-byte swizzle (box_cols * 2 bytes must be <= 128).  Out-of-bounds elements read as zero.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols);
+
+#define OPSG_CHECK_ARG(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) return ::opsg::set_error(OPSG_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define OPSG_CHECK_LAUNCH(what)                                     \
+  do {                                                              \
+    int _rc = ::opsg::check_cuda(cudaGetLastError(), what);         \
+    if (_rc) return _rc;                                            \
+  } while (0)
+
+}  // namespace opsg

@@ -1,0 +1,222 @@
+"""torch.Tensor -> raw pointer marshalling for the C ABI (include/opsg_b200.h).
+
+PyTorch is used only for device memory and streams; every function here enqueues hand-written CUDA
+kernels from libopsg_b200.so on the current torch CUDA stream and returns without synchronising.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, OUT_BF16, OUT_F32, OUT_F32_ATOMIC  # noqa: F401
+
+launch_count = 0   # kernels enqueued through this module (bench.py reports it as gpu_launches)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(t: torch.Tensor, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (libopsg_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def pair_mask_bits(pan: torch.Tensor, img_hw, pad_hw, tok_hw, obj_ids: torch.Tensor, words: Optional[int] = None):
+    """K2: int32 pan map [h,w] + object ids [N] -> uint32-as-int32 bit masks [N, words]."""
+    pan = _cuda(pan, torch.int32, "pan").contiguous()
+    obj_ids = _cuda(obj_ids, torch.int32, "obj_ids").contiguous()
+    L = tok_hw[0] * tok_hw[1]
+    words = words or max(1, (L + 31) // 32)
+    bits = torch.empty((obj_ids.numel(), words), dtype=torch.int32, device=pan.device)
+    _lib.check(_lib.load().opsg_pair_mask_bits(_ptr(pan), pan.shape[0], pan.shape[1], int(img_hw[0]), int(img_hw[1]),
+                                              int(pad_hw[0]), int(pad_hw[1]), int(tok_hw[0]), int(tok_hw[1]),
+                                              _ptr(obj_ids), obj_ids.numel(), _ptr(bits), words, _stream()))
+    _count()
+    return bits
+
+
+def patch_im2col(feat: torch.Tensor, patch: int) -> torch.Tensor:
+    """K1 operand: fp32 [C,h,w] -> bf16 [L, C*patch*patch]."""
+    feat = _cuda(feat, torch.float32, "feat").contiguous()
+    C, h, w = feat.shape
+    L = (h // patch) * (w // patch)
+    out = torch.empty((L, C * patch * patch), dtype=torch.bfloat16, device=feat.device)
+    _lib.check(_lib.load().opsg_patch_im2col(_ptr(feat), C, h, w, patch, _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, residual: Optional[torch.Tensor] = None,
+         act: int = ACT_NONE, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, bias_along_m: bool = False,
+         k_splits: int = 1, atomic: bool = False) -> torch.Tensor:
+    """D = act(a @ w.T + bias + residual).  a bf16 [M,K], w bf16 [N,K] (nn.Linear layout)."""
+    _cuda(a, torch.bfloat16, "a"); _cuda(w, torch.bfloat16, "w")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    mode = OUT_F32_ATOMIC if atomic else (OUT_BF16 if out.dtype == torch.bfloat16 else OUT_F32)
+    if bias is not None:
+        _cuda(bias, torch.float32, "bias")
+    if residual is not None:
+        _cuda(residual, torch.bfloat16, "residual")
+        assert residual.shape == (M, N) and residual.stride(1) == 1
+    _lib.check(_lib.load().opsg_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                         _ptr(bias), int(bias_along_m), _ptr(residual),
+                                         residual.stride(0) if residual is not None else 0, act, mode, k_splits, _stream()))
+    _count()
+    return out
+
+
+def cast_f32_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, torch.float32, "x")
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().opsg_cast_f32_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, cols, _stream()))
+    _count()
+    return out
+
+
+def init_rows_f32(out: torch.Tensor, row: Optional[torch.Tensor]) -> torch.Tensor:
+    _cuda(out, torch.float32, "out")
+    _lib.check(_lib.load().opsg_init_rows_f32(_ptr(out), out.stride(0), _ptr(row), out.shape[0], out.shape[1], _stream()))
+    _count()
+    return out
+
+
+def qformer_embed_ln(query, input_ids, word_emb, pos_emb, gamma, beta, eps, out=None):
+    """K7: rows [B*nq + B*T, d] bf16 in the split (query rows | text rows) layout."""
+    nq, d = query.shape
+    B, T = input_ids.shape
+    _cuda(input_ids, torch.int32, "input_ids")
+    if out is None:
+        out = torch.empty((B * (nq + T), d), dtype=torch.bfloat16, device=query.device)
+    _lib.check(_lib.load().opsg_qformer_embed_ln(_ptr(query), nq, _ptr(input_ids), B, T, _ptr(word_emb), word_emb.shape[0],
+                                                _ptr(pos_emb), _ptr(gamma), _ptr(beta), float(eps), d, _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out=None) -> torch.Tensor:
+    _cuda(x, torch.bfloat16, "x")
+    assert x.is_contiguous()
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.load().opsg_layernorm_bf16(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(out), rows, cols, _stream()))
+    _count()
+    return out
+
+
+def self_attn_small(qkv, text_mask, B, n_query, T, num_heads, head_dim, text_queries: bool, out=None):
+    _cuda(qkv, torch.bfloat16, "qkv")
+    d = num_heads * head_dim
+    assert qkv.is_contiguous() and qkv.shape[1] == 3 * d
+    rows = B * (n_query + T) if text_queries else B * n_query
+    if out is None:
+        out = torch.empty((rows, d), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.load().opsg_self_attn_small(_ptr(qkv), _ptr(text_mask), B, n_query, T, num_heads, head_dim,
+                                               int(text_queries), _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def xattn_pairs(q, k, vt, bits, num_objects, B, n_query, L, num_heads, head_dim, pair_index=None, out=None):
+    """K5: q bf16 [B*nq, d]; k bf16 [L, d]; vt bf16 [d, ld>=L]; bits int32 [N, words]."""
+    _cuda(q, torch.bfloat16, "q"); _cuda(k, torch.bfloat16, "k"); _cuda(vt, torch.bfloat16, "vt")
+    assert q.is_contiguous()
+    if out is None:
+        out = torch.empty_like(q)
+    _lib.check(_lib.load().opsg_xattn_pairs(_ptr(q), _ptr(k), k.stride(0), _ptr(vt), vt.stride(0), _ptr(bits), bits.shape[1],
+                                           _ptr(pair_index), num_objects, B, n_query, L, num_heads, head_dim, _ptr(out),
+                                           _stream()))
+    _count()
+    return out
+
+
+def exist_filter_topk(x: torch.Tensor, ld_x: int, B: int, d: int, w: torch.Tensor, b: torch.Tensor, threshold: float, k: int):
+    """K8: returns (logits fp32 [B], probs fp32 [B], mask uint8 [B], topk int32 [k])."""
+    dev = x.device
+    logits = torch.empty(B, dtype=torch.float32, device=dev)
+    probs = torch.empty(B, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, dtype=torch.uint8, device=dev)
+    topk = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().opsg_exist_filter_topk(_ptr(x), ld_x, B, d, _ptr(w), _ptr(b), float(threshold), k, _ptr(logits),
+                                                 _ptr(probs), _ptr(mask), _ptr(topk), _stream()))
+    _count(2)
+    return logits, probs, mask, topk[:k]
+
+
+def mask_pool_pairs(feat: torch.Tensor, label: torch.Tensor, num_objects: int, with_pairs: bool = True):
+    """K11: feat fp32 [C,h,w], label int32 [h,w] -> (obj [N,C], pair [N*N,2C] or None)."""
+    _cuda(feat, torch.float32, "feat"); _cuda(label, torch.int32, "label")
+    C, h, w = feat.shape
+    obj = torch.empty((num_objects, C), dtype=torch.float32, device=feat.device)
+    cnt = torch.empty((num_objects,), dtype=torch.float32, device=feat.device)
+    pair = torch.empty((num_objects * num_objects, 2 * C), dtype=torch.float32, device=feat.device) if with_pairs else None
+    _lib.check(_lib.load().opsg_mask_pool_pairs(_ptr(feat.contiguous()), C, h, w, _ptr(label.contiguous()), num_objects,
+                                               _ptr(cnt), _ptr(obj), _ptr(pair), _stream()))
+    _count(3 if with_pairs else 2)
+    return obj, pair
+
+
+def gather_rows(src: torch.Tensor, row_elems: int, idx: torch.Tensor, out=None):
+    _cuda(src, torch.bfloat16, "src"); _cuda(idx, torch.int32, "idx")
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n, row_elems), dtype=torch.bfloat16, device=src.device)
+    _lib.check(_lib.load().opsg_gather_rows_bf16(_ptr(src), row_elems, _ptr(idx), n, _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def embed_gather(table, ids, out, pos_table=None, pos=None):
+    _cuda(table, torch.bfloat16, "table"); _cuda(ids, torch.int32, "ids")
+    n, d = ids.numel(), table.shape[1]
+    _lib.check(_lib.load().opsg_embed_gather(_ptr(table), d, _ptr(ids), _ptr(pos_table), _ptr(pos), n, _ptr(out),
+                                            out.stride(0), _stream()))
+    _count()
+    return out
+
+
+def llm_attn(q, k_cache, v_cache, key_mask, nseq, q_len, q_pos0, num_heads, head_dim, scale, out):
+    max_ctx = k_cache.shape[1]
+    _lib.check(_lib.load().opsg_llm_attn(_ptr(q), q.stride(0), _ptr(k_cache), _ptr(v_cache), max_ctx, _ptr(key_mask), nseq,
+                                        q_len, q_pos0, num_heads, head_dim, float(scale), _ptr(out), out.stride(0), _stream()))
+    _count()
+    return out
+
+
+def kv_append(qkv, nseq, q_len, pos0, d_model, k_cache, v_cache):
+    _lib.check(_lib.load().opsg_kv_append(_ptr(qkv), qkv.stride(0), nseq, q_len, pos0, d_model, _ptr(k_cache), _ptr(v_cache),
+                                         k_cache.shape[1], _stream()))
+    _count()
+
+
+def argmax_rows(logits: torch.Tensor, out=None):
+    _cuda(logits, torch.float32, "logits")
+    rows, cols = logits.shape
+    if out is None:
+        out = torch.empty(rows, dtype=torch.int32, device=logits.device)
+    _lib.check(_lib.load().opsg_argmax_rows(_ptr(logits), logits.stride(0), rows, cols, _ptr(out), _stream()))
+    _count()
+    return out

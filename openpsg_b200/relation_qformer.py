@@ -1,0 +1,185 @@
+"""RelationQueryTransformer: the N^2 pair-query Q-Former + existence filter on libopsg_b200 kernels.
+
+Host-side orchestration of rows a3-a8 of SURVEY.md §8 for ONE image: what the reference does at
+``relation_transformer_head_v4.py:155-209,236-237,408-435`` by calling HF's
+``InstructBlipQFormerModel`` (modeling_instructblip.py:634-938) on N^2 expanded copies.  Here:
+
+  * pair masks stay as N x ceil(L/32) bit words (K2) and are OR-ed inside the cross-attention kernel;
+  * image tokens are projected to K / V^T ONCE per image per layer (K3), not once per pair;
+  * all pairs' rows are stacked along M: rows [0, B*33) are query rows (pair-major), rows
+    [B*33, B*33 + B*T) are instruction-text rows, so every Linear is one tcgen05 GEMM (K6);
+  * the last layer only computes what ``[:, :33]`` (v4:185) can observe.
+
+Every arithmetic step is a C-ABI call (``openpsg_b200.ops``); torch only owns the buffers.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+NUM_HEADS = 12
+HEAD_DIM = 64
+N_QUERY = 33
+LN_EPS = 1e-12
+
+
+def _bf16(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class PackedQFormer:
+    """Device-resident, kernel-ready copy of the head's relation-query weights (bf16 matrices, fp32
+    biases / LayerNorm / embedding tables).  Built from a state dict with the reference's parameter
+    names (SURVEY.md §5 checkpoint contract)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device, num_layers: int = 2, patch: int = 16,
+                 prefix: str = "relation_qformer."):
+        self.device = device
+        self.num_layers = num_layers
+        self.patch = patch
+        d = sd["rel_cls_query"].shape[-1]
+        self.d = d
+        self.query = _f32(torch.cat([sd["rel_cls_query"], sd["relation_query"]], dim=1)[0], device)      # [33,d]
+        pw = sd["patch_embed.proj.weight"]
+        self.patch_w = _bf16(pw.reshape(pw.shape[0], -1), device)                                           # [256, 65536]
+        self.patch_b = _f32(sd["patch_embed.proj.bias"], device)
+        e = prefix + "embeddings."
+        self.word_emb = _f32(sd[e + "word_embeddings.weight"], device)
+        self.pos_emb = _f32(sd[e + "position_embeddings.weight"], device)
+        self.emb_ln = (_f32(sd[e + "layernorm.weight"], device), _f32(sd[e + "layernorm.bias"], device))
+        self.layers = []
+        for l in range(num_layers):
+            lp = f"{prefix}encoder.layer.{l}."
+
+            def W(name):
+                return _bf16(sd[lp + name + ".weight"], device)
+
+            def Bv(name):
+                return _f32(sd[lp + name + ".bias"], device)
+
+            def LN(name):
+                return (_f32(sd[lp + name + ".weight"], device), _f32(sd[lp + name + ".bias"], device))
+
+            a = "attention.attention."
+            c = "crossattention.attention."
+            layer = dict(
+                w_qkv=_bf16(torch.cat([sd[lp + a + "query.weight"], sd[lp + a + "key.weight"], sd[lp + a + "value.weight"]], 0), device),
+                b_qkv=_f32(torch.cat([sd[lp + a + "query.bias"], sd[lp + a + "key.bias"], sd[lp + a + "value.bias"]], 0), device),
+                w_o=W("attention.output.dense"), b_o=Bv("attention.output.dense"), ln_self=LN("attention.output.LayerNorm"),
+                w_cq=W(c + "query"), b_cq=Bv(c + "query"),
+                w_ck=W(c + "key"), b_ck=Bv(c + "key"), w_cv=W(c + "value"), b_cv=Bv(c + "value"),
+                w_co=W("crossattention.output.dense"), b_co=Bv("crossattention.output.dense"),
+                ln_cross=LN("crossattention.output.LayerNorm"),
+                w_iq=W("intermediate_query.dense"), b_iq=Bv("intermediate_query.dense"),
+                w_oq=W("output_query.dense"), b_oq=Bv("output_query.dense"), ln_q=LN("output_query.LayerNorm"),
+                w_it=W("intermediate.dense"), b_it=Bv("intermediate.dense"),
+                w_ot=W("output.dense"), b_ot=Bv("output.dense"), ln_t=LN("output.LayerNorm"),
+            )
+            self.layers.append(layer)
+        self.exist_w = _f32(sd["binary_rel_cls_pred.weight"].reshape(-1), device)
+        self.exist_b = _f32(sd["binary_rel_cls_pred.bias"].reshape(-1), device)
+
+
+@dataclass
+class RelationQueryOutput:
+    hidden: torch.Tensor            # bf16 [B*33, d]: last_hidden_state[:, :33] stacked pair-major
+    logits: torch.Tensor            # fp32 [B]
+    probs: torch.Tensor             # fp32 [B]
+    exist_mask: torch.Tensor        # uint8 [B]
+    topk: torch.Tensor              # int32 [k]
+    mask_bits: torch.Tensor         # int32 [N, words]
+    image_tokens: torch.Tensor      # bf16 [L, 256]
+    intermediates: Optional[dict] = None
+
+
+class RelationQueryTransformer:
+    def __init__(self, weights: PackedQFormer):
+        self.w = weights
+
+    # -- K1 ------------------------------------------------------------------------------------------
+    def image_tokens(self, feat: torch.Tensor) -> torch.Tensor:
+        """timm PatchEmbed (v4:410): Conv2d(k=s=16) as im2col + split-K tcgen05 GEMM.  feat fp32 [C,h,w]."""
+        w = self.w
+        a = ops.patch_im2col(feat, w.patch)                                  # bf16 [L, C*p*p]
+        L, K = a.shape
+        acc = torch.empty((L, w.patch_w.shape[0]), dtype=torch.float32, device=feat.device)
+        ops.init_rows_f32(acc, w.patch_b)
+        kb = K // 64
+        m_tiles = (L + 127) // 128
+        splits = max(1, min(kb, 148 // max(1, m_tiles)))
+        ops.gemm(a, w.patch_w, out=acc, atomic=True, k_splits=splits)
+        return ops.cast_f32_bf16(acc)
+
+    # -- a3..a8 --------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, feat: torch.Tensor, pan: torch.Tensor, img_hw, pad_hw, obj_ids: torch.Tensor,
+                input_ids: torch.Tensor, text_mask: torch.Tensor, *, topk: int = 20, threshold: float = 0.5,
+                pair_index: Optional[torch.Tensor] = None, keep_intermediates: bool = False) -> RelationQueryOutput:
+        """feat fp32 [C,h,w]; pan int32 [Hp,Wp]; obj_ids int32 [N]; input_ids/text_mask int32 [B,T]
+        (B = N*N unless pair_index int32 [B] selects a subset of pairs)."""
+        w = self.w
+        dev = feat.device
+        d = w.d
+        N = obj_ids.numel()
+        B, T = input_ids.shape
+        th, tw = feat.shape[-2] // w.patch, feat.shape[-1] // w.patch
+        L = th * tw
+        inter = {} if keep_intermediates else None
+
+        bits = ops.pair_mask_bits(pan, img_hw, pad_hw, (th, tw), obj_ids)       # K2
+        X = self.image_tokens(feat)                                              # K1  [L,256]
+        h = ops.qformer_embed_ln(w.query, input_ids, w.word_emb, w.pos_emb, w.emb_ln[0], w.emb_ln[1], LN_EPS)   # K7
+        RQ = B * N_QUERY
+        if inter is not None:
+            inter["embeddings"] = h
+        Lp = (L + 7) // 8 * 8
+        for li, lw in enumerate(w.layers):
+            last = li == len(w.layers) - 1
+            # K3: per-image K and V^T for this layer's cross-attention (shared by all pairs)
+            kc = ops.gemm(X, lw["w_ck"], lw["b_ck"])                             # [L, d]
+            vt = torch.zeros((d, Lp), dtype=torch.bfloat16, device=dev)
+            ops.gemm(lw["w_cv"], X, lw["b_cv"], bias_along_m=True, out=vt[:, :L])  # V^T [d, L]
+            # self-attention over the 33 + T rows of every pair
+            qkv = ops.gemm(h, lw["w_qkv"], lw["b_qkv"])                          # [R, 3d]
+            ctx = ops.self_attn_small(qkv, text_mask, B, N_QUERY, T, NUM_HEADS, HEAD_DIM, text_queries=not last)
+            rows = ctx.shape[0]                                                  # R, or B*33 on the last layer
+            pre = ops.gemm(ctx, lw["w_o"], lw["b_o"], residual=h[:rows])
+            h1 = ops.layernorm(pre, lw["ln_self"][0], lw["ln_self"][1], LN_EPS)
+            hq = h1[:RQ]
+            # K5: masked pair x image cross-attention on the query rows
+            qc = ops.gemm(hq, lw["w_cq"], lw["b_cq"])
+            cx = ops.xattn_pairs(qc, kc, vt, bits, N, B, N_QUERY, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index)
+            pre = ops.gemm(cx, lw["w_co"], lw["b_co"], residual=hq)
+            hq2 = ops.layernorm(pre, lw["ln_cross"][0], lw["ln_cross"][1], LN_EPS)
+            # FFN (query rows; text rows only where a later layer can still see them)
+            h_next = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
+            f = ops.gemm(hq2, lw["w_iq"], lw["b_iq"], act=ops.ACT_GELU)
+            pre = ops.gemm(f, lw["w_oq"], lw["b_oq"], residual=hq2)
+            ops.layernorm(pre, lw["ln_q"][0], lw["ln_q"][1], LN_EPS, out=h_next[:RQ])
+            if not last and T > 0:
+                ht = h1[RQ:]
+                f = ops.gemm(ht, lw["w_it"], lw["b_it"], act=ops.ACT_GELU)
+                pre = ops.gemm(f, lw["w_ot"], lw["b_ot"], residual=ht)
+                ops.layernorm(pre, lw["ln_t"][0], lw["ln_t"][1], LN_EPS, out=h_next[RQ:])
+            if inter is not None:
+                inter[f"l{li}.self"] = h1
+                inter[f"l{li}.xattn_q"] = qc
+                inter[f"l{li}.xattn_ctx"] = cx
+                inter[f"l{li}.cross"] = hq2
+                inter[f"l{li}.out"] = h_next
+                inter[f"l{li}.k"] = kc
+                inter[f"l{li}.vt"] = vt
+            h = h_next
+        out = h[:RQ]
+        logits, probs, mask, top = ops.exist_filter_topk(out, N_QUERY * d, B, d, w.exist_w, w.exist_b, threshold,
+                                                         min(topk, B))           # K8
+        return RelationQueryOutput(hidden=out, logits=logits, probs=probs, exist_mask=mask, topk=top, mask_bits=bits,
+                                   image_tokens=X, intermediates=inter)

@@ -212,19 +212,21 @@ class SyntheticTokenizer:
 
 
 def init_parameters(module: torch.nn.Module, seed: int = 0, *, skip_prefixes=()) -> None:
-    """Fill every parameter from one seeded CPU generator, in sorted-name order.
+    """Fill every parameter from a CPU generator seeded with (seed, crc32(parameter name)).
 
-    Being a pure function of (names, shapes, seed) it gives the reference head (built under the
-    oracle shims) and the drop-in head identical weights without shipping 270 MB fixtures.
+    Being a pure function of (name, shape, seed) it gives the reference head (built under the oracle
+    shims), the oracle port and the drop-in head identical weights — whichever subset of modules each
+    one owns — without shipping 270 MB fixtures.
     Scales: Linear/Conv weights ~ N(0, 0.04^2) (patch_embed ~ 1/sqrt(fan_in)), biases ~ N(0, 0.02^2),
     LayerNorm gamma = 1 + 0.1 N(0,1), embeddings ~ N(0, 0.02^2), learned queries ~ N(0, 1)
     (reference init v4:87-90), language-model weights ~ N(0, 0.02^2).
     """
-    gen = torch.Generator().manual_seed(seed)
+    gen = torch.Generator()
     with torch.no_grad():
         for name, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
             if any(name.startswith(pre) for pre in skip_prefixes):
                 continue
+            gen.manual_seed((seed * 1000003 + zlib.crc32(name.encode("utf-8"))) & 0x7FFFFFFFFFFF)
             lname = name.lower()
             r = torch.randn(p.shape, generator=gen, dtype=torch.float32)
             is_lm = name.startswith("language_model")

@@ -1,0 +1,339 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (openpsg_b200.ops -> libopsg_b200.so).
+
+Integer / bit outputs must be bit-exact against the oracle; floating-point outputs are compared with a
+torch fp32 evaluation of the same bf16-rounded inputs, tolerance stated per test."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from openpsg_b200 import synth
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from openpsg_b200 import ops as _ops
+    return _ops
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand_bf16(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen) * scale).to(torch.bfloat16)
+
+
+# ----------------------------------------------------------------------------------------------
+# K6: tcgen05 GEMM.  tolerance: |err| <= 1e-2 * max|ref| + bf16 output rounding (2^-8 relative)
+# ----------------------------------------------------------------------------------------------
+GEMM_CASES = [
+    # M, N, K, bias, residual, act, out_dtype
+    (128, 256, 64, False, False, 0, torch.bfloat16),
+    (128, 256, 768, True, False, 0, torch.bfloat16),
+    (300, 768, 768, True, True, 0, torch.bfloat16),
+    (1000, 3072, 768, True, False, 1, torch.bfloat16),
+    (517, 768, 3072, True, True, 0, torch.bfloat16),
+    (2112, 2304, 768, True, False, 0, torch.bfloat16),
+    (100, 2560, 320, True, False, 2, torch.bfloat16),
+    (49, 1024, 320, False, False, 0, torch.float32),
+    (20000, 768, 768, True, True, 0, torch.bfloat16),
+    (130, 72, 136, True, False, 0, torch.float32),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: f"{c[0]}x{c[1]}x{c[2]}")
+def test_gemm(ops, case):
+    M, N, K, use_bias, use_res, act, odt = case
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = _rand_bf16((M, K), g)
+    w = _rand_bf16((N, K), g, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=g) if use_bias else None
+    res = _rand_bf16((M, N), g) if use_res else None
+    ref = a.float() @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    if res is not None:
+        ref = ref + res.float()
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    out = ops.gemm(a.cuda(), w.cuda(), bias.cuda() if bias is not None else None,
+                   residual=res.cuda() if res is not None else None, act=act, out_dtype=odt)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs().max().item()
+    tol = 1.2e-2 * ref.abs().max().item()
+    assert err <= tol, f"max err {err} > {tol}"
+
+
+def test_gemm_bias_along_m_strided_out(ops):
+    g = torch.Generator().manual_seed(5)
+    for L in (16, 20, 252, 256):
+        a = _rand_bf16((768, 256), g, 0.06)           # W_v
+        x = _rand_bf16((L, 256), g)                   # image tokens
+        bias = torch.randn(768, generator=g)
+        Lp = (L + 7) // 8 * 8
+        out = torch.zeros((768, Lp), dtype=torch.bfloat16, device="cuda")
+        ops.gemm(a.cuda(), x.cuda(), bias.cuda(), bias_along_m=True, out=out[:, :L])
+        torch.cuda.synchronize()
+        ref = a.float() @ x.float().t() + bias[:, None]
+        assert (out[:, :L].float().cpu() - ref).abs().max() <= 1.2e-2 * ref.abs().max()
+        assert out[:, L:].abs().max().item() == 0 if Lp > L else True
+
+
+def test_gemm_split_k_atomic(ops):
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 256, 256, 8192
+    a = _rand_bf16((M, K), g)
+    w = _rand_bf16((N, K), g, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=g)
+    acc = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    ops.init_rows_f32(acc, bias.cuda())
+    ops.gemm(a.cuda(), w.cuda(), out=acc, atomic=True, k_splits=37)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    assert (acc.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max()
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from openpsg_b200._lib import OpsgError
+    a = torch.zeros((8, 12), dtype=torch.bfloat16, device="cuda")     # K=12 -> lda not multiple of 8
+    w = torch.zeros((8, 12), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(OpsgError):
+        ops.gemm(a, w)
+
+
+# ----------------------------------------------------------------------------------------------
+# K2: bit-exact masks
+# ----------------------------------------------------------------------------------------------
+def _mask_case(inputs):
+    meta, info = inputs["img_metas"][0], inputs["object_info"][0]
+    ids = [int(i) for i in info["object_id_list"]]
+    fh, fw = inputs["mask_features"].shape[-2:]
+    ref = restated.object_token_masks(info["pan_results"].numpy(), meta["img_shape"][:2], meta["pad_shape"][:2],
+                                      (fh, fw), 16, ids)
+    return info["pan_results"], meta, ids, (fh // 16, fw // 16), ref
+
+
+@pytest.mark.parametrize("name", ["cfg1", "stress", "cfg2"])
+def test_pair_mask_bits_bit_exact(ops, name):
+    inputs = synth.make_stress_inputs() if name == "stress" else synth.make_image_inputs(synth.WORKLOADS[name], 0)
+    pan, meta, ids, tok, ref = _mask_case(inputs)
+    bits = ops.pair_mask_bits(pan.to(torch.int32).cuda(), meta["img_shape"][:2], meta["pad_shape"][:2], tok,
+                              torch.tensor(ids, dtype=torch.int32).cuda())
+    got = bits.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, restated.pack_mask_bits(ref))
+
+
+def test_pair_mask_bits_ragged_shapes(ops):
+    rs = np.random.RandomState(0)
+    for (ph, pw, ih, iw, Hp, Wp) in [(480, 640, 800, 1067, 800, 1088), (427, 640, 800, 1199, 800, 1216),
+                                     (100, 37, 333, 500, 352, 512), (64, 64, 64, 64, 64, 64)]:
+        pan = rs.randint(0, 7, size=(ph, pw)).astype(np.int32)
+        ids = [0, 1, 2, 3, 4, 5, 6, 1005]
+        fh, fw = Hp // 4, Wp // 4
+        ref = restated.object_token_masks(pan, (ih, iw), (Hp, Wp), (fh, fw), 16, ids)
+        bits = ops.pair_mask_bits(torch.from_numpy(pan).cuda(), (ih, iw), (Hp, Wp), (fh // 16, fw // 16),
+                                  torch.tensor(ids, dtype=torch.int32).cuda())
+        assert np.array_equal(bits.cpu().numpy().view(np.uint32), restated.pack_mask_bits(ref))
+
+
+# ----------------------------------------------------------------------------------------------
+# K1 operand / K7 / LayerNorm
+# ----------------------------------------------------------------------------------------------
+def test_patch_im2col_exact(ops):
+    g = torch.Generator().manual_seed(1)
+    feat = torch.randn(8, 40, 72, generator=g)       # h=40 -> 2 token rows (floor), w=72 -> 4 token cols
+    out = ops.patch_im2col(feat.cuda(), 16).float().cpu()
+    x = feat[:, :32, :64].reshape(8, 2, 16, 4, 16).permute(1, 3, 0, 2, 4).reshape(8, 8 * 256)
+    assert torch.equal(out, x.to(torch.bfloat16).float())
+
+
+def test_qformer_embed_ln(ops):
+    g = torch.Generator().manual_seed(2)
+    d, nq, B, T, V = 768, 33, 5, 16, 1000
+    query = torch.randn(nq, d, generator=g)
+    word = torch.randn(V, d, generator=g) * 0.02
+    pos = torch.randn(512, d, generator=g) * 0.02
+    gamma = 1 + 0.1 * torch.randn(d, generator=g)
+    beta = 0.02 * torch.randn(d, generator=g)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    out = ops.qformer_embed_ln(query.cuda(), ids.to(torch.int32).cuda(), word.cuda(), pos.cuda(), gamma.cuda(),
+                               beta.cuda(), 1e-12).float().cpu()
+    ln = lambda x: torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-12)
+    ref_q = ln(query)[None].expand(B, -1, -1).reshape(B * nq, d)
+    ref_t = ln(word[ids] + pos[:T]).reshape(B * T, d)
+    ref = torch.cat([ref_q, ref_t])
+    assert (out - ref).abs().max() < 2.5e-2       # bf16 output rounding of O(4) values
+
+
+@pytest.mark.parametrize("cols", [768, 320, 2560])
+def test_layernorm(ops, cols):
+    g = torch.Generator().manual_seed(3)
+    x = _rand_bf16((333, cols), g, 2.0)
+    gamma = 1 + 0.1 * torch.randn(cols, generator=g)
+    beta = 0.1 * torch.randn(cols, generator=g)
+    out = ops.layernorm(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5).float().cpu()
+    ref = torch.nn.functional.layer_norm(x.float(), (cols,), gamma, beta, 1e-5)
+    assert (out - ref).abs().max() < 3e-2
+
+
+# ----------------------------------------------------------------------------------------------
+# K4: small self-attention (Q-Former split layout).  tol 2e-2 abs on O(1) outputs (bf16 P and output)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("text_queries", [True, False])
+def test_self_attn_small(ops, text_queries):
+    g = torch.Generator().manual_seed(4)
+    B, nq, T, H, hd = 7, 33, 16, 12, 64
+    d = H * hd
+    R = B * (nq + T)
+    qkv = _rand_bf16((R, 3 * d), g)
+    tmask = (torch.arange(T)[None, :] < torch.randint(10, T + 1, (B, 1), generator=g)).to(torch.int32)
+    out = ops.self_attn_small(qkv.cuda(), tmask.cuda(), B, nq, T, H, hd, text_queries).float().cpu()
+    f = qkv.float()
+    for p in range(B):
+        rows = list(range(p * nq, (p + 1) * nq)) + list(range(B * nq + p * T, B * nq + (p + 1) * T))
+        x = f[rows]
+        q, k, v = (x[:, i * d:(i + 1) * d].reshape(-1, H, hd).transpose(0, 1) for i in range(3))
+        valid = torch.cat([torch.ones(nq, dtype=torch.bool), tmask[p].bool()])
+        s = q @ k.transpose(-1, -2) / 8.0
+        s = s.masked_fill(~valid[None, None, :], float("-inf"))
+        ref = (torch.softmax(s, -1) @ v).transpose(0, 1).reshape(-1, d)
+        nrows = len(rows) if text_queries else nq
+        got = out[rows[:nrows]]
+        assert (got - ref[:nrows]).abs().max() < 2e-2
+
+
+# ----------------------------------------------------------------------------------------------
+# K5: pair x image masked cross-attention (tcgen05).  tol 2e-2 abs (bf16 P, bf16 output)
+# ----------------------------------------------------------------------------------------------
+def _xattn_ref(q, k, v, masks, N, pair_index, nq):
+    B = q.shape[0] // nq
+    H, hd = 12, 64
+    qh = q.float().reshape(B, nq, H, hd).permute(0, 2, 1, 3)
+    kh = k.float().reshape(-1, H, hd).permute(1, 0, 2)
+    vh = v.float().reshape(-1, H, hd).permute(1, 0, 2)
+    pi = pair_index if pair_index is not None else torch.arange(B)
+    M = masks[pi // N] | masks[pi % N]
+    bias = (1.0 - M.float()) * torch.finfo(torch.float32).min
+    s = qh @ kh.transpose(-1, -2) / 8.0 + bias[:, None, None, :]
+    o = torch.softmax(s, -1) @ vh
+    return o.permute(0, 2, 1, 3).reshape(B * nq, H * hd)
+
+
+@pytest.mark.parametrize("L,N,B", [(256, 40, 1600), (16, 8, 64), (20, 7, 49), (252, 5, 25), (256, 3, 9)])
+def test_xattn_pairs(ops, L, N, B):
+    g = torch.Generator().manual_seed(L * 100 + N)
+    nq, d = 33, 768
+    q = _rand_bf16((B * nq, d), g)
+    k = _rand_bf16((L, d), g)
+    v = _rand_bf16((L, d), g)
+    masks = torch.rand(N, L, generator=g) < 0.15
+    masks[N - 1] = False                                  # empty object -> pair (N-1, N-1) is all-masked
+    bits = torch.from_numpy(restated.pack_mask_bits(masks.numpy()).view(np.int32))
+    Lp = (L + 7) // 8 * 8
+    vt = torch.zeros((d, Lp), dtype=torch.bfloat16)
+    vt[:, :L] = v.t()
+    out = ops.xattn_pairs(q.cuda(), k.cuda(), vt.cuda(), bits.cuda(), N, B, nq, L, 12, 64).float().cpu()
+    ref = _xattn_ref(q, k, v, masks, N, None, nq)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-2, err
+    # all-masked pair attends uniformly: its context is the mean of V
+    last = out[(B - 1) * nq:(B - 1) * nq + 1]
+    assert (last - v.float().mean(0, keepdim=True)).abs().max() < 2e-2
+
+
+def test_xattn_pairs_with_pair_index(ops):
+    g = torch.Generator().manual_seed(77)
+    L, N, nq, d = 256, 12, 33, 768
+    idx = torch.tensor([5, 143, 0, 77, 12, 12, 100], dtype=torch.int32)
+    B = idx.numel()
+    q = _rand_bf16((B * nq, d), g)
+    k = _rand_bf16((L, d), g)
+    v = _rand_bf16((L, d), g)
+    masks = torch.rand(N, L, generator=g) < 0.1
+    bits = torch.from_numpy(restated.pack_mask_bits(masks.numpy()).view(np.int32))
+    out = ops.xattn_pairs(q.cuda(), k.cuda(), v.t().contiguous().cuda(), bits.cuda(), N, B, nq, L, 12, 64,
+                          pair_index=idx.cuda()).float().cpu()
+    ref = _xattn_ref(q, k, v, masks, N, idx.long(), nq)
+    assert (out - ref).abs().max() < 2e-2
+
+
+def test_xattn_rejects_long_context(ops):
+    from openpsg_b200._lib import OPSG_E_UNSUPPORTED, OpsgError
+    z = torch.zeros((33, 768), dtype=torch.bfloat16, device="cuda")
+    k = torch.zeros((300, 768), dtype=torch.bfloat16, device="cuda")
+    vt = torch.zeros((768, 304), dtype=torch.bfloat16, device="cuda")
+    bits = torch.zeros((1, 10), dtype=torch.int32, device="cuda")
+    with pytest.raises(OpsgError) as e:
+        ops.xattn_pairs(z, k, vt, bits, 1, 1, 33, 300, 12, 64)
+    assert e.value.code == OPSG_E_UNSUPPORTED
+
+
+# ----------------------------------------------------------------------------------------------
+# K8: existence filter: logits within 1e-4 of fp32; index set / mask bit-exact given the logits
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,k", [(64, 20), (1600, 20), (6400, 100), (49, 49)])
+def test_exist_filter_topk(ops, B, k):
+    g = torch.Generator().manual_seed(B)
+    d, nq = 768, 33
+    x = _rand_bf16((B * nq, d), g)
+    w = torch.randn(d, generator=g) * 0.04
+    b = torch.randn(1, generator=g) * 0.02
+    logits, probs, mask, top = ops.exist_filter_topk(x.cuda(), nq * d, B, d, w.cuda(), b.cuda(), 0.5, k)
+    torch.cuda.synchronize()
+    ref = restated.existence_logits(x.float()[::nq], w, b)
+    z = logits.cpu()
+    assert (z - ref).abs().max() < 1e-4
+    assert top.cpu().tolist() == restated.topk_pairs(z, k)            # bit-exact on identical filter inputs
+    assert np.array_equal(mask.cpu().numpy().astype(bool), restated.existence_mask(z))
+    assert (probs.cpu() - torch.sigmoid(z)).abs().max() < 1e-6
+
+
+def test_topk_ties_go_to_lower_index(ops):
+    d, nq, B = 768, 33, 300
+    x = torch.zeros((B * nq, d), dtype=torch.bfloat16)
+    x[::nq, 0] = torch.tensor([float(i % 3) for i in range(B)], dtype=torch.bfloat16)
+    w = torch.zeros(d)
+    w[0] = 1.0
+    _, _, _, top = ops.exist_filter_topk(x.cuda(), nq * d, B, d, w.cuda(), torch.zeros(1).cuda(), 0.5, 10)
+    assert top.cpu().tolist() == [2 + 3 * i for i in range(10)]
+
+
+# ----------------------------------------------------------------------------------------------
+# K11: mask mean-pool + pair gather (fp32 sums, different order: tol 1e-4 relative)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(256, 64, 64, 8), (256, 256, 256, 40), (16, 33, 47, 5)])
+def test_mask_pool_pairs(ops, shape):
+    C, h, w, N = shape
+    g = torch.Generator().manual_seed(C + h)
+    feat = torch.randn(C, h, w, generator=g)
+    wl = synth.Workload("t", h * 4, w * 4, N)
+    label = torch.randint(-1, N, (h, w), generator=g).to(torch.int32)
+    label[label == N - 1] = -1                            # last object owns nothing -> zero embedding
+    if h >= 64:                                           # coherent regions like a panoptic map
+        pan = synth.make_panoptic_map(h, w, N, g, ensure_token_coverage=False)
+        label = (pan % 1000).to(torch.int32)
+        label[label == N - 1] = -1
+    obj, pair = ops.mask_pool_pairs(feat.cuda(), label.cuda(), N)
+    masks = torch.stack([label == i for i in range(N)])
+    ref_obj, ref_pair = restated.mask_pool_pairs(feat, masks)
+    assert (obj.cpu() - ref_obj).abs().max() < 1e-4
+    assert (pair.cpu() - ref_pair).abs().max() < 1e-4
+    assert obj[N - 1].abs().max().item() == 0
+
+
+def test_argmax_and_gathers(ops):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(37, 50272, generator=g)
+    x[3, 100] = x[3, 40000] = 99.0
+    got = ops.argmax_rows(x.cuda()).cpu()
+    assert torch.equal(got.long(), x.argmax(1)) and got[3] == 100
+    src = _rand_bf16((50, 32 * 768), g)
+    idx = torch.tensor([4, 4, 49, 0], dtype=torch.int32)
+    assert torch.equal(ops.gather_rows(src.cuda(), 32 * 768, idx.cuda()).cpu(), src[idx.long()])

@@ -1,0 +1,125 @@
+"""GPU end-to-end parity of the relation-query path (a2-a8) against (i) the golden vectors produced by the
+unmodified reference head and (ii) the fp32 oracle, on identical seeded inputs.
+
+Tolerances (bf16 operands, fp32 accumulate / softmax / LayerNorm):
+  max|dO| <= 8e-2, mean|dO| <= 6e-3 on the Q-Former output (std 1), |dz| <= 3e-2 on existence logits,
+  index sets bit-exact outside the 2*tol margin band around the k-th logit / around 0."""
+import numpy as np
+import pytest
+import torch
+
+from openpsg_b200 import synth
+from oracle import restated
+from tests.helpers import build_product_head, margin_set_equal
+
+pytestmark = pytest.mark.gpu
+
+TOL_O_MAX, TOL_O_MEAN, TOL_Z = 8e-2, 6e-3, 3e-2
+
+
+@pytest.fixture(scope="module")
+def head():
+    return build_product_head(device="cuda:0")
+
+
+def _inputs(name):
+    if name == "stress":
+        return synth.make_stress_inputs()
+    return synth.make_image_inputs(synth.WORKLOADS[name], 0)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "stress", "cfg2"])
+def test_relation_queries_match_reference_golden(golden, head, name):
+    g = golden(name)
+    out_dict = head(synth.inputs_to(_inputs(name), "cuda:0"))
+    assert set(out_dict) == {"rel_pred", "rel_score"}
+    out = head.last_output
+    torch.cuda.synchronize()
+    keep = g["keep_pairs"]
+    B = out.logits.numel()
+    hidden = out.hidden.float().cpu().reshape(B, 33, 768)
+    # masks: bit-exact
+    L = g["pair_masks"].shape[1]
+    bits = out.mask_bits.cpu().numpy().view(np.uint32)
+    obj = ((bits[:, np.arange(L) // 32] >> (np.arange(L) % 32).astype(np.uint32)) & 1).astype(bool)
+    pm = restated.pair_masks(obj)
+    ref_pm = g["pair_masks"].numpy()
+    assert np.array_equal(pm[keep.numpy()] if name == "cfg2" else pm, ref_pm)
+    # image tokens
+    tok = out.image_tokens.float().cpu()
+    ref_tok = g["image_tokens"]
+    assert ((tok[::16] if name == "cfg2" else tok) - ref_tok).abs().max() < 4e-2
+    # Q-Former output rows
+    d = (hidden[keep] - g["qformer_out_keep"]).abs()
+    assert d.max() <= TOL_O_MAX, d.max()
+    assert d.mean() <= TOL_O_MEAN, d.mean()
+    # existence logits + filter
+    z = out.logits.cpu()
+    assert (z - g["exist_logits"]).abs().max() <= TOL_Z
+    ok, diff = margin_set_equal(out.topk.cpu().tolist(), g["exist_logits"], 20, TOL_Z)
+    assert ok, diff
+    zr = g["exist_logits"]
+    decided = zr.abs() > 2 * TOL_Z
+    assert torch.equal(out.exist_mask.cpu().bool()[decided], (zr > 0)[decided])
+    # given OUR logits the selection is bit-exact (index-stable)
+    assert out.topk.cpu().tolist() == restated.topk_pairs(z, 20)
+
+
+def test_relation_queries_match_oracle_intermediates(head):
+    """Stage-by-stage comparison with the fp32 restatement on the stress image (all pairs)."""
+    inputs = synth.make_stress_inputs()
+    sd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
+    meta, info = inputs["img_metas"][0], inputs["object_info"][0]
+    ids = [int(i) for i in info["object_id_list"]]
+    m = torch.from_numpy(restated.object_token_masks(info["pan_results"].numpy(), meta["img_shape"][:2],
+                                                     meta["pad_shape"][:2], inputs["mask_features"].shape[-2:], 16, ids))
+    tokens = restated.patch_embed(inputs["mask_features"], sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], 16)
+    from openpsg_b200.categories import object_categories
+    n = len(ids)
+    names = [object_categories[i % 1000] for i in ids]
+    enc = synth.SyntheticTokenizer("qformer")(
+        ['Is there a relation between {} and {}?'.format(names[p // n], names[p % n]) for p in range(n * n)])
+    query = torch.cat([sd["rel_cls_query"], sd["relation_query"]], dim=1)[0]
+    ref, inter = restated.qformer_forward(sd, query, enc["input_ids"], enc["attention_mask"], tokens, m,
+                                          return_intermediates=True)
+    gi = synth.inputs_to(inputs, "cuda:0")
+    eng = head._engine or head.repack("cuda:0")._engine
+    out = eng.forward(gi["mask_features"][0], gi["object_info"][0]["pan_results"].to(torch.int32),
+                      meta["img_shape"][:2], meta["pad_shape"][:2], torch.tensor(ids, dtype=torch.int32, device="cuda:0"),
+                      enc["input_ids"].to(torch.int32).cuda(), enc["attention_mask"].to(torch.int32).cuda(),
+                      keep_intermediates=True)
+    B, T = enc["input_ids"].shape
+
+    def split(x):   # oracle [B,S,768] -> product split layout
+        return torch.cat([x[:, :33].reshape(B * 33, -1), x[:, 33:].reshape(B * T, -1)])
+
+    got = {k: v.float().cpu() for k, v in out.intermediates.items()}
+    assert (got["embeddings"] - split(inter["embeddings"])).abs().max() < 3e-2
+    assert (got["l0.self"] - split(inter["l0.self"])).abs().max() < 5e-2
+    assert (got["l0.xattn_ctx"] - inter["l0.xattn_ctx"].reshape(B * 33, -1)).abs().max() < 3e-2
+    assert (got["l0.cross"] - inter["l0.cross"].reshape(B * 33, -1)).abs().max() < 6e-2
+    assert (got["l0.out"] - split(inter["l0.out"])).abs().max() < 8e-2
+    assert (got["l1.out"] - inter["l1.out"][:, :33].reshape(B * 33, -1)).abs().max() < TOL_O_MAX
+    # the all-masked pair (6,6): finite, uniform attention == mean of V
+    assert torch.isfinite(out.hidden.float()).all()
+
+
+def test_subset_of_pairs_equals_full_run(head):
+    """pair_index (sampled pairs, the reference's qformer_sampled_idxes) gives the same rows as the full run."""
+    inputs = synth.inputs_to(_inputs("cfg1"), "cuda:0")
+    head(inputs)
+    full = head.last_output.hidden.float().cpu().reshape(64, 33, 768)
+    eng = head._engine
+    idx = torch.tensor([3, 17, 17, 63, 0], dtype=torch.int32)
+    from openpsg_b200.categories import object_categories
+    ids = synth.object_ids(8)
+    names = [object_categories[i % 1000] for i in ids]
+    enc = synth.SyntheticTokenizer("qformer")(
+        ['Is there a relation between {} and {}?'.format(names[p // 8], names[p % 8]) for p in idx.tolist()])
+    meta = inputs["img_metas"][0]
+    out = eng.forward(inputs["mask_features"][0], inputs["object_info"][0]["pan_results"].to(torch.int32),
+                      meta["img_shape"][:2], meta["pad_shape"][:2], torch.tensor(ids, dtype=torch.int32, device="cuda:0"),
+                      enc["input_ids"].to(torch.int32).cuda(), enc["attention_mask"].to(torch.int32).cuda(),
+                      pair_index=idx.cuda(), topk=5)
+    sub = out.hidden.float().cpu().reshape(5, 33, 768)
+    assert (sub - full[idx.long()]).abs().max() < 2e-2     # same arithmetic, different tile packing
