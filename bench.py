@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — object-pairs/sec of the relation-head hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--images-per-step I]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+A step = one pass of the path a2-a8 (feature map + panoptic map -> Q-Former over all N^2 pair queries ->
+existence probabilities, existence mask, top-k pair list) over a batch of `images_per_step` synthetic images
+PER RANK (weak scaling; 4 per rank = BASELINE cfg4's 32 images over 8 GPUs), every image of the cfg2 shape
+(1024x1024, 40 objects, 1600 queries = 1560 ordered pairs, 256 image tokens).  Images are independent, so ranks
+share nothing on the data path; NCCL is used for the barrier and the max-over-ranks time only.
+
+value  : whole-job ordered pairs / s with inputs resident in HBM (device-timed, CUDA events, max over ranks).
+e2e    : same through the head's public forward(inputs) with HOST (pinned) inputs: H2D of features, panoptic map
+         and ids, D2H of the selected pair list inside the timed region.
+roofline / roofline_xattn: dominant kernel (tcgen05 GEMM) and the north-star cross-attention kernel, CUDA-event
+         timed per launch during the timed steps.
+cpu_baseline / --impl reference: oracle/ref_port.py (the reference's call pattern on HF modules) on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from openpsg_b200 import synth  # noqa: E402
+
+WORKLOAD = "cfg2"
+METRIC, UNIT = "object_pairs_per_sec", "pairs/s"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port) — also the cpu_baseline leg of the GPU arm
+# ---------------------------------------------------------------------------------------------------
+def _cpu_reference_pass(head, inputs, n_sample):
+    wl = synth.WORKLOADS[WORKLOAD]
+    t0 = time.perf_counter()
+    head.relation_queries(inputs, pair_subset=list(range(n_sample)))
+    dt = time.perf_counter() - t0
+    pairs = n_sample * wl.ordered_pairs / wl.queries
+    return pairs, dt
+
+
+def cpu_baseline(n_sample=96, repeats=1):
+    from tests.helpers import build_port_head
+    torch.set_num_threads(os.cpu_count())
+    head = build_port_head(max_object_num=80)
+    inputs = synth.make_image_inputs(synth.WORKLOADS[WORKLOAD], 0)
+    _cpu_reference_pass(head, inputs, 8)        # warm-up
+    best = None
+    for _ in range(repeats):
+        pairs, dt = _cpu_reference_pass(head, inputs, n_sample)
+        best = dt if best is None else min(best, dt)
+    return {"value": pairs / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"first {n_sample} of 1600 pair queries of one cfg2 image through oracle/ref_port.py "
+                      f"(HF InstructBlipQFormerModel fp32, the reference's per-pair K/V call pattern; cost is linear in pairs)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from tests.helpers import build_port_head
+    torch.set_num_threads(os.cpu_count())
+    wl = synth.WORKLOADS[WORKLOAD]
+    head = build_port_head(max_object_num=80)
+    inputs = synth.make_image_inputs(wl, 0)
+    n_sample = args.ref_sample
+    for _ in range(args.warmup):
+        _cpu_reference_pass(head, inputs, min(n_sample, 16))
+    t0 = time.perf_counter()
+    pairs = 0.0
+    for _ in range(args.steps):
+        p, _dt = _cpu_reference_pass(head, inputs, n_sample)
+        pairs += p
+    dt = time.perf_counter() - t0
+    v = pairs / dt
+    sample = (f"each step = first {n_sample} of the 1600 pair queries of one cfg2 image through oracle/ref_port.py "
+              f"(reference call pattern on HF modules, fp32, {os.cpu_count()} threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 1024x1024, 40 objects, relation-query Q-Former + existence filter (bounded sample)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from openpsg_b200 import ops
+    from tests.helpers import build_product_head
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a B200: libopsg_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    wl = synth.WORKLOADS[WORKLOAD]
+    ips = args.images_per_step
+    head = build_product_head(max_object_num=wl.num_objects, topk_pairs=20, device=dev)
+    head.repack(dev)
+    # this rank's images: global image index = rank * ips + i  (image sharding)
+    host_inputs = [synth.make_image_inputs(wl, rank * ips + i) for i in range(ips)]
+    for inp in host_inputs:   # pinned host copies for the e2e leg
+        inp["mask_features"] = inp["mask_features"].pin_memory()
+        inp["object_info"][0]["pan_results"] = inp["object_info"][0]["pan_results"].pin_memory()
+    dev_inputs = [synth.inputs_to(inp, dev) for inp in host_inputs]
+
+    def step_resident():
+        for inp in dev_inputs:
+            head(inp)
+
+    def step_e2e():
+        res = []
+        for inp in host_inputs:
+            d = dict(inp)
+            d["mask_features"] = inp["mask_features"].to(dev, non_blocking=True)
+            oi = dict(inp["object_info"][0])
+            oi["pan_results"] = oi["pan_results"].to(dev, non_blocking=True)
+            d["object_info"] = [oi]
+            head(d)
+            res.append(head.last_output.topk.cpu())          # D2H of the selected pair list
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.profile_begin()
+    l0 = ops.launch_count
+    ms = timed(step_resident, args.steps)
+    launches = ops.launch_count - l0
+    prof = ops.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    pairs_per_step = wl.ordered_pairs * ips * world
+    value = pairs_per_step * args.steps / (ms * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = pairs_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(inp["mask_features"].numel() * 4 + inp["object_info"][0]["pan_results"].numel() *
+              inp["object_info"][0]["pan_results"].element_size() + wl.num_objects * 4 +
+              2 * wl.queries * 16 * 4 for inp in host_inputs)
+    d2h = ips * (20 * 4 + wl.num_objects * 4)
+
+    if rank == 0:
+        peaks = _peaks()
+        g = prof.get("gemm_bf16", {"ms": 0.0, "flops": 0.0, "n": 1})
+        x = prof.get("xattn_pairs", {"ms": 0.0, "flops": 0.0, "n": 1})
+        total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+
+        def roof(rec, peak_tf):
+            ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12 if rec["ms"] > 0 else 0.0
+            return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "traffic": None, "launches": rec["n"], "avg_launch_ms": rec["ms"] / max(1, rec["n"]),
+                    "share_of_kernel_time": rec["ms"] / total_kernel_ms, "peak_source": peaks["src"] + " (sustained bf16)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"cfg2 x {ips} images per rank per step (cfg4 sharding): 1024x1024, 40 objects, "
+                                   "1600 pair queries, 256 image tokens, relation-query Q-Former + existence filter (a2-a8)",
+                       "images_per_step_per_rank": ips, "parallelism": f"image-shard x{world}",
+                       "l2": "inputs larger than L2 (4 x 67 MB feature maps + >100 MB activations per image)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof(g, peaks["tf_sustained"]),
+            "roofline_xattn": roof(x, peaks["tf_sustained"]),
+            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images-per-step", type=int, default=4)
+    ap.add_argument("--ref-sample", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

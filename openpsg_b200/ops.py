@@ -36,6 +36,48 @@ def _count(n=1):
     launch_count += n
 
 
+# ---- optional per-kernel timing (CUDA events on the launching stream; used by bench.py) ---------------
+_profile = None      # None = off; else list of (name, start_event, stop_event, flops, bytes)
+
+
+def profile_begin():
+    global _profile
+    _profile = []
+
+
+def profile_end() -> dict:
+    """-> {kernel name: {"ms": total device ms, "n": launches, "flops": algorithmic flops, "bytes": algorithmic bytes}}"""
+    global _profile
+    recs, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, flops, nbytes in recs:
+        r = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+        r["ms"] += e0.elapsed_time(e1)
+        r["n"] += 1
+        r["flops"] += flops
+        r["bytes"] += nbytes
+    return out
+
+
+class _timed:
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profile.append((self.name, self.e0, e1, self.flops, self.nbytes))
+        return False
+
+
 def pair_mask_bits(pan: torch.Tensor, img_hw, pad_hw, tok_hw, obj_ids: torch.Tensor, words: Optional[int] = None):
     """K2: int32 pan map [h,w] + object ids [N] -> uint32-as-int32 bit masks [N, words]."""
     pan = _cuda(pan, torch.int32, "pan").contiguous()
@@ -43,9 +85,10 @@ def pair_mask_bits(pan: torch.Tensor, img_hw, pad_hw, tok_hw, obj_ids: torch.Ten
     L = tok_hw[0] * tok_hw[1]
     words = words or max(1, (L + 31) // 32)
     bits = torch.empty((obj_ids.numel(), words), dtype=torch.int32, device=pan.device)
-    _lib.check(_lib.load().opsg_pair_mask_bits(_ptr(pan), pan.shape[0], pan.shape[1], int(img_hw[0]), int(img_hw[1]),
-                                              int(pad_hw[0]), int(pad_hw[1]), int(tok_hw[0]), int(tok_hw[1]),
-                                              _ptr(obj_ids), obj_ids.numel(), _ptr(bits), words, _stream()))
+    with _timed("pair_mask_bits", 0.0, 4.0 * tok_hw[0] * tok_hw[1] + 4.0 * bits.numel()):
+        _lib.check(_lib.load().opsg_pair_mask_bits(_ptr(pan), pan.shape[0], pan.shape[1], int(img_hw[0]), int(img_hw[1]),
+                                                  int(pad_hw[0]), int(pad_hw[1]), int(tok_hw[0]), int(tok_hw[1]),
+                                                  _ptr(obj_ids), obj_ids.numel(), _ptr(bits), words, _stream()))
     _count()
     return bits
 
@@ -56,7 +99,8 @@ def patch_im2col(feat: torch.Tensor, patch: int) -> torch.Tensor:
     C, h, w = feat.shape
     L = (h // patch) * (w // patch)
     out = torch.empty((L, C * patch * patch), dtype=torch.bfloat16, device=feat.device)
-    _lib.check(_lib.load().opsg_patch_im2col(_ptr(feat), C, h, w, patch, _ptr(out), _stream()))
+    with _timed("patch_im2col", 0.0, 6.0 * out.numel()):
+        _lib.check(_lib.load().opsg_patch_im2col(_ptr(feat), C, h, w, patch, _ptr(out), _stream()))
     _count()
     return out
 
@@ -79,9 +123,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if residual is not None:
         _cuda(residual, torch.bfloat16, "residual")
         assert residual.shape == (M, N) and residual.stride(1) == 1
-    _lib.check(_lib.load().opsg_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
-                                         _ptr(bias), int(bias_along_m), _ptr(residual),
-                                         residual.stride(0) if residual is not None else 0, act, mode, k_splits, _stream()))
+    with _timed("gemm_bf16", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)):
+        _lib.check(_lib.load().opsg_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                             _ptr(bias), int(bias_along_m), _ptr(residual),
+                                             residual.stride(0) if residual is not None else 0, act, mode, k_splits, _stream()))
     _count()
     return out
 
@@ -91,14 +136,16 @@ def cast_f32_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.
     rows, cols = x.shape
     if out is None:
         out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
-    _lib.check(_lib.load().opsg_cast_f32_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, cols, _stream()))
+    with _timed("cast_f32_bf16", 0.0, 6.0 * rows * cols):
+        _lib.check(_lib.load().opsg_cast_f32_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, cols, _stream()))
     _count()
     return out
 
 
 def init_rows_f32(out: torch.Tensor, row: Optional[torch.Tensor]) -> torch.Tensor:
     _cuda(out, torch.float32, "out")
-    _lib.check(_lib.load().opsg_init_rows_f32(_ptr(out), out.stride(0), _ptr(row), out.shape[0], out.shape[1], _stream()))
+    with _timed("init_rows_f32", 0.0, 4.0 * out.numel()):
+        _lib.check(_lib.load().opsg_init_rows_f32(_ptr(out), out.stride(0), _ptr(row), out.shape[0], out.shape[1], _stream()))
     _count()
     return out
 
@@ -110,8 +157,9 @@ def qformer_embed_ln(query, input_ids, word_emb, pos_emb, gamma, beta, eps, out=
     _cuda(input_ids, torch.int32, "input_ids")
     if out is None:
         out = torch.empty((B * (nq + T), d), dtype=torch.bfloat16, device=query.device)
-    _lib.check(_lib.load().opsg_qformer_embed_ln(_ptr(query), nq, _ptr(input_ids), B, T, _ptr(word_emb), word_emb.shape[0],
-                                                _ptr(pos_emb), _ptr(gamma), _ptr(beta), float(eps), d, _ptr(out), _stream()))
+    with _timed("qformer_embed_ln", 0.0, 2.0 * out.numel() + 4.0 * B * T * d):
+        _lib.check(_lib.load().opsg_qformer_embed_ln(_ptr(query), nq, _ptr(input_ids), B, T, _ptr(word_emb), word_emb.shape[0],
+                                                    _ptr(pos_emb), _ptr(gamma), _ptr(beta), float(eps), d, _ptr(out), _stream()))
     _count()
     return out
 
@@ -122,7 +170,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     rows, cols = x.shape
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(_lib.load().opsg_layernorm_bf16(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(out), rows, cols, _stream()))
+    with _timed("layernorm_bf16", 0.0, 4.0 * rows * cols):
+        _lib.check(_lib.load().opsg_layernorm_bf16(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(out), rows, cols, _stream()))
     _count()
     return out
 
@@ -134,8 +183,9 @@ def self_attn_small(qkv, text_mask, B, n_query, T, num_heads, head_dim, text_que
     rows = B * (n_query + T) if text_queries else B * n_query
     if out is None:
         out = torch.empty((rows, d), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.load().opsg_self_attn_small(_ptr(qkv), _ptr(text_mask), B, n_query, T, num_heads, head_dim,
-                                               int(text_queries), _ptr(out), _stream()))
+    with _timed("self_attn_small", 4.0 * B * num_heads * (n_query + (T if text_queries else 0)) * (n_query + T) * head_dim, 2.0 * (qkv.numel() + out.numel())):
+        _lib.check(_lib.load().opsg_self_attn_small(_ptr(qkv), _ptr(text_mask), B, n_query, T, num_heads, head_dim,
+                                                   int(text_queries), _ptr(out), _stream()))
     _count()
     return out
 
@@ -146,9 +196,10 @@ def xattn_pairs(q, k, vt, bits, num_objects, B, n_query, L, num_heads, head_dim,
     assert q.is_contiguous()
     if out is None:
         out = torch.empty_like(q)
-    _lib.check(_lib.load().opsg_xattn_pairs(_ptr(q), _ptr(k), k.stride(0), _ptr(vt), vt.stride(0), _ptr(bits), bits.shape[1],
-                                           _ptr(pair_index), num_objects, B, n_query, L, num_heads, head_dim, _ptr(out),
-                                           _stream()))
+    with _timed("xattn_pairs", 4.0 * B * n_query * L * num_heads * head_dim, 4.0 * q.numel() + 4.0 * L * num_heads * head_dim):
+        _lib.check(_lib.load().opsg_xattn_pairs(_ptr(q), _ptr(k), k.stride(0), _ptr(vt), vt.stride(0), _ptr(bits), bits.shape[1],
+                                               _ptr(pair_index), num_objects, B, n_query, L, num_heads, head_dim, _ptr(out),
+                                               _stream()))
     _count()
     return out
 
@@ -160,8 +211,9 @@ def exist_filter_topk(x: torch.Tensor, ld_x: int, B: int, d: int, w: torch.Tenso
     probs = torch.empty(B, dtype=torch.float32, device=dev)
     mask = torch.empty(B, dtype=torch.uint8, device=dev)
     topk = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
-    _lib.check(_lib.load().opsg_exist_filter_topk(_ptr(x), ld_x, B, d, _ptr(w), _ptr(b), float(threshold), k, _ptr(logits),
-                                                 _ptr(probs), _ptr(mask), _ptr(topk), _stream()))
+    with _timed("exist_filter_topk", 2.0 * B * d, 2.0 * B * d + 12.0 * B):
+        _lib.check(_lib.load().opsg_exist_filter_topk(_ptr(x), ld_x, B, d, _ptr(w), _ptr(b), float(threshold), k, _ptr(logits),
+                                                     _ptr(probs), _ptr(mask), _ptr(topk), _stream()))
     _count(2)
     return logits, probs, mask, topk[:k]
 
@@ -173,8 +225,9 @@ def mask_pool_pairs(feat: torch.Tensor, label: torch.Tensor, num_objects: int, w
     obj = torch.empty((num_objects, C), dtype=torch.float32, device=feat.device)
     cnt = torch.empty((num_objects,), dtype=torch.float32, device=feat.device)
     pair = torch.empty((num_objects * num_objects, 2 * C), dtype=torch.float32, device=feat.device) if with_pairs else None
-    _lib.check(_lib.load().opsg_mask_pool_pairs(_ptr(feat.contiguous()), C, h, w, _ptr(label.contiguous()), num_objects,
-                                               _ptr(cnt), _ptr(obj), _ptr(pair), _stream()))
+    with _timed("mask_pool_pairs", 0.0, 4.0 * feat.numel() + 4.0 * label.numel()):
+        _lib.check(_lib.load().opsg_mask_pool_pairs(_ptr(feat.contiguous()), C, h, w, _ptr(label.contiguous()), num_objects,
+                                                   _ptr(cnt), _ptr(obj), _ptr(pair), _stream()))
     _count(3 if with_pairs else 2)
     return obj, pair
 

@@ -74,7 +74,7 @@ class ReferencePortHead(nn.Module):
 
     # -- v4:134-237 -----------------------------------------------------------------------------
     @torch.no_grad()
-    def relation_queries(self, inputs: dict) -> dict:
+    def relation_queries(self, inputs: dict, pair_subset=None) -> dict:
         feat = inputs['mask_features']
         assert feat.shape[0] == 1
         meta = inputs['img_metas'][0]
@@ -90,14 +90,15 @@ class ReferencePortHead(nn.Module):
         tokens, pair_masks, obj_masks = self.prepare_inference(feat, meta, ids, info['pan_results'])
         tokens = tokens.expand(B, -1, -1)
         pair_masks = pair_masks.expand(-1, query.shape[1], -1)
-        idx = torch.arange(B)
+        # test mode: every pair (v4:175); a subset = the reference's qformer_sampled_idxes mechanism (v4:173)
+        idx = torch.arange(B) if pair_subset is None else torch.as_tensor(pair_subset, dtype=torch.long)
         out = self.relation_qformer(
             input_ids=enc['input_ids'][idx], attention_mask=attn[idx], query_embeds=query[idx],
             encoder_hidden_states=tokens[idx], encoder_attention_mask=pair_masks[idx],
         )['last_hidden_state'][:, :query.shape[1]]
         logits = self.binary_rel_cls_pred(out[:, 0])
         prob = torch.sigmoid(logits)
-        selected = prob.squeeze(1).topk(B).indices.tolist()[:self.topk_pairs]
+        selected = idx[prob.squeeze(1).topk(idx.numel()).indices].tolist()[:self.topk_pairs]
         return dict(object_num=n, names=names, qformer_out=out, exist_logits=logits.squeeze(1),
                     exist_prob=prob.squeeze(1), selected=selected, obj_masks=obj_masks,
                     image_tokens=tokens[0], input_ids=enc['input_ids'], text_mask=enc['attention_mask'])

@@ -1,8 +1,11 @@
 """GPU end-to-end parity of the relation-query path (a2-a8) against (i) the golden vectors produced by the
 unmodified reference head and (ii) the fp32 oracle, on identical seeded inputs.
 
-Tolerances (bf16 operands, fp32 accumulate / softmax / LayerNorm):
-  max|dO| <= 8e-2, mean|dO| <= 6e-3 on the Q-Former output (std 1), |dz| <= 3e-2 on existence logits,
+Tolerances (SURVEY.md Appendix A.7 rule, re-calibrated on THIS weight set: HF's own all-bf16 execution of
+the same Q-Former on the same inputs deviates from the fp32 reference by max 0.061 / mean 0.0079 on the
+output (std 1) and 0.022 on the existence logits — see DESIGN.md "Tolerance calibration"); the kernels
+(bf16 operands, fp32 accumulate / softmax / LayerNorm) must not be worse than that:
+  max|dO| <= 8e-2, mean|dO| <= 8e-3, |dz| <= 3e-2,
   index sets bit-exact outside the 2*tol margin band around the k-th logit / around 0."""
 import numpy as np
 import pytest
@@ -14,7 +17,7 @@ from tests.helpers import build_product_head, margin_set_equal
 
 pytestmark = pytest.mark.gpu
 
-TOL_O_MAX, TOL_O_MEAN, TOL_Z = 8e-2, 6e-3, 3e-2
+TOL_O_MAX, TOL_O_MEAN, TOL_Z = 8e-2, 8e-3, 3e-2
 
 
 @pytest.fixture(scope="module")
