@@ -1,13 +1,21 @@
 // K3/K6/K9/K10c — D = act(A . W^T + bias + residual), bf16 operands, fp32 accumulation in TMEM.
 //
-// Persistent warp-specialised tcgen05 kernel (one CTA per SM, cta_group::1):
+// Persistent warp-specialised tcgen05 kernel (one CTA per SM, cta_group::1, 384 threads):
 //   warp 0 (1 thread)  TMA producer : A tile [128 x 64] + W tile [BN x 64] per stage, 128B swizzle
 //   warp 1 (1 thread)  MMA issuer   : 4 x tcgen05.mma 128 x BN x 16 per stage, accumulator in TMEM
 //   warp 2             TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4-7          epilogue     : tcgen05.ld 32x32b (thread = row), bias/residual/act, 16B stores
-// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static tile
-// scheduler (tile = blockIdx.x + i * gridDim.x, N fastest so the CTAs resident at one time share A tiles
-// through L2).  Out-of-bounds rows/cols/K are zero-filled by TMA and predicated away in the epilogue.
+//   warps 4-11         epilogue     : warp = (TMEM lane quarter, 32-column half of a 64-column slab);
+//                                     tcgen05.ld 32x32b (thread = row), bias / residual / activation in
+//                                     registers, bf16 pack -> 128B-swizzled staging slab in shared memory ->
+//                                     one TMA store per [128 x 64] slab (double-buffered, bulk async groups).
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static tile scheduler
+// (tile = blockIdx.x + i * gridDim.x, N fastest so the CTAs resident at one time share A tiles through L2).
+// Out-of-bounds rows/cols/K are zero-filled by TMA on load and clipped by TMA on store.
+// fp32 / atomic outputs, unaligned D and BN = 32 tiles use predicated direct stores instead of the TMA store.
+//
+// Round-1 ncu finding that shaped this epilogue (profiles/r1_ncu_gemm_a.md): with 4 epilogue warps storing
+// 16-byte pieces of 32 different rows per instruction, K = 768 GEMMs ran at 20-28 % tensor-pipe activity
+// (epilogue-bound) while K = 3072 reached 60-66 %.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -15,7 +23,9 @@ namespace opsg {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kSlabBytes = kBM * 128;   // [128 rows x 64 bf16] staging slab
 
 struct GemmParams {
   void* D;
@@ -28,6 +38,7 @@ struct GemmParams {
   int out_mode;
   int k_splits;
   int m_tiles, n_tiles;
+  int tma_store;
 };
 
 template <int BN, int STAGES>
@@ -35,19 +46,22 @@ struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = (BN >= 64) ? 2 * kSlabBytes : 0;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // +1024 for manual alignment
+  static constexpr int kTotal = STAGES * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024: manual alignment
 };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   using S = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * S::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
+  uint8_t* staging = smem + STAGES * S::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::kStagingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -60,13 +74,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmD);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], kEpiThreads);
     }
     mbar_fence_init();
   }
@@ -134,67 +149,139 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    constexpr int SLABW = (BN >= 64) ? 64 : BN;        // columns per slab
+    constexpr int NSLAB = BN / SLABW;
+    const int ew = warp - 4;
+    const int q = ew & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = ew >> 2;               // which 32 columns of the slab
+    const bool has_cols = half * 32 < SLABW;
     const int row_in_tile = q * 32 + lane;
+    const bool elected = (threadIdx.x == 4 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t buf = 0;
+    const __nv_bfloat16* resid = p.residual;
+
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_t = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
       const int m_t = rest % p.m_tiles;
       const int split = rest / p.m_tiles;
       const bool has_k = split * kb_per_split < kb_total;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int row = m_t * kBM + row_in_tile;
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       const float bias_m = (p.bias && p.bias_along_m && row_ok) ? p.bias[row] : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n_t * BN + c * 32;
-        if (row_ok && col0 < p.N && has_k) {
-          float f[32];
+
+      // residual prefetch (registers) for slab s: this thread's 32 columns of its own row.  Rows / columns that
+      // cannot use 16-byte loads (ragged N, unaligned views) are read element-wise at add time instead.
+      uint4 rres[4];
+      bool rfast = false;
+      auto fetch_residual = [&](int slab) {
+        const int c0 = n_t * BN + slab * SLABW + half * 32;
+        rfast = false;
+        if (!resid || !row_ok || !has_cols || c0 + 32 > p.N) return;
+        const __nv_bfloat16* r = resid + static_cast<size_t>(row) * p.ldr + c0;
+        if ((reinterpret_cast<uintptr_t>(r) & 15) != 0) return;
+        rfast = true;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          const bool full = (col0 + 32 <= p.N);
+        for (int j = 0; j < 4; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(r) + j);
+      };
+      fetch_residual(0);
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+#pragma unroll 1
+      for (int slab = 0; slab < NSLAB; ++slab) {
+        const int col0 = n_t * BN + slab * SLABW + half * 32;
+        float f[32];
+        if (has_cols) {
+          uint32_t v[32];
+          tmem_ld32(taddr + slab * SLABW + half * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = has_k ? __uint_as_float(v[j]) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        }
+        if (slab == NSLAB - 1) {            // accumulator fully read -> hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        const bool col_ok = has_cols && col0 < p.N;
+        const bool full = col0 + 32 <= p.N;
+        if (col_ok) {
           if (p.bias) {
             if (p.bias_along_m) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] += bias_m;
-            } else {
+            } else if (full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-            }
-          }
-          if (p.residual) {
-            const __nv_bfloat16* r = p.residual + static_cast<size_t>(row) * p.ldr + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(r) + j);
-                f[j * 8 + 0] += bf16_lo(u.x); f[j * 8 + 1] += bf16_hi(u.x);
-                f[j * 8 + 2] += bf16_lo(u.y); f[j * 8 + 3] += bf16_hi(u.y);
-                f[j * 8 + 4] += bf16_lo(u.z); f[j * 8 + 5] += bf16_hi(u.z);
-                f[j * 8 + 6] += bf16_lo(u.w); f[j * 8 + 7] += bf16_hi(u.w);
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                f[j * 4 + 0] += b4.x; f[j * 4 + 1] += b4.y; f[j * 4 + 2] += b4.z; f[j * 4 + 3] += b4.w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) f[j] += __bfloat162float(r[j]);
+                if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
             }
           }
+          if (resid && !rfast && row_ok) {
+            const __nv_bfloat16* r = resid + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += __bfloat162float(r[j]);
+          }
+          if (rfast) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[j * 8 + 0] += bf16_lo(rres[j].x); f[j * 8 + 1] += bf16_hi(rres[j].x);
+              f[j * 8 + 2] += bf16_lo(rres[j].y); f[j * 8 + 3] += bf16_hi(rres[j].y);
+              f[j * 8 + 4] += bf16_lo(rres[j].z); f[j * 8 + 5] += bf16_hi(rres[j].z);
+              f[j * 8 + 6] += bf16_lo(rres[j].w); f[j * 8 + 7] += bf16_hi(rres[j].w);
+            }
+          }
+        }
+        if (slab + 1 < NSLAB) fetch_residual(slab + 1);
+        if (col_ok) {
           if (p.act == OPSG_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
           } else if (p.act == OPSG_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
+        }
+
+        if (p.tma_store) {
+          // staging slab `buf`: its previous TMA store (two slabs ago) must have drained before we overwrite it
+          if (elected) tma_store_wait_read<1>();
+          named_bar_sync(1, kEpiThreads);
+          if (has_cols) {
+            uint8_t* rowp = staging + buf * kSlabBytes + row_in_tile * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int chunk = (half * 4 + g) ^ (row_in_tile & 7);
+              uint4 u;
+              u.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+              u.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+              u.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+              u.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, kEpiThreads);
+          if (elected) {     // always commit (possibly empty) so that group counting stays one-per-slab
+            if (has_k && n_t * BN + slab * SLABW < p.N)
+              tma_store_2d(staging + buf * kSlabBytes, &tmD, n_t * BN + slab * SLABW, m_t * kBM);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        } else if (row_ok && col_ok && has_k) {
           if (p.out_mode == OPSG_OUT_BF16) {
             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
             if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
@@ -231,10 +318,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && elected) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -246,8 +332,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, GemmParams p,
+                       cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES>;
+  static_assert(S::kTotal <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
     int rc = check_cuda(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -255,11 +343,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     if (rc) return rc;
     configured = true;
   }
+  if (BN < 64) p.tma_store = 0;
   p.n_tiles = (p.N + BN - 1) / BN;
   p.m_tiles = (p.M + kBM - 1) / kBM;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = total < opsg_num_sms() ? total : opsg_num_sms();
-  gemm_bf16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmD, p);
   OPSG_CHECK_LAUNCH("gemm_bf16_kernel");
   return OPSG_OK;
 }
@@ -279,6 +368,7 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
   OPSG_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 elements (TMA)");
   OPSG_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm: A/W must be 16-byte aligned");
   OPSG_CHECK_ARG(out_mode >= OPSG_OUT_BF16 && out_mode <= OPSG_OUT_F32_ATOMIC, "gemm: bad out_mode");
+  OPSG_CHECK_ARG(act >= OPSG_ACT_NONE && act <= OPSG_ACT_RELU, "gemm: bad activation");
   OPSG_CHECK_ARG(k_splits >= 1, "gemm: k_splits must be >= 1");
   if (k_splits > 1)
     OPSG_CHECK_ARG(out_mode == OPSG_OUT_F32_ATOMIC && !bias && !residual && act == OPSG_ACT_NONE,
@@ -291,21 +381,28 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
   const int sms = opsg_num_sms();
   while (bn > 32 && (N <= bn / 2 || m_tiles * ((N + bn - 1) / bn) * k_splits < sms)) bn >>= 1;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD;
   rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, kBK);
   if (rc) return rc;
+  const int tma_store = (out_mode == OPSG_OUT_BF16 && bn >= 64 && (ldd % 8) == 0 && ((uintptr_t)D & 15) == 0) ? 1 : 0;
+  if (tma_store) {
+    rc = make_tmap_bf16_2d(&tmD, D, (uint64_t)M, (uint64_t)N, (uint64_t)ldd, kBM, 64);
+    if (rc) return rc;
+  } else {
+    tmD = tmA;   // unused by the kernel
+  }
 
   GemmParams p;
   p.D = D; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.ldr = ldr; p.bias_along_m = bias_along_m; p.act = act;
-  p.out_mode = out_mode; p.k_splits = k_splits; p.m_tiles = 0; p.n_tiles = 0;
+  p.out_mode = out_mode; p.k_splits = k_splits; p.m_tiles = 0; p.n_tiles = 0; p.tma_store = tma_store;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 256: return launch_gemm<256, 4>(tmA, tmB, p, st);
-    case 128: return launch_gemm<128, 6>(tmA, tmB, p, st);
-    case 64: return launch_gemm<64, 8>(tmA, tmB, p, st);
-    default: return launch_gemm<32, 8>(tmA, tmB, p, st);
+    case 256: return launch_gemm<256, 4>(tmA, tmB, tmD, p, st);
+    case 128: return launch_gemm<128, 6>(tmA, tmB, tmD, p, st);
+    case 64: return launch_gemm<64, 8>(tmA, tmB, tmD, p, st);
+    default: return launch_gemm<32, 8>(tmA, tmB, tmD, p, st);
   }
 }
