@@ -140,6 +140,15 @@ int opsg_gather_rows_bf16(const opsg_bf16* src, int row_elems, const int32_t* id
                           void* stream);
 int opsg_embed_gather(const opsg_bf16* table, int d, const int32_t* ids, const opsg_bf16* pos_table,
                       const int32_t* pos, int n_rows, opsg_bf16* out, int ld_out, void* stream);
+/* opsg_llm_build_prefix (v4:294-301 + HF OPT :56-70, :321-330): the embedded prompt of nseq selected pairs,
+ *   out[s, t, :] = (t < n_prefix ? proj[s*proj_rows_per_seq + proj_row0 + t, :] : table[ids[s, t - n_prefix], :])
+ *                  + pos_table[pos[s, t], :]      (pos_table may be NULL: no learned positions, e.g. RoPE models)
+ *   proj = language_projection applied to the gathered Q-Former rows (33 rows per pair, row 0 = cls row is skipped
+ *   with proj_row0 = 1, n_prefix = 32); ids int32 [nseq, T] left-padded prompt tokens; pos int32 [nseq, n_prefix+T];
+ *   out bf16 [nseq, n_prefix + T, d] contiguous. */
+int opsg_llm_build_prefix(const opsg_bf16* proj, int proj_rows_per_seq, int proj_row0, int n_prefix,
+                          const opsg_bf16* table, const int32_t* ids, int T, const opsg_bf16* pos_table,
+                          const int32_t* pos, int nseq, int d, opsg_bf16* out, void* stream);
 int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_cache, const opsg_bf16* v_cache, int max_ctx,
                   const uint8_t* key_mask, int nseq, int q_len, int q_pos0, int num_heads, int head_dim, float scale,
                   opsg_bf16* out, int ld_out, void* stream);

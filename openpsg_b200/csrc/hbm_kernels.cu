@@ -330,6 +330,31 @@ __global__ void embed_gather_kernel(const __nv_bfloat16* __restrict__ table, int
   *(reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * ld_out) + c) = u;
 }
 
+// a9: out[s, t] = (t < n_prefix ? proj[s * rows_per_seq + row0 + t] : table[ids[s, t - n_prefix]]) + pos_table[pos[s, t]]
+__global__ void llm_build_prefix_kernel(const __nv_bfloat16* __restrict__ proj, int rows_per_seq, int row0, int n_prefix,
+                                        const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ ids, int T,
+                                        const __nv_bfloat16* __restrict__ pos_table, const int32_t* __restrict__ pos,
+                                        int nseq, int d, __nv_bfloat16* __restrict__ out) {
+  const int vec = d / 8;
+  const int Tp = n_prefix + T;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(nseq) * Tp * vec) return;
+  const int c = static_cast<int>(idx % vec);
+  const long long r = idx / vec;
+  const int t = static_cast<int>(r % Tp), s = static_cast<int>(r / Tp);
+  const __nv_bfloat16* src = t < n_prefix ? proj + (static_cast<size_t>(s) * rows_per_seq + row0 + t) * d
+                                          : table + static_cast<size_t>(ids[static_cast<size_t>(s) * T + (t - n_prefix)]) * d;
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + c);
+  if (pos_table) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(pos_table + static_cast<size_t>(pos[r]) * d) + c);
+    u.x = pack_bf16x2(bf16_lo(u.x) + bf16_lo(q.x), bf16_hi(u.x) + bf16_hi(q.x));
+    u.y = pack_bf16x2(bf16_lo(u.y) + bf16_lo(q.y), bf16_hi(u.y) + bf16_hi(q.y));
+    u.z = pack_bf16x2(bf16_lo(u.z) + bf16_lo(q.z), bf16_hi(u.z) + bf16_hi(q.z));
+    u.w = pack_bf16x2(bf16_lo(u.w) + bf16_lo(q.w), bf16_hi(u.w) + bf16_hi(q.w));
+  }
+  *(reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * d) + c) = u;
+}
+
 __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
                                                           int32_t* __restrict__ out) {
   __shared__ float s_val[8];
@@ -512,6 +537,25 @@ extern "C" int opsg_embed_gather(const opsg_bf16* table, int d, const int32_t* i
       reinterpret_cast<const __nv_bfloat16*>(table), d, ids, reinterpret_cast<const __nv_bfloat16*>(pos_table), pos, n_rows,
       reinterpret_cast<__nv_bfloat16*>(out), ld_out);
   OPSG_CHECK_LAUNCH("embed_gather_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_llm_build_prefix(const opsg_bf16* proj, int proj_rows_per_seq, int proj_row0, int n_prefix,
+                                     const opsg_bf16* table, const int32_t* ids, int T, const opsg_bf16* pos_table,
+                                     const int32_t* pos, int nseq, int d, opsg_bf16* out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(out && nseq > 0 && d > 0 && d % 8 == 0 && n_prefix >= 0 && T >= 0 && n_prefix + T > 0,
+                 "llm_build_prefix: bad shape");
+  OPSG_CHECK_ARG((n_prefix == 0 || proj) && (T == 0 || (table && ids)), "llm_build_prefix: null pointer");
+  OPSG_CHECK_ARG(proj_row0 >= 0 && proj_row0 + n_prefix <= proj_rows_per_seq, "llm_build_prefix: prefix rows out of range");
+  OPSG_CHECK_ARG(!pos_table || pos, "llm_build_prefix: pos_table without pos");
+  const long long total = static_cast<long long>(nseq) * (n_prefix + T) * (d / 8);
+  llm_build_prefix_kernel<<<ceil_div(total, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(proj), proj_rows_per_seq, proj_row0, n_prefix,
+      reinterpret_cast<const __nv_bfloat16*>(table), ids, T, reinterpret_cast<const __nv_bfloat16*>(pos_table), pos, nseq, d,
+      reinterpret_cast<__nv_bfloat16*>(out));
+  OPSG_CHECK_LAUNCH("llm_build_prefix_kernel");
   return OPSG_OK;
 }
 

@@ -1,4 +1,5 @@
-// K5 — pair-query x image-feature masked cross-attention on tcgen05 tensor cores (the north-star kernel).
+// K5 (v1, kept as the A/B baseline of round 1: select with OPSG_XATTN_IMPL=1) — pair-query x image-feature masked
+// cross-attention on tcgen05 tensor cores.  Superseded by xattn_pairs.cu (v2).
 //
 // All pairs' query rows are stacked along M (row = pair * n_query + r); K and V are projected once per image
 // and shared by every pair, so per head the whole thing is  softmax(Q[M x 64] . K^T[64 x L] + mask(pair)) . V.
@@ -17,6 +18,7 @@
 #include "host_util.h"
 
 namespace opsg {
+namespace xa1 {
 
 constexpr int kXaThreads = 256;
 constexpr int kXaKeys = 256;       // max keys (one N=256 MMA)
@@ -281,11 +283,13 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+}  // namespace xa1
 }  // namespace opsg
 
 using namespace opsg;
+using namespace opsg::xa1;
 
-extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
+extern "C" int opsg_xattn_pairs_v1(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
                                 const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                                 int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream) {
   int rc = opsg_device_check();

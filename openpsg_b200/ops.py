@@ -251,6 +251,18 @@ def embed_gather(table, ids, out, pos_table=None, pos=None):
     return out
 
 
+def llm_build_prefix(proj, rows_per_seq, row0, n_prefix, table, ids, pos_table, pos, out):
+    """a9: out [nseq, n_prefix+T, d] = cat(proj rows, table[ids]) + pos_table[pos]."""
+    _cuda(proj, torch.bfloat16, "proj"); _cuda(table, torch.bfloat16, "table"); _cuda(ids, torch.int32, "ids")
+    nseq, T = ids.shape
+    d = table.shape[1]
+    assert out.is_contiguous() and out.shape == (nseq, n_prefix + T, d)
+    _lib.check(_lib.load().opsg_llm_build_prefix(_ptr(proj), rows_per_seq, row0, n_prefix, _ptr(table), _ptr(ids), T,
+                                                _ptr(pos_table), _ptr(pos), nseq, d, _ptr(out), _stream()))
+    _count()
+    return out
+
+
 def llm_attn(q, k_cache, v_cache, key_mask, nseq, q_len, q_pos0, num_heads, head_dim, scale, out):
     max_ctx = k_cache.shape[1]
     _lib.check(_lib.load().opsg_llm_attn(_ptr(q), q.stride(0), _ptr(k_cache), _ptr(v_cache), max_ctx, _ptr(key_mask), nseq,
