@@ -3,9 +3,11 @@ unmodified reference head and (ii) the fp32 oracle, on identical seeded inputs.
 
 Tolerances (SURVEY.md Appendix A.7 rule, re-calibrated on THIS weight set: HF's own all-bf16 execution of
 the same Q-Former on the same inputs deviates from the fp32 reference by max 0.061 / mean 0.0079 on the
-output (std 1) and 0.022 on the existence logits — see DESIGN.md "Tolerance calibration"); the kernels
-(bf16 operands, fp32 accumulate / softmax / LayerNorm) must not be worse than that:
-  max|dO| <= 8e-2, mean|dO| <= 8e-3, |dz| <= 3e-2,
+output (std 1) and, on the existence logits, by max 0.022 over cfg1's 64 pairs and max 0.046 / mean 0.0077 /
+p99 0.025 over cfg2's 1600 pairs — see DESIGN.md "Tolerance calibration"); the kernels (bf16 operands, fp32
+accumulate / softmax / LayerNorm) must not be worse than that:
+  max|dO| <= 8e-2, mean|dO| <= 8e-3, |dz| <= 3e-2 (<= 4e-2 over the 1600 pairs of cfg2: the max of 25x more
+  samples of the same error distribution), mean|dz| <= 1e-2,
   index sets bit-exact outside the 2*tol margin band around the k-th logit / around 0."""
 import numpy as np
 import pytest
@@ -58,7 +60,9 @@ def test_relation_queries_match_reference_golden(golden, head, name):
     assert d.mean() <= TOL_O_MEAN, d.mean()
     # existence logits + filter
     z = out.logits.cpu()
-    assert (z - g["exist_logits"]).abs().max() <= TOL_Z
+    dz = (z - g["exist_logits"]).abs()
+    assert dz.max() <= (4e-2 if name == "cfg2" else TOL_Z), dz.max()
+    assert dz.mean() <= 1e-2, dz.mean()
     ok, diff = margin_set_equal(out.topk.cpu().tolist(), g["exist_logits"], 20, TOL_Z)
     assert ok, diff
     zr = g["exist_logits"]
