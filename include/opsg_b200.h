@@ -106,10 +106,20 @@ int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_mask, int B, 
  * bits: uint32 [N, words] from opsg_pair_mask_bits; pair_index int32 [B] or NULL (p -> pair p);
  * pair p = (i, j) = (pair / N, pair % N) attends keys where bits[i] | bits[j]; masked keys get the
  * reference's finfo.min bias (weight exactly 0; an all-masked pair attends uniformly to all L keys).
- * ctx_out: bf16 [B*n_query, d].  Requires head_dim == 64, L <= 256. */
+ * ctx_out: bf16 [B*n_query, d].  Requires head_dim == 64, L <= 256.
+ *
+ * bias_tiles (optional, recommended): the pair masks pre-arranged as tensor-core operand tiles by
+ * opsg_xattn_bias_tiles() into a caller-provided buffer of opsg_xattn_bias_tiles_bytes(B, n_query) bytes.
+ * They depend only on (bits, pair_index, N, B, n_query, L) — one build per image serves every head of both
+ * Q-Former layers — and let the kernel apply the mask as an additive bias inside the QK^T MMA.  With
+ * bias_tiles == NULL the self-contained (slower) kernel that ORs the bit rows per score row is used. */
+size_t opsg_xattn_bias_tiles_bytes(int B, int n_query);
+int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
+                          int n_query, int L, void* tiles_out, void* stream);
 int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
                      const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
-                     int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream);
+                     int n_query, int L, int num_heads, int head_dim, const void* bias_tiles, opsg_bf16* ctx_out,
+                     void* stream);
 
 /* ---- a8 / K8: relation-existence filter -----------------------------------------------------------
  * Replaces v4:206-209 (Linear(768,1) + sigmoid on out[:,0]) and v4:236-237 (topk(B).indices[:k]).

@@ -1,65 +1,108 @@
-// K5 (v2) — pair-query x image-feature masked cross-attention on tcgen05 tensor cores (the north-star kernel).
+// K5 (v3) — pair-query x image-feature masked cross-attention on tcgen05 tensor cores (the north-star kernel).
 //
 // All pairs' query rows are stacked along M (row = pair * n_query + r); K and V are projected once per image
 // and shared by every pair, so per head the whole thing is  softmax(Q[M x 64] . K^T[64 x L] + mask(pair)) . V.
-// Work unit = (128-row tile, head); a persistent CTA walks a contiguous, head-major range of units (at most two
-// heads per CTA, each head's K [256 x 64] and V^T [80 x 256] stay resident in their own shared-memory set).
+// Work unit = (128-row tile, head); a persistent CTA walks a contiguous, head-major range of units with the
+// head's K [256 x 64] and [V^T | 1 | 0] [80 x 256] resident in shared memory.
 //
-// 384 threads:
-//   warp 0 (1 thread)  TMA producer : K / V^T once per head, Q tile per unit (2 stages)
-//   warp 1 (1 thread)  MMA issuer   : S_b = Q.K^T    (128 x 256 x 64, SS, 4 MMAs)   -> TMEM cols [256b, 256b+256)
-//                                     O_b = P_b.[V|1] (128 x 80 x 256, TS, 16 MMAs)  -> TMEM cols [256b+128, 256b+208)
-//   warp 2             TMEM allocator (512 columns = two S buffers)
-//   warps 4-7 / 8-11   softmax warpgroup 0 / 1: units alternate between the two warpgroups and the two TMEM
-//                      buffers, so the MMAs of unit i+1 overlap the softmax of unit i.  Thread = score row:
-//                      row max over the pair's keys (mask = bits[i] | bits[j], never materialised in HBM),
-//                      p = exp2(s*scale - max), P written back IN PLACE over S as packed bf16 (tcgen05.st; it is
-//                      the A operand of the PV MMA straight from TMEM), row sum produced by the MMA itself through a
-//                      ones row appended to V^T, O/rowsum -> bf16 -> 128B-swizzled smem -> one TMA store per unit.
-// Mask semantics follow HF's `(1 - m) * finfo.min` additive bias: masked keys get weight exactly 0 and a pair
-// whose union mask is empty attends uniformly to all L keys.
+// 640 threads:
+//   warp 0 (1 thread)  TMA producer : K / V^T on a head change, Q tile per unit (2 stages)
+//   warp 1 (1 thread)  MMA issuer   : S_b  = Q.K^T + A_aug.B_aug^T   (128 x 256 x (64+16), SS, 5 MMAs)
+//                                     O_b  = P_b.[V|1]               (128 x 80 x 256, TS, 16 MMAs)
+//   warp 2             TMEM allocator (512 columns = two 256-column buffers)
+//   warp 3             per-head mean of V (output of uniform-attention rows)
+//   The pair mask enters the scores as an additive bias computed BY THE MMA: a fifth k-step multiplies
+//   A_aug[r, t] = 1 for the tile-local pair slot t of row r with B_aug[key, t] = 0 if the key belongs to
+//   bits[i_t] | bits[j_t] else -16384 (bf16-exact; keys >= L get -16384 in every slot).  Both operand tiles are
+//   built once per image by xattn_bias_tiles_kernel (they depend on the masks and the pair order only, not on the
+//   head or the layer), stored in global memory in the MMA's no-swizzle core-matrix order and fetched with one
+//   bulk copy per unit next to the Q tile.
+//   warps 4-19         softmax: two warpgroups per TMEM buffer split the 256 keys (thread = row x 128 keys); units
+//                      alternate between the buffers, so the MMAs of unit i+1 run under the softmax of unit i.
+//                      Row max (halves exchanged through smem), p = exp2(s*scale - max) with no per-element mask
+//                      work, packed bf16 P written IN PLACE over the consumed scores (half 0 ascending into columns
+//                      [0,64), half 1 descending into [192,256)) and used as the TMEM A operand of the PV MMA; the
+//                      row sum comes out of that MMA through the ones row of [V^T | 1]; O (columns [64,144)) is
+//                      scaled, packed and leaves through a swizzled staging tile and one TMA store per unit.
+// Mask semantics follow HF's `(1 - m) * finfo.min` additive bias: masked keys get weight exactly 0
+// (exp2(-16384 * scale) underflows to +0) and a pair whose union mask is empty attends uniformly to all L keys
+// (those rows are written as the fp32 mean of V).
 //
-// Why this shape (profiles/r1_ncu_xattn_a.md): v1 ran one softmax warp per scheduler strictly serial with the
-// MMAs (9.7 % tensor-pipe activity, issue slots 28 % busy, 11.5 k cycles per unit for 1024 cycles of MMA work).
+// Shape history: profiles/r1_ncu_xattn_a.md (v1: 9.7 % tensor-pipe activity, serial softmax),
+// profiles/r1_ncu_xattn_h.md (v2: 20 %, ALU pipe 45 % busy with FSEL/FMNMX/R2P mask work, MUFU 38 %),
+// profiles/r1_ncu_xattn_i.md (v3 with an in-kernel mask-builder warp: 17.6 %, softmax warps starved by the builder).
 #include "common.cuh"
 #include "host_util.h"
 
 extern "C" int opsg_xattn_pairs_v1(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
                                    const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                                    int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream);
+extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
+                                   const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
+                                   int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream);
 
 namespace opsg {
 
-constexpr int kXaThreads = 384;
+constexpr int kXaThreads = 640;
 constexpr int kXaKeys = 256;       // max keys (one N=256 MMA)
 constexpr int kXaHd = 64;
 constexpr int kXaPvN = 80;         // PV MMA N: 64 value dims + 1 ones row (row sum) + 15 zero rows
+constexpr int kXaSlots = 8;        // tile-local pair slots carried by the mask k-step
 
 struct XattnParams {
-  const uint32_t* bits;
-  const int32_t* pair_index;
-  int words, num_objects, n_query, L, num_heads, d_model;
+  const uint8_t* tiles;      // [m_tiles][kXaTileBytes] A_aug | B_aug in core-matrix order (xattn_bias_tiles_kernel)
+  const uint8_t* row_flags;  // [m_tiles * 128] 1 = the row's pair has an empty union mask (uniform attention)
+  int L, num_heads, d_model;
   int rows;          // B * n_query
   int m_tiles;
   int total_units;
-  int flags;         // bit 0: row sum by FADD in registers instead of the ones row (debug / A-B)
+  int desc_swap;     // debug: swap LBO / SBO of the no-swizzle descriptors
   float scale_log2e;
 };
 
+constexpr int kXaAugA = 128 * 32;                       // 4096 : A_aug [128 rows x 16 slots] bf16
+constexpr int kXaAugB = kXaKeys * 32;                   // 8192 : B_aug [256 keys x 16 slots] bf16
+constexpr int kXaTileBytes = kXaAugA + kXaAugB;         // 12288 per 128-row tile
+
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices stored contiguously (128 B); lbo = byte distance
+// between the two core matrices of a K = 16 step, sbo = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 struct XaSmem {
-  static constexpr int kKSet = kXaKeys * 128;           // 32768: K [256 keys x 64] SW128 K-major
+  static constexpr int kK = kXaKeys * 128;              // 32768: K [256 keys x 64] SW128 K-major
   static constexpr int kVBlk = kXaPvN * 128;            // 10240: one 64-key block of [V^T | 1 | 0] (80 rows x 128 B)
   static constexpr int kVBox = 64 * 128;                // 8192 : bytes TMA writes into a block (rows 0-63)
-  static constexpr int kVSet = 4 * kVBlk;               // 40960
+  static constexpr int kV = 4 * kVBlk;                  // 40960
   static constexpr int kQ = 128 * 128;                  // 16384 per stage
-  static constexpr int kOst = 128 * 128;                // 16384 per warpgroup: O staging for the TMA store
+  static constexpr int kOst = 128 * 128;                // 16384 per TMEM buffer: O staging for the TMA store
+  static constexpr int kAug = 12288;                    // per stage: A_aug (4096) | B_aug (8192), core-matrix order
+  static constexpr int kMax = 2 * 2 * 128 * 4;          // 2048 : partial row maxima [buffer][half][row]
+  static constexpr int kVbar = 2 * 64 * 4;              // 512  : mean of V per head parity
   static constexpr int kOffK = 0;
-  static constexpr int kOffV = kOffK + 2 * kKSet;       // 65536
-  static constexpr int kOffQ = kOffV + 2 * kVSet;       // 147456
-  static constexpr int kOffO = kOffQ + 2 * kQ;          // 180224
-  static constexpr int kOffBar = kOffO + 2 * kOst;      // 212992
+  static constexpr int kOffV = kOffK + kK;
+  static constexpr int kOffQ = kOffV + kV;
+  static constexpr int kOffO = kOffQ + 2 * kQ;
+  static constexpr int kOffAug = kOffO + 2 * kOst;
+  static constexpr int kOffMax = kOffAug + 2 * kAug;
+  static constexpr int kOffVbar = kOffMax + kMax;
+  static constexpr int kOffBar = kOffVbar + kVbar;
   static constexpr int kTotal = kOffBar + 256 + 1024;
 };
+static_assert(XaSmem::kOffV % 1024 == 0 && XaSmem::kOffQ % 1024 == 0 && XaSmem::kOffO % 1024 == 0 &&
+              XaSmem::kOffAug % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 static_assert(XaSmem::kTotal <= 232448, "shared memory budget exceeded");
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -83,6 +126,75 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   return v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mask-bias operand tiles, once per image (shared by all heads and both layers).
+// Tile t (128 stacked query rows) -> 12288 bytes in the no-swizzle K-major core-matrix order the MMA reads:
+//   A_aug: 16 row groups x [k-core 0: 8 rows x 16 B (slots 0-7) | k-core 1: 128 B of zeros]
+//   B_aug: 32 key groups x [k-core 0: 8 keys x 16 B (slots 0-7) | k-core 1: zeros]
+// followed (after all tiles) by one flag byte per row: 1 = the row's pair mask is empty.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int32_t* __restrict__ pair_index,
+                        int num_objects, int num_pairs, int n_query, int L, int rows, uint8_t* __restrict__ tiles,
+                        uint8_t* __restrict__ row_flags) {
+  const int mt = blockIdx.x;
+  const int t = threadIdx.x;
+  const int first_pair = (mt * 128) / n_query;
+  const int last_pair = min(num_pairs - 1, (mt * 128 + 127) / n_query);
+  const int nslots = last_pair - first_pair + 1;              // <= kXaSlots (host-checked)
+  __shared__ uint32_t s_union[kXaSlots][8];                   // union mask words per slot, real keys only
+  __shared__ uint32_t s_any[kXaSlots];
+  if (t < kXaSlots * 8) {
+    const int slot = t >> 3, w = t & 7;
+    uint32_t u = 0;
+    if (slot < nslots) {
+      const int pair = first_pair + slot;
+      const int pidx = max(0, pair_index ? pair_index[pair] : pair);
+      const int oi = min(pidx / num_objects, num_objects - 1), oj = pidx % num_objects;
+      const uint32_t keyok = (w < (L >> 5)) ? 0xffffffffu : (w == (L >> 5) ? ((1u << (L & 31)) - 1u) : 0u);
+      if (w < words) u = (bits[static_cast<size_t>(oi) * words + w] | bits[static_cast<size_t>(oj) * words + w]) & keyok;
+    }
+    s_union[slot][w] = u;
+  }
+  __syncthreads();
+  if (t < kXaSlots) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) any |= s_union[t][w];
+    s_any[t] = any;
+  }
+  __syncthreads();
+  uint8_t* tile = tiles + static_cast<size_t>(mt) * kXaTileBytes;
+  {  // B_aug: thread = key
+    const int key = t;
+    uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int s = 0; s < kXaSlots; ++s) {
+      const bool allowed = (s_union[s][key >> 5] >> (key & 31)) & 1u;     // keys >= L were cleared by keyok
+      if (s < nslots && !allowed) pk[s >> 1] |= (s & 1) ? 0xC6800000u : 0x0000C680u;     // bf16(-16384)
+    }
+    uint8_t* dst = tile + kXaAugA + (key >> 3) * 256 + (key & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0, 0, 0, 0);
+  }
+  if (t < 128) {  // A_aug: thread = row
+    const int row = mt * 128 + t;
+    uint32_t pk[4] = {0u, 0u, 0u, 0u};
+    uint8_t flag = 0;
+    if (row < rows) {
+      const int slot = row / n_query - first_pair;
+#pragma unroll
+      for (int s = 0; s < kXaSlots; ++s)
+        if (s == slot) pk[s >> 1] = (s & 1) ? 0x3F800000u : 0x00003F80u;                 // bf16(1.0)
+      flag = s_any[slot] == 0 ? 1 : 0;
+    }
+    uint8_t* dst = tile + (t >> 3) * 256 + (t & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0, 0, 0, 0);
+    row_flags[row] = flag;
+  }
+}
+
 __global__ void __launch_bounds__(kXaThreads, 1)
 xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmO,
@@ -93,15 +205,22 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sV = smem + XaSmem::kOffV;
   uint8_t* sQ = smem + XaSmem::kOffQ;
   uint8_t* sO = smem + XaSmem::kOffO;
+  uint8_t* sAug = smem + XaSmem::kOffAug;                                    // [stage] A_aug | B_aug
+  float* sMax = reinterpret_cast<float*>(smem + XaSmem::kOffMax);            // [buffer][half][row]
+  float* sVbar = reinterpret_cast<float*>(smem + XaSmem::kOffVbar);          // [head parity][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XaSmem::kOffBar);
-  uint64_t* q_full = bars;          // [2]
+  uint64_t* q_full = bars;          // [2]  Q tile + mask-bias tiles of a unit
   uint64_t* q_empty = bars + 2;     // [2]
-  uint64_t* kv_full = bars + 4;     // [2]  one per head set
-  uint64_t* s_full = bars + 6;      // [2]
-  uint64_t* p_ready = bars + 8;     // [2]
-  uint64_t* o_full = bars + 10;     // [2]
-  uint64_t* s_free = bars + 12;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* s_full = bars + 4;      // [2]
+  uint64_t* p_ready = bars + 6;     // [2]
+  uint64_t* o_full = bars + 8;      // [2]
+  uint64_t* s_free = bars + 10;     // [2]
+  uint64_t* vbar_ready = bars + 12; // [2]
+  uint64_t* k_full = bars + 14;
+  uint64_t* k_empty = bars + 15;
+  uint64_t* v_full = bars + 16;
+  uint64_t* v_empty = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,12 +233,14 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int b = 0; b < 2; ++b) {
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
-      mbar_init(&kv_full[b], 1);
       mbar_init(&s_full[b], 1);
-      mbar_init(&p_ready[b], 128);
+      mbar_init(&p_ready[b], 256);
       mbar_init(&o_full[b], 1);
-      mbar_init(&s_free[b], 128);
+      mbar_init(&s_free[b], 256);
+      mbar_init(&vbar_ready[b], 1);
     }
+    mbar_init(k_full, 1); mbar_init(k_empty, 1);
+    mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -128,11 +249,10 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   // rows 64..79 of every [V^T | 1 | 0] block: row 64 = ones (the PV MMA then also produces the row sum), rest zero.
   // Row 64 has (row & 7) == 0 and all its 16-byte chunks are equal, so the 128B swizzle does not matter here.
-  for (int idx = threadIdx.x; idx < 8 * 128; idx += kXaThreads) {
-    const int blk = idx >> 7, within = idx & 127;                // 8 blocks (2 sets x 4), 16 rows x 8 chunks each
+  for (int idx = threadIdx.x; idx < 4 * 128; idx += kXaThreads) {
+    const int blk = idx >> 7, within = idx & 127;                // 4 blocks, 16 rows x 8 chunks each
     const uint32_t one2 = (within < 8) ? 0x3F803F80u : 0u;        // bf16 1.0 pairs in row 64
-    uint8_t* dst = sV + (blk >> 2) * XaSmem::kVSet + (blk & 3) * XaSmem::kVBlk + XaSmem::kVBox + within * 16;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(one2, one2, one2, one2);
+    *reinterpret_cast<uint4*>(sV + blk * XaSmem::kVBlk + XaSmem::kVBox + within * 16) = make_uint4(one2, one2, one2, one2);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -140,7 +260,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // contiguous, head-major unit range of this CTA (spans at most two heads: host guarantees per <= m_tiles)
+  // contiguous, head-major unit range of this CTA
   const int per = (p.total_units + gridDim.x - 1) / gridDim.x;
   const int u_begin = blockIdx.x * per;
   const int u_end = min(p.total_units, u_begin + per);
@@ -149,60 +269,79 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (threadIdx.x == 0) {
     // ===================== TMA producer =====================
-    int cur_head = -1;
+    int cur_head = -1, loads = 0;
     for (int i = 0; i < n_units; ++i) {
       const int u = u_begin + i;
       const int head = u / p.m_tiles, mt = u % p.m_tiles;
-      if (head != cur_head) {
-        const int set = head - head0;
-        mbar_expect_tx(&kv_full[set], XaSmem::kKSet + 4 * XaSmem::kVBox);
-        tma_load_2d(sK + set * XaSmem::kKSet, &tmK, &kv_full[set], head * kXaHd, 0);
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-          tma_load_2d(sV + set * XaSmem::kVSet + kb * XaSmem::kVBlk, &tmVt, &kv_full[set], kb * 64, head * kXaHd);
-        cur_head = head;
+      const bool new_head = head != cur_head;
+      if (new_head) {      // K first: QK^T of this unit only needs K (V may still be in use by the previous unit's PV)
+        if (loads > 0) mbar_wait(k_empty, (loads - 1) & 1);
+        mbar_expect_tx(k_full, XaSmem::kK);
+        tma_load_2d(sK, &tmK, k_full, head * kXaHd, 0);
       }
       const int b = i & 1;
       mbar_wait(&q_empty[b], ((i >> 1) & 1) ^ 1);
-      mbar_expect_tx(&q_full[b], XaSmem::kQ);
+      mbar_expect_tx(&q_full[b], XaSmem::kQ + kXaTileBytes);
       tma_load_2d(sQ + b * XaSmem::kQ, &tmQ, &q_full[b], head * kXaHd, mt * 128);
+      bulk_load_1d(sAug + b * XaSmem::kAug, p.tiles + static_cast<size_t>(mt) * kXaTileBytes, kXaTileBytes, &q_full[b]);
+      if (new_head) {
+        if (loads > 0) mbar_wait(v_empty, (loads - 1) & 1);
+        mbar_expect_tx(v_full, 4 * XaSmem::kVBox);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sV + kb * XaSmem::kVBlk, &tmVt, v_full, kb * 64, head * kXaHd);
+        ++loads;
+        cur_head = head;
+      }
     }
   } else if (threadIdx.x == 32) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kXaKeys);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kXaPvN);
-    bool kv_ready[2] = {false, false};
+    const uint32_t lbo = p.desc_swap ? 256u : 128u, sbo = p.desc_swap ? 128u : 256u;
+    int k_waits = 0, v_waits = 0, head_qk = -1, head_pv = -1;
+    auto head_of = [&](int j) { return (u_begin + j) / p.m_tiles; };
     auto issue_qk = [&](int j) {
-      const int set = (u_begin + j) / p.m_tiles - head0;
+      const int head = head_of(j);
       const int b = j & 1;
-      if (!kv_ready[set]) {
-        mbar_wait(&kv_full[set], 0);
-        kv_ready[set] = true;
+      if (head != head_qk) {
+        mbar_wait(k_full, k_waits & 1);
+        ++k_waits;
+        head_qk = head;
       }
       mbar_wait(&q_full[b], (j >> 1) & 1);
       mbar_wait(&s_free[b], ((j >> 1) & 1) ^ 1);     // O of unit j-2 has been read out of this buffer
       tc_fence_after();
       const uint32_t a = smem_u32(sQ + b * XaSmem::kQ);
-      const uint32_t kk = smem_u32(sK + set * XaSmem::kKSet);
+      const uint32_t kk = smem_u32(sK);
+      const uint32_t aug = smem_u32(sAug + b * XaSmem::kAug);
       const uint32_t d = tmem_base + b * 256;
 #pragma unroll
       for (int k = 0; k < kXaHd / 16; ++k)
         umma_ss(d, umma_desc_k_sw128(a + k * 32), umma_desc_k_sw128(kk + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+      umma_ss(d, umma_desc_k_noswz(aug, lbo, sbo), umma_desc_k_noswz(aug + kXaAugA, lbo, sbo), idesc_qk, 1u);  // + mask bias
       tc_commit(&q_empty[b]);
       tc_commit(&s_full[b]);
+      if (j + 1 < n_units && head_of(j + 1) != head) tc_commit(k_empty);
     };
     auto issue_pv = [&](int i) {
-      const int set = (u_begin + i) / p.m_tiles - head0;
+      const int head = head_of(i);
       const int b = i & 1;
+      if (head != head_pv) {
+        mbar_wait(v_full, v_waits & 1);
+        ++v_waits;
+        head_pv = head;
+      }
       mbar_wait(&p_ready[b], (i >> 1) & 1);          // P_b complete in TMEM, S_b fully consumed
       tc_fence_after();
-      const uint32_t pa = tmem_base + b * 256;        // P: 128 columns of packed bf16 pairs (keys 2c, 2c+1)
-      const uint32_t od = tmem_base + b * 256 + 128;  // O: 80 fp32 columns
-      const uint32_t vb = smem_u32(sV + set * XaSmem::kVSet);
+      const uint32_t pa = tmem_base + b * 256;        // P: keys 0-127 in columns [0,64), keys 128-255 in [192,256)
+      const uint32_t od = tmem_base + b * 256 + 64;   // O: 80 fp32 columns [64,144)
+      const uint32_t vb = smem_u32(sV);
 #pragma unroll
       for (int k = 0; k < kXaKeys / 16; ++k)
-        umma_ts(od, pa + k * 8, umma_desc_k_sw128(vb + (k >> 2) * XaSmem::kVBlk + (k & 3) * 32), idesc_pv, k > 0 ? 1u : 0u);
+        umma_ts(od, pa + (k < 8 ? k * 8 : 192 + (k - 8) * 8),
+                umma_desc_k_sw128(vb + (k >> 2) * XaSmem::kVBlk + (k & 3) * 32), idesc_pv, k > 0 ? 1u : 0u);
       tc_commit(&o_full[b]);
+      if (i + 1 < n_units && head_of(i + 1) != head) tc_commit(v_empty);
     };
     if (n_units > 0) issue_qk(0);
     if (n_units > 1) issue_qk(1);
@@ -210,119 +349,131 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       issue_pv(i);
       if (i + 2 < n_units) issue_qk(i + 2);
     }
+  } else if (warp == 3) {
+    // ===================== per-head mean of V over the L real keys (rows whose pair mask is empty) =====================
+    int v_waits = 0, cur_head = -1;
+    for (int i = 0; i < n_units; ++i) {
+      const int head = (u_begin + i) / p.m_tiles;
+      if (head == cur_head) continue;
+      cur_head = head;
+      const int hs = head - head0;
+      mbar_wait(v_full, v_waits & 1);
+      ++v_waits;
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int n = lane + rr * 32;                        // value dim; the swizzle only permutes chunks inside a row
+        float acc = 0.f;
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint4* rowp = reinterpret_cast<const uint4*>(sV + kb * XaSmem::kVBlk + n * 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 x = rowp[c];
+            acc += bf16_lo(x.x) + bf16_hi(x.x) + bf16_lo(x.y) + bf16_hi(x.y) + bf16_lo(x.z) + bf16_hi(x.z) +
+                   bf16_lo(x.w) + bf16_hi(x.w);
+          }
+        }
+        sVbar[(hs & 1) * 64 + n] = acc / static_cast<float>(p.L);     // keys >= L are zero-filled by TMA
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&vbar_ready[hs & 1]);
+      // the next head's V may only be read after this head's last PV: v_full's next phase orders that for us
+    }
   } else if (warp >= 4) {
-    // ===================== softmax + epilogue warpgroups =====================
-    const int wg = (warp - 4) >> 2;                      // 0 / 1 = TMEM buffer = unit parity
+    // ===================== softmax + epilogue warps =====================
+    const int sw = warp - 4;
+    const int b = sw >> 3;                               // TMEM buffer = unit parity
+    const int half = (sw >> 2) & 1;                      // which 128 keys of the row
     const int q = warp & 3;                              // TMEM lane quarter of this warp (warp id % 4)
     const int r = q * 32 + lane;                         // row inside the tile
-    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = tmem_base + wg * 256 + lane_off;
-    const uint32_t tO = tS + 128;
-    const bool elected = (warp == 4 + 4 * wg) && lane == 0;
-    uint8_t* stage_row = sO + wg * XaSmem::kOst + r * 128;
-    const int full_words = p.L >> 5;
-    const uint32_t tail_mask = (p.L & 31) ? ((1u << (p.L & 31)) - 1u) : 0u;
-    const bool sum_in_regs = (p.flags & 1) != 0;
+    const uint32_t tS = tmem_base + b * 256 + (static_cast<uint32_t>(q * 32) << 16);
+    const bool elected = (sw & 7) == 0 && lane == 0;
+    uint8_t* stage_row = sO + b * XaSmem::kOst + r * 128;
+    float* my_max = sMax + (b * 2 + half) * 128 + r;
+    const float* other_max = sMax + (b * 2 + (half ^ 1)) * 128 + r;
 
-    for (int i = wg; i < n_units; i += 2) {
+    for (int i = b; i < n_units; i += 2) {
       const uint32_t parity = (i >> 1) & 1;
       const int u = u_begin + i;
       const int head = u / p.m_tiles, mt = u % p.m_tiles;
-      const int row = mt * 128 + r;
-      const bool valid = row < p.rows;
-      // pair mask = bits[i] | bits[j], restricted to the L real keys
-      uint32_t m[8];
-      bool empty = true;
-      {
-        int oi = 0, oj = 0;
-        if (valid) {
-          const int pair = row / p.n_query;
-          const int pidx = p.pair_index ? p.pair_index[pair] : pair;
-          oi = pidx / p.num_objects;
-          oj = pidx % p.num_objects;
-        }
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const uint32_t keyok = (w < full_words) ? 0xffffffffu : (w == full_words ? tail_mask : 0u);
-          uint32_t v = 0;
-          if (valid && w < p.words)
-            v = __ldg(p.bits + static_cast<size_t>(oi) * p.words + w) | __ldg(p.bits + static_cast<size_t>(oj) * p.words + w);
-          m[w] = v & keyok;
-          empty = empty && (m[w] == 0);
-        }
-        if (empty) {   // finfo.min on every key -> uniform attention over the L real keys
-#pragma unroll
-          for (int w = 0; w < 8; ++w) m[w] = (w < full_words) ? 0xffffffffu : (w == full_words ? tail_mask : 0u);
-        }
-      }
-      const float sc = empty ? 0.f : p.scale_log2e;       // empty: every real key gets exp2(0) = 1
+      const bool uniform = __ldg(p.row_flags + mt * 128 + r) != 0;     // empty pair mask -> uniform attention (HF finfo.min)
 
-      mbar_wait(&s_full[wg], parity);
+      mbar_wait(&s_full[b], parity);
       tc_fence_after();
-      // pass 1: row max over unmasked keys
-      float mx = -INFINITY;
+      // pass 1: row max of the biased scores over this thread's 128 keys, then across the two halves
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
-        tmem_ld32(tS + c * 32, v);
+        tmem_ld32(tS + (half * 4 + c) * 32, v);
         tmem_ld_wait();
-        const uint32_t mw = m[c];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((mw >> j) & 1u) ? __uint_as_float(v[j]) : -INFINITY);
+        for (int j = 0; j < 32; j += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[j]));
+          m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+          m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+        }
       }
-      if (mx == -INFINITY) mx = 0.f;
-      const float mxs = mx * sc;
-      // pass 2: p = exp2(s*scale - max*scale) on the pair's keys, 0 elsewhere; packed bf16 P overwrites S in place
-      float sum = 0.f;
+      float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      *my_max = mx;
+      named_bar_sync(1 + b, 256);
+      mx = fmaxf(mx, *other_max);
+      const float mxs = mx * p.scale_log2e;
+      // pass 2: p = exp2(s*scale - max*scale); packed bf16 P overwrites consumed score columns
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = half ? 3 - cc : cc;                // half 1 walks its chunks downwards (in-place safety)
         uint32_t v[32];
-        tmem_ld32(tS + c * 32, v);
+        tmem_ld32(tS + (half * 4 + c) * 32, v);
         tmem_ld_wait();
-        const uint32_t mw = m[c];
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -mxs));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -mxs));
-          const float p0 = ((mw >> (2 * j)) & 1u) ? e0 : 0.f;
-          const float p1 = ((mw >> (2 * j + 1)) & 1u) ? e1 : 0.f;
-          if (sum_in_regs) sum += p0 + p1;
-          pk[j] = pack_bf16x2(p0, p1);
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs));
+          pk[j] = pack_bf16x2(e0, e1);
         }
-        tmem_st16(tS + c * 16, pk);      // P cols [16c, 16c+16) only overlap S chunks <= c (already consumed)
+        tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_ready[wg]);
+      mbar_arrive(&p_ready[b]);
 
-      // epilogue: O / rowsum -> bf16 -> swizzled staging row -> TMA store of the [128 x 64] tile
-      mbar_wait(&o_full[wg], parity);
+      // epilogue: this thread's 32 output columns: O / rowsum -> bf16 -> swizzled staging row -> TMA store
+      mbar_wait(&o_full[b], parity);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tO, o0);
-      tmem_ld32(tO + 32, o1);
-      const uint32_t osum = tmem_ld1(tO + 64);
+      uint32_t o[32];
+      tmem_ld32(tS + 64 + half * 32, o);
+      const uint32_t osum = tmem_ld1(tS + 64 + 64);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&s_free[wg]);                          // buffer may be overwritten by QK^T of unit i+2
-      const float inv = 1.f / (sum_in_regs ? sum : __uint_as_float(osum));
-      if (elected) tma_store_wait_read<0>();             // previous unit's store has drained this staging tile
-      named_bar_sync(1 + wg, 128);
+      mbar_arrive(&s_free[b]);                           // buffer may be overwritten by QK^T of unit i+2
+      float f[32];
+      const float inv = 1.f / __uint_as_float(osum);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint32_t* src = (g < 4) ? (o0 + g * 8) : (o1 + (g - 4) * 8);
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(o[j]) * inv;
+      if (uniform) {
+        const int hs = head - head0;
+        mbar_wait(&vbar_ready[hs & 1], (hs >> 1) & 1);
+        const float* vb = sVbar + (hs & 1) * 64 + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = vb[j];
+      }
+      if (elected) tma_store_wait_read<0>();             // previous unit's store has drained this staging tile
+      named_bar_sync(3 + b, 256);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
         uint4 u4;
-        u4.x = pack_bf16x2(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-        u4.y = pack_bf16x2(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-        u4.z = pack_bf16x2(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-        u4.w = pack_bf16x2(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-        *reinterpret_cast<uint4*>(stage_row + ((g ^ (r & 7)) * 16)) = u4;
+        u4.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+        u4.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+        u4.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+        u4.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(stage_row + (((half * 4 + g) ^ (r & 7)) * 16)) = u4;
       }
       fence_proxy_async_smem();
-      named_bar_sync(3 + wg, 128);
+      named_bar_sync(5 + b, 256);
       if (elected) {
-        tma_store_2d(sO + wg * XaSmem::kOst, &tmO, head * kXaHd, mt * 128);
+        tma_store_2d(sO + b * XaSmem::kOst, &tmO, head * kXaHd, mt * 128);
         tma_store_commit();
       }
     }
@@ -341,24 +492,54 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 using namespace opsg;
 
+extern "C" size_t opsg_xattn_bias_tiles_bytes(int B, int n_query) {
+  if (B <= 0 || n_query <= 0) return 0;
+  const size_t m_tiles = (static_cast<size_t>(B) * n_query + 127) / 128;
+  return m_tiles * (kXaTileBytes + 128);
+}
+
+extern "C" int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
+                                     int n_query, int L, void* tiles_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(bits && tiles_out, "xattn_bias_tiles: null pointer");
+  OPSG_CHECK_ARG(B > 0 && n_query > 0 && L > 0 && num_objects > 0, "xattn_bias_tiles: bad shape");
+  if (L > kXaKeys) return set_error(OPSG_E_UNSUPPORTED, "xattn_bias_tiles: L=%d image tokens > %d unsupported", L, kXaKeys);
+  OPSG_CHECK_ARG(words >= (L + 31) / 32 && words <= 8, "xattn_bias_tiles: words=%d inconsistent with L=%d", words, L);
+  if (127 / n_query + 2 > kXaSlots)
+    return set_error(OPSG_E_UNSUPPORTED, "xattn_bias_tiles: n_query=%d puts more than %d pairs in a 128-row tile", n_query, kXaSlots);
+  OPSG_CHECK_ARG(((uintptr_t)tiles_out & 15) == 0, "xattn_bias_tiles: output must be 16-byte aligned");
+  const int rows = B * n_query;
+  const int m_tiles = (rows + 127) / 128;
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(tiles_out);
+  xattn_bias_tiles_kernel<<<m_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      bits, words, pair_index, num_objects, B, n_query, L, rows, tiles, tiles + static_cast<size_t>(m_tiles) * kXaTileBytes);
+  OPSG_CHECK_LAUNCH("xattn_bias_tiles_kernel");
+  return OPSG_OK;
+}
+
 extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
                                 const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
-                                int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream) {
-  static const int impl = [] { const char* e = getenv("OPSG_XATTN_IMPL"); return e ? atoi(e) : 2; }();
-  static const int flags = [] { const char* e = getenv("OPSG_XATTN_FLAGS"); return e ? atoi(e) : 0; }();
+                                int n_query, int L, int num_heads, int head_dim, const void* bias_tiles,
+                                opsg_bf16* ctx_out, void* stream) {
+  static const int impl = [] { const char* e = getenv("OPSG_XATTN_IMPL"); return e ? atoi(e) : 3; }();
+  static const int desc_swap = [] { const char* e = getenv("OPSG_XATTN_DESC_SWAP"); return e ? atoi(e) : 0; }();
   if (impl == 1)
     return opsg_xattn_pairs_v1(q, k, ld_k, vt, ld_vt, bits, words, pair_index, num_objects, B, n_query, L, num_heads,
                                head_dim, ctx_out, stream);
+  // without precomputed mask-bias tiles (or for shapes they do not cover) the self-contained v2 kernel runs
+  if (impl == 2 || !bias_tiles || n_query <= 0 || 127 / n_query + 2 > kXaSlots)
+    return opsg_xattn_pairs_v2(q, k, ld_k, vt, ld_vt, bits, words, pair_index, num_objects, B, n_query, L, num_heads,
+                               head_dim, ctx_out, stream);
   int rc = opsg_device_check();
   if (rc) return rc;
-  OPSG_CHECK_ARG(q && k && vt && bits && ctx_out, "xattn_pairs: null pointer");
+  OPSG_CHECK_ARG(q && k && vt && ctx_out, "xattn_pairs: null pointer");
   OPSG_CHECK_ARG(B > 0 && n_query > 0 && L > 0 && num_heads > 0 && num_objects > 0, "xattn_pairs: bad shape");
   if (head_dim != kXaHd) return set_error(OPSG_E_UNSUPPORTED, "xattn_pairs: head_dim %d unsupported (64 only)", head_dim);
   if (L > kXaKeys) return set_error(OPSG_E_UNSUPPORTED, "xattn_pairs: L=%d image tokens > %d unsupported", L, kXaKeys);
-  OPSG_CHECK_ARG(words >= (L + 31) / 32 && words <= 8, "xattn_pairs: words=%d inconsistent with L=%d", words, L);
   const int d_model = num_heads * head_dim;
   OPSG_CHECK_ARG(ld_k >= d_model && ld_k % 8 == 0 && ld_vt >= L && ld_vt % 8 == 0, "xattn_pairs: bad leading dims");
-  OPSG_CHECK_ARG(((uintptr_t)ctx_out & 15) == 0, "xattn_pairs: ctx_out must be 16-byte aligned");
+  OPSG_CHECK_ARG(((uintptr_t)ctx_out & 15) == 0 && ((uintptr_t)bias_tiles & 15) == 0, "xattn_pairs: ctx_out / bias_tiles must be 16-byte aligned");
   const int rows = B * n_query;
   CUtensorMap tmQ, tmK, tmVt, tmO;
   rc = make_tmap_bf16_2d(&tmQ, q, (uint64_t)rows, (uint64_t)d_model, (uint64_t)d_model, 128, 64);
@@ -377,15 +558,14 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
     configured = true;
   }
   XattnParams p;
-  p.bits = bits; p.pair_index = pair_index;
-  p.words = words; p.num_objects = num_objects; p.n_query = n_query; p.L = L; p.num_heads = num_heads; p.d_model = d_model;
-  p.rows = rows; p.m_tiles = (rows + 127) / 128; p.total_units = p.m_tiles * num_heads;
-  p.flags = flags;
+  p.m_tiles = (rows + 127) / 128;
+  p.tiles = reinterpret_cast<const uint8_t*>(bias_tiles);
+  p.row_flags = p.tiles + static_cast<size_t>(p.m_tiles) * kXaTileBytes;
+  p.L = L; p.num_heads = num_heads; p.d_model = d_model;
+  p.rows = rows; p.total_units = p.m_tiles * num_heads;
+  p.desc_swap = desc_swap;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   const int grid = p.total_units < opsg_num_sms() ? p.total_units : opsg_num_sms();
-  // each CTA's contiguous unit range must span at most two heads (two resident K/V sets)
-  const int per = (p.total_units + grid - 1) / grid;
-  if (per > p.m_tiles) return set_error(OPSG_E_UNSUPPORTED, "xattn_pairs: unit range %d spans more than two heads", per);
   xattn_pairs_kernel<<<grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmVt, tmO, p);
   OPSG_CHECK_LAUNCH("xattn_pairs_kernel");
   return OPSG_OK;

@@ -190,16 +190,34 @@ def self_attn_small(qkv, text_mask, B, n_query, T, num_heads, head_dim, text_que
     return out
 
 
-def xattn_pairs(q, k, vt, bits, num_objects, B, n_query, L, num_heads, head_dim, pair_index=None, out=None):
-    """K5: q bf16 [B*nq, d]; k bf16 [L, d]; vt bf16 [d, ld>=L]; bits int32 [N, words]."""
+def xattn_bias_tiles(bits, num_objects, B, n_query, L, pair_index=None):
+    """K5 operand prep (once per image): pair masks as tensor-core bias tiles -> uint8 buffer for xattn_pairs."""
+    _cuda(bits, torch.int32, "bits")
+    lib = _lib.load()
+    nbytes = lib.opsg_xattn_bias_tiles_bytes(B, n_query)
+    tiles = torch.empty(nbytes, dtype=torch.uint8, device=bits.device)
+    with _timed("xattn_bias_tiles", 0.0, float(nbytes)):
+        _lib.check(lib.opsg_xattn_bias_tiles(_ptr(bits), bits.shape[1], _ptr(pair_index), num_objects, B, n_query, L,
+                                             _ptr(tiles), _stream()))
+    _count()
+    return tiles
+
+
+def xattn_pairs(q, k, vt, bits, num_objects, B, n_query, L, num_heads, head_dim, pair_index=None, out=None, bias_tiles=None):
+    """K5: q bf16 [B*nq, d]; k bf16 [L, d]; vt bf16 [d, ld>=L]; bits int32 [N, words]; bias_tiles from
+    xattn_bias_tiles (None -> built here; False -> none: the library's self-contained kernel)."""
     _cuda(q, torch.bfloat16, "q"); _cuda(k, torch.bfloat16, "k"); _cuda(vt, torch.bfloat16, "vt")
     assert q.is_contiguous()
     if out is None:
         out = torch.empty_like(q)
+    if bias_tiles is None:
+        bias_tiles = xattn_bias_tiles(bits, num_objects, B, n_query, L, pair_index)
+    elif bias_tiles is False:
+        bias_tiles = None
     with _timed("xattn_pairs", 4.0 * B * n_query * L * num_heads * head_dim, 4.0 * q.numel() + 4.0 * L * num_heads * head_dim):
         _lib.check(_lib.load().opsg_xattn_pairs(_ptr(q), _ptr(k), k.stride(0), _ptr(vt), vt.stride(0), _ptr(bits), bits.shape[1],
-                                               _ptr(pair_index), num_objects, B, n_query, L, num_heads, head_dim, _ptr(out),
-                                               _stream()))
+                                               _ptr(pair_index), num_objects, B, n_query, L, num_heads, head_dim,
+                                               _ptr(bias_tiles), _ptr(out), _stream()))
     _count()
     return out
 

@@ -135,6 +135,7 @@ class RelationQueryTransformer:
         inter = {} if keep_intermediates else None
 
         bits = ops.pair_mask_bits(pan, img_hw, pad_hw, (th, tw), obj_ids)       # K2
+        bias_tiles = ops.xattn_bias_tiles(bits, N, B, N_QUERY, L, pair_index)    # K5 mask operand tiles (both layers)
         X = self.image_tokens(feat)                                              # K1  [L,256]
         h = ops.qformer_embed_ln(w.query, input_ids, w.word_emb, w.pos_emb, w.emb_ln[0], w.emb_ln[1], LN_EPS)   # K7
         RQ = B * N_QUERY
@@ -156,7 +157,8 @@ class RelationQueryTransformer:
             hq = h1[:RQ]
             # K5: masked pair x image cross-attention on the query rows
             qc = ops.gemm(hq, lw["w_cq"], lw["b_cq"])
-            cx = ops.xattn_pairs(qc, kc, vt, bits, N, B, N_QUERY, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index)
+            cx = ops.xattn_pairs(qc, kc, vt, bits, N, B, N_QUERY, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index,
+                                 bias_tiles=bias_tiles)
             pre = ops.gemm(cx, lw["w_co"], lw["b_co"], residual=hq)
             hq2 = ops.layernorm(pre, lw["ln_cross"][0], lw["ln_cross"][1], LN_EPS)
             # FFN (query rows; text rows only where a later layer can still see them)

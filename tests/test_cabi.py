@@ -16,7 +16,7 @@ HEADER = (ROOT / "include" / "opsg_b200.h").read_text()
 def _declared():
     text = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|const char\*)\s+(opsg_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(opsg_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args == "void" else len([a for a in args.split(",") if a.strip()])
     return out

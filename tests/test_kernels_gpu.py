@@ -248,6 +248,58 @@ def test_xattn_pairs(ops, L, N, B):
     assert (last - v.float().mean(0, keepdim=True)).abs().max() < 2e-2
 
 
+def test_xattn_pairs_without_bias_tiles(ops):
+    """bias_tiles == NULL selects the self-contained kernel (per-row OR of the bit rows): same results."""
+    g = torch.Generator().manual_seed(3)
+    L, N, nq, d = 252, 6, 33, 768
+    B = N * N
+    q, k, v = _rand_bf16((B * nq, d), g), _rand_bf16((L, d), g), _rand_bf16((L, d), g)
+    masks = torch.rand(N, L, generator=g) < 0.2
+    masks[0] = False
+    bits = torch.from_numpy(restated.pack_mask_bits(masks.numpy()).view(np.int32))
+    vt = torch.zeros((d, 256), dtype=torch.bfloat16)
+    vt[:, :L] = v.t()
+    a = ops.xattn_pairs(q.cuda(), k.cuda(), vt.cuda(), bits.cuda(), N, B, nq, L, 12, 64, bias_tiles=False).float().cpu()
+    b = ops.xattn_pairs(q.cuda(), k.cuda(), vt.cuda(), bits.cuda(), N, B, nq, L, 12, 64).float().cpu()
+    ref = _xattn_ref(q, k, v, masks, N, None, nq)
+    assert (a - ref).abs().max() < 2e-2 and (b - ref).abs().max() < 2e-2
+
+
+def test_xattn_bias_tiles_bit_exact(ops):
+    """The mask-bias operand tiles are integer work: compare every byte with a numpy restatement."""
+    g = torch.Generator().manual_seed(4)
+    L, N, nq = 200, 9, 33
+    B = N * N
+    masks = torch.rand(N, L, generator=g) < 0.1
+    masks[3] = False
+    bits = torch.from_numpy(restated.pack_mask_bits(masks.numpy()).view(np.int32))
+    got = ops.xattn_bias_tiles(bits.cuda(), N, B, nq, L).cpu().numpy()
+    rows = B * nq
+    m_tiles = (rows + 127) // 128
+    tiles, flags = got[:m_tiles * 12288].reshape(m_tiles, 12288), got[m_tiles * 12288:]
+    pm = restated.pair_masks(masks.numpy())                       # [B, L]
+    NEG, ONE = 0xC680, 0x3F80
+    for mt in range(m_tiles):
+        first = (mt * 128) // nq
+        last = min(B - 1, (mt * 128 + 127) // nq)
+        a = tiles[mt, :4096].view(np.uint16).reshape(16, 2, 8, 8)     # [row group][k-core][row][slot]
+        b = tiles[mt, 4096:].view(np.uint16).reshape(32, 2, 8, 8)
+        assert not a[:, 1].any() and not b[:, 1].any()
+        for r in range(128):
+            row = mt * 128 + r
+            exp = np.zeros(8, np.uint16)
+            if row < rows:
+                exp[row // nq - first] = ONE
+                assert flags[row] == (0 if pm[row // nq].any() else 1)
+            assert np.array_equal(a[r // 8, 0, r % 8], exp)
+        for key in range(256):
+            exp = np.zeros(8, np.uint16)
+            for s in range(last - first + 1):
+                if not (key < L and pm[first + s, key]):
+                    exp[s] = NEG
+            assert np.array_equal(b[key // 8, 0, key % 8], exp), (mt, key)
+
+
 def test_xattn_pairs_with_pair_index(ops):
     g = torch.Generator().manual_seed(77)
     L, N, nq, d = 256, 12, 33, 768
