@@ -24,6 +24,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of a CONVERGED warp (call it under warp-uniform control flow only).  Issuing tcgen05.mma / TMA from
+// `if (elect_one_sync())` inside a warp-uniform branch lets ptxas move the operands to uniform registers directly;
+// under `if (threadIdx.x == k)` it has to wrap every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+// (measured: ~93 cycles per MMA issue instead of the MMA's own 32-128 cycles, scripts/ubench/mma_cost.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier

@@ -1,8 +1,8 @@
 // K3/K6/K9/K10c — D = act(A . W^T + bias + residual), bf16 operands, fp32 accumulation in TMEM.
 //
 // Persistent warp-specialised tcgen05 kernel (one CTA per SM, cta_group::1, 384 threads):
-//   warp 0 (1 thread)  TMA producer : A tile [128 x 64] + W tile [BN x 64] per stage, 128B swizzle
-//   warp 1 (1 thread)  MMA issuer   : 4 x tcgen05.mma 128 x BN x 16 per stage, accumulator in TMEM
+//   warp 0 (elected lane) TMA producer : A tile [128 x 64] + W tile [BN x 64] per stage, 128B swizzle
+//   warp 1 (elected lane) MMA issuer   : 4 x tcgen05.mma 128 x BN x 16 per stage, accumulator in TMEM
 //   warp 2             TMEM allocator (2 accumulator stages x BN columns)
 //   warps 4-11         epilogue     : warp = (TMEM lane quarter, 32-column half of a 64-column slab);
 //                                     tcgen05.ld 32x32b (thread = row), bias / residual / activation in
@@ -98,8 +98,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int kb_total = (p.K + kBK - 1) / kBK;
   const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
 
-  if (threadIdx.x == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -111,14 +111,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kb1 = min(kb_total, kb0 + kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-        tma_load_2d(smem_a + stage * S::kABytes, &tmA, &full_bar[stage], kb * kBK, m_t * kBM);
-        tma_load_2d(smem_b + stage * S::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_t * BN);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_2d(smem_a + stage * S::kABytes, &tmA, &full_bar[stage], kb * kBK, m_t * kBM);
+          tma_load_2d(smem_b + stage * S::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_t * BN);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, elect.sync lane issues tcgen05.mma + commits) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
     int stage = 0;
     uint32_t phase = 0;
@@ -134,17 +137,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
-        const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+        if (elect_one_sync()) {
+          const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * S::kABytes));
+          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * S::kBBytes));
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          umma_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                  (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k)      // +32 bytes per K step = +2 in the descriptor's 16-byte address field
+            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty_bar[stage]);
+          if (kb + 1 == kb1) tc_commit(&tmem_full[acc]);
         }
-        tc_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&tmem_full[acc]);
+      if (kb0 >= kb1) {                           // split without K blocks: still hand an (unused) accumulator over
+        if (elect_one_sync()) tc_commit(&tmem_full[acc]);
+        __syncwarp();
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {

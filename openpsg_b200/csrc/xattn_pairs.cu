@@ -6,8 +6,8 @@
 // head's K [256 x 64] and [V^T | 1 | 0] [80 x 256] resident in shared memory.
 //
 // 640 threads:
-//   warp 0 (1 thread)  TMA producer : K / V^T on a head change, Q tile per unit (2 stages)
-//   warp 1 (1 thread)  MMA issuer   : S_b  = Q.K^T + A_aug.B_aug^T   (128 x 256 x (64+16), SS, 5 MMAs)
+//   warp 0 (elected lane) TMA producer : K / V^T on a head change, Q tile + mask-bias tiles per unit (2 stages)
+//   warp 1 (elected lane) MMA issuer   : S_b  = Q.K^T + A_aug.B_aug^T   (128 x 256 x (64+16), SS, 5 MMAs)
 //                                     O_b  = P_b.[V|1]               (128 x 80 x 256, TS, 16 MMAs)
 //   warp 2             TMEM allocator (512 columns = two 256-column buffers)
 //   warp 3             per-head mean of V (output of uniform-attention rows)
@@ -57,6 +57,7 @@ struct XattnParams {
   int m_tiles;
   int total_units;
   int desc_swap;     // debug: swap LBO / SBO of the no-swizzle descriptors
+  long long* trace;  // debug: per-unit clock64 stamps of CTA 0 ([unit][8]); NULL in production
   float scale_log2e;
 };
 
@@ -109,6 +110,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// exp2 on the FMA / ALU pipes for x <= 0 (FA-4 style MUFU offload): round-to-nearest split x = n + f by the
+// 1.5*2^23 magic constant, degree-3 minimax 2^f on [-0.5, 0.5] (max relative error 7.6e-5, 50x below the bf16
+// rounding of P), exponent added through the integer bits of t.  x is clamped to -125 so the exponent field cannot
+// wrap: a masked score (bias -16384) gives 2^-125 instead of +0, which no fp32 accumulation can see.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float n = t - 12582912.f;
+  const float f = x - n;
+  float p = fmaf(0.05518026649951935f, f, 0.24261191487312317f);
+  p = fmaf(p, f, 0.6932594180107117f);
+  p = fmaf(p, f, 0.9999279975891113f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 // registers -> TMEM: this thread's lane (row), 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -195,6 +210,9 @@ xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int3
   }
 }
 
+// POLY_MOD: 0 = every exponential on the MUFU; m > 0 = elements with (index % m == 1) use ex2_poly.
+// PREFETCH : tcgen05.ld of the next 32-column chunk in flight while the current one is processed.
+template <int POLY_MOD, bool PREFETCH>
 __global__ void __launch_bounds__(kXaThreads, 1)
 xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmO,
@@ -267,8 +285,8 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_units = max(0, u_end - u_begin);
   const int head0 = u_begin / p.m_tiles;
 
-  if (threadIdx.x == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (warp-uniform loop, elect.sync lane issues) =====================
     int cur_head = -1, loads = 0;
     for (int i = 0; i < n_units; ++i) {
       const int u = u_begin + i;
@@ -276,25 +294,34 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool new_head = head != cur_head;
       if (new_head) {      // K first: QK^T of this unit only needs K (V may still be in use by the previous unit's PV)
         if (loads > 0) mbar_wait(k_empty, (loads - 1) & 1);
-        mbar_expect_tx(k_full, XaSmem::kK);
-        tma_load_2d(sK, &tmK, k_full, head * kXaHd, 0);
+        if (elect_one_sync()) {
+          mbar_expect_tx(k_full, XaSmem::kK);
+          tma_load_2d(sK, &tmK, k_full, head * kXaHd, 0);
+        }
+        __syncwarp();
       }
       const int b = i & 1;
       mbar_wait(&q_empty[b], ((i >> 1) & 1) ^ 1);
-      mbar_expect_tx(&q_full[b], XaSmem::kQ + kXaTileBytes);
-      tma_load_2d(sQ + b * XaSmem::kQ, &tmQ, &q_full[b], head * kXaHd, mt * 128);
-      bulk_load_1d(sAug + b * XaSmem::kAug, p.tiles + static_cast<size_t>(mt) * kXaTileBytes, kXaTileBytes, &q_full[b]);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&q_full[b], XaSmem::kQ + kXaTileBytes);
+        tma_load_2d(sQ + b * XaSmem::kQ, &tmQ, &q_full[b], head * kXaHd, mt * 128);
+        bulk_load_1d(sAug + b * XaSmem::kAug, p.tiles + static_cast<size_t>(mt) * kXaTileBytes, kXaTileBytes, &q_full[b]);
+      }
+      __syncwarp();
       if (new_head) {
         if (loads > 0) mbar_wait(v_empty, (loads - 1) & 1);
-        mbar_expect_tx(v_full, 4 * XaSmem::kVBox);
+        if (elect_one_sync()) {
+          mbar_expect_tx(v_full, 4 * XaSmem::kVBox);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sV + kb * XaSmem::kVBlk, &tmVt, v_full, kb * 64, head * kXaHd);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d(sV + kb * XaSmem::kVBlk, &tmVt, v_full, kb * 64, head * kXaHd);
+        }
+        __syncwarp();
         ++loads;
         cur_head = head;
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, elect.sync lane issues tcgen05.mma + commits) =====================
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kXaKeys);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kXaPvN);
     const uint32_t lbo = p.desc_swap ? 256u : 128u, sbo = p.desc_swap ? 128u : 256u;
@@ -311,17 +338,22 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&q_full[b], (j >> 1) & 1);
       mbar_wait(&s_free[b], ((j >> 1) & 1) ^ 1);     // O of unit j-2 has been read out of this buffer
       tc_fence_after();
-      const uint32_t a = smem_u32(sQ + b * XaSmem::kQ);
-      const uint32_t kk = smem_u32(sK);
-      const uint32_t aug = smem_u32(sAug + b * XaSmem::kAug);
-      const uint32_t d = tmem_base + b * 256;
+      const bool release_k = j + 1 < n_units && head_of(j + 1) != head;
+      if (elect_one_sync()) {
+        if (p.trace && blockIdx.x == 0) p.trace[j * 8 + 0] = clock64();
+        const uint64_t a_desc = umma_desc_k_sw128(smem_u32(sQ + b * XaSmem::kQ));
+        const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK));
+        const uint32_t aug = smem_u32(sAug + b * XaSmem::kAug);
+        const uint32_t d = tmem_base + b * 256;
 #pragma unroll
-      for (int k = 0; k < kXaHd / 16; ++k)
-        umma_ss(d, umma_desc_k_sw128(a + k * 32), umma_desc_k_sw128(kk + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-      umma_ss(d, umma_desc_k_noswz(aug, lbo, sbo), umma_desc_k_noswz(aug + kXaAugA, lbo, sbo), idesc_qk, 1u);  // + mask bias
-      tc_commit(&q_empty[b]);
-      tc_commit(&s_full[b]);
-      if (j + 1 < n_units && head_of(j + 1) != head) tc_commit(k_empty);
+        for (int k = 0; k < kXaHd / 16; ++k)           // +32 bytes per K step = +2 in the 16-byte address field
+          umma_ss(d, a_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+        umma_ss(d, umma_desc_k_noswz(aug, lbo, sbo), umma_desc_k_noswz(aug + kXaAugA, lbo, sbo), idesc_qk, 1u);  // + mask bias
+        tc_commit(&q_empty[b]);
+        tc_commit(&s_full[b]);
+        if (release_k) tc_commit(k_empty);
+      }
+      __syncwarp();
     };
     auto issue_pv = [&](int i) {
       const int head = head_of(i);
@@ -333,15 +365,20 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       mbar_wait(&p_ready[b], (i >> 1) & 1);          // P_b complete in TMEM, S_b fully consumed
       tc_fence_after();
-      const uint32_t pa = tmem_base + b * 256;        // P: keys 0-127 in columns [0,64), keys 128-255 in [192,256)
-      const uint32_t od = tmem_base + b * 256 + 64;   // O: 80 fp32 columns [64,144)
-      const uint32_t vb = smem_u32(sV);
+      const bool release_v = i + 1 < n_units && head_of(i + 1) != head;
+      if (elect_one_sync()) {
+        if (p.trace && blockIdx.x == 0) p.trace[i * 8 + 1] = clock64();
+        const uint32_t pa = tmem_base + b * 256;        // P: keys 0-127 in columns [0,64), keys 128-255 in [192,256)
+        const uint32_t od = tmem_base + b * 256 + 64;   // O: 80 fp32 columns [64,144)
+        const uint64_t v_desc = umma_desc_k_sw128(smem_u32(sV));
 #pragma unroll
-      for (int k = 0; k < kXaKeys / 16; ++k)
-        umma_ts(od, pa + (k < 8 ? k * 8 : 192 + (k - 8) * 8),
-                umma_desc_k_sw128(vb + (k >> 2) * XaSmem::kVBlk + (k & 3) * 32), idesc_pv, k > 0 ? 1u : 0u);
-      tc_commit(&o_full[b]);
-      if (i + 1 < n_units && head_of(i + 1) != head) tc_commit(v_empty);
+        for (int k = 0; k < kXaKeys / 16; ++k)
+          umma_ts(od, pa + (k < 8 ? k * 8 : 192 + (k - 8) * 8),
+                  v_desc + (k >> 2) * (XaSmem::kVBlk >> 4) + (k & 3) * 2, idesc_pv, k > 0 ? 1u : 0u);
+        tc_commit(&o_full[b]);
+        if (release_v) tc_commit(v_empty);
+      }
+      __syncwarp();
     };
     if (n_units > 0) issue_qk(0);
     if (n_units > 1) issue_qk(1);
@@ -399,49 +436,102 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
       mbar_wait(&s_full[b], parity);
       tc_fence_after();
-      // pass 1: row max of the biased scores over this thread's 128 keys, then across the two halves
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + (half * 4 + c) * 32, v);
-        tmem_ld_wait();
+      const bool tr = p.trace && blockIdx.x == 0 && (sw & 7) == 0 && lane == 0;
+      if (tr) p.trace[i * 8 + 2] = clock64();
+      auto exp2_sel = [&](float x, int idx) -> float {
+        if (POLY_MOD > 0 && (idx % (POLY_MOD > 0 ? POLY_MOD : 1)) == 1) return ex2_poly(x);
+        return ex2_approx(x);
+      };
+      float mx;
+      if constexpr (PREFETCH) {
+        // pass 1: row max of the biased scores over this thread's 128 keys, then across the two halves.
+        // tcgen05.ld of chunk c+1 is in flight while chunk c is reduced (two register sets).
+        uint32_t va[32], vb[32];
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        tmem_ld32(tS + (half * 4) * 32, va);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          m0 = fmaxf(m0, __uint_as_float(v[j]));
-          m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
-          m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
-          m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
-        }
-      }
-      float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      *my_max = mx;
-      named_bar_sync(1 + b, 256);
-      mx = fmaxf(mx, *other_max);
-      const float mxs = mx * p.scale_log2e;
-      // pass 2: p = exp2(s*scale - max*scale); packed bf16 P overwrites consumed score columns
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = half ? 3 - cc : cc;                // half 1 walks its chunks downwards (in-place safety)
-        uint32_t v[32];
-        tmem_ld32(tS + (half * 4 + c) * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          tmem_ld_wait();
+          if (c + 1 < 4) tmem_ld32(tS + (half * 4 + c + 1) * 32, nxt);
+          else tmem_ld32(tS + (half * 4 + (half ? 3 : 0)) * 32, nxt);      // first chunk of pass 2 (nxt == va)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs));
-          pk[j] = pack_bf16x2(e0, e1);
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(cur[j]));
+            m1 = fmaxf(m1, __uint_as_float(cur[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(cur[j + 2]));
+            m3 = fmaxf(m3, __uint_as_float(cur[j + 3]));
+          }
         }
-        tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        *my_max = mx;
+        named_bar_sync(1 + b, 256);
+        mx = fmaxf(mx, *other_max);
+        const float mxs = mx * p.scale_log2e;
+        // pass 2: p = exp2(s*scale - max*scale); packed bf16 P overwrites consumed score columns
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = half ? 3 - cc : cc;                // half 1 walks its chunks downwards (in-place safety)
+          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+          tmem_ld_wait();
+          if (cc + 1 < 4) tmem_ld32(tS + (half * 4 + (half ? 2 - cc : cc + 1)) * 32, nxt);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = exp2_sel(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2e, -mxs), 2 * j);
+            const float e1 = exp2_sel(fmaf(__uint_as_float(cur[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
+        }
+      } else {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tS + (half * 4 + c) * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[j]));
+            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+            m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+          }
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        *my_max = mx;
+        named_bar_sync(1 + b, 256);
+        mx = fmaxf(mx, *other_max);
+        const float mxs = mx * p.scale_log2e;
+        if (tr) p.trace[i * 8 + 3] = clock64();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = half ? 3 - cc : cc;                // half 1 walks its chunks downwards (in-place safety)
+          uint32_t v[32];
+          tmem_ld32(tS + (half * 4 + c) * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = exp2_sel(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs), 2 * j);
+            const float e1 = exp2_sel(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
+      if (tr) p.trace[i * 8 + 4] = clock64();
       mbar_arrive(&p_ready[b]);
 
       // epilogue: this thread's 32 output columns: O / rowsum -> bf16 -> swizzled staging row -> TMA store
       mbar_wait(&o_full[b], parity);
       tc_fence_after();
+      if (tr) p.trace[i * 8 + 5] = clock64();
       uint32_t o[32];
       tmem_ld32(tS + 64 + half * 32, o);
       const uint32_t osum = tmem_ld1(tS + 64 + 64);
@@ -476,6 +566,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_store_2d(sO + b * XaSmem::kOst, &tmO, head * kXaHd, mt * 128);
         tma_store_commit();
       }
+      if (tr) p.trace[i * 8 + 6] = clock64();
     }
     if (elected) tma_store_wait_all<0>();
   }
@@ -491,6 +582,10 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }  // namespace opsg
 
 using namespace opsg;
+
+static long long* g_xattn_trace = nullptr;
+// debug hook (not part of the public header): device buffer of >= 8 * units_per_cta int64 for per-unit clock stamps
+extern "C" void opsg_debug_xattn_trace(void* dev_buffer) { g_xattn_trace = reinterpret_cast<long long*>(dev_buffer); }
 
 extern "C" size_t opsg_xattn_bias_tiles_bytes(int B, int n_query) {
   if (B <= 0 || n_query <= 0) return 0;
@@ -550,11 +645,18 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmO, ctx_out, (uint64_t)rows, (uint64_t)d_model, (uint64_t)d_model, 128, 64);
   if (rc) return rc;
+  static const int variant = [] { const char* e = getenv("OPSG_XATTN_VARIANT"); return e ? atoi(e) : 0; }();
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const XattnParams);
+  static const KernelFn kernels[] = {xattn_pairs_kernel<0, false>, xattn_pairs_kernel<0, true>, xattn_pairs_kernel<3, false>,
+                                     xattn_pairs_kernel<3, true>, xattn_pairs_kernel<4, false>, xattn_pairs_kernel<6, false>};
+  const KernelFn kernel = kernels[(variant >= 0 && variant < 6) ? variant : 0];
   static bool configured = false;
   if (!configured) {
-    rc = check_cuda(cudaFuncSetAttribute(xattn_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XaSmem::kTotal),
-                    "cudaFuncSetAttribute(xattn)");
-    if (rc) return rc;
+    for (KernelFn f : kernels) {
+      rc = check_cuda(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, XaSmem::kTotal),
+                      "cudaFuncSetAttribute(xattn)");
+      if (rc) return rc;
+    }
     configured = true;
   }
   XattnParams p;
@@ -564,9 +666,10 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   p.L = L; p.num_heads = num_heads; p.d_model = d_model;
   p.rows = rows; p.total_units = p.m_tiles * num_heads;
   p.desc_swap = desc_swap;
+  p.trace = g_xattn_trace;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   const int grid = p.total_units < opsg_num_sms() ? p.total_units : opsg_num_sms();
-  xattn_pairs_kernel<<<grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmVt, tmO, p);
+  kernel<<<grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmVt, tmO, p);
   OPSG_CHECK_LAUNCH("xattn_pairs_kernel");
   return OPSG_OK;
 }
