@@ -143,6 +143,56 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+# DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_ncu_gemm_c.md: mean of the eight
+# layer-0 GEMM launches of one cfg2 image; profiles/r1_ncu_xattn_k.md is the N=80 launch, the N=40 launch of
+# profiles/r1_ncu_xattn_h.md moved 129 MB) — per launch, like `achieved`.
+NCU_TRAFFIC_BYTES = {"gemm_bf16": 287e6, "xattn_pairs": 129e6}
+
+
+def _llm_leg(dev, head, hidden, steps):
+    """cfg3's LLM leg (a9-a10): top-100 pairs x 32 new tokens through a random-init OPT-2.7B, batched prefill + decode."""
+    from transformers import OPTConfig, OPTForCausalLM
+    from openpsg_b200.llm import build_llm_engine
+    wl = synth.WORKLOADS["cfg3"]
+    t0 = time.perf_counter()
+    with torch.device(dev):
+        lm = OPTForCausalLM(OPTConfig(**synth.OPT_2P7B)).eval()
+        proj = torch.nn.Linear(768, synth.OPT_2P7B["hidden_size"])
+    eng = build_llm_engine(lm, proj, dev)
+    weight_bytes = 2.0 * sum(p.numel() for n, p in lm.named_parameters() if "embed_positions" not in n)
+    del lm
+    torch.cuda.empty_cache()
+    init_s = time.perf_counter() - t0
+    k, T, T_new = wl.topk_pairs, 17, wl.max_new_tokens
+    g = torch.Generator().manual_seed(5)
+    sel = torch.randperm(hidden.shape[0] // 33, generator=g)[:k].to(torch.int32).to(dev)
+    ids = torch.randint(4, synth.OPT_2P7B["vocab_size"], (k, T), generator=g).to(torch.int32).to(dev)
+    lens = torch.randint(14, T + 1, (k, 1), generator=g)
+    mask = (torch.arange(T)[None, :] >= (T - lens)).to(torch.int32).to(dev)            # left padded
+    for _ in range(2):
+        out = eng.generate(hidden, sel, ids, mask, max_new_tokens=T_new)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = eng.generate(hidden, sel, ids, mask, max_new_tokens=T_new)
+        toks = out.tokens.cpu()                                                         # D2H of the generated ids
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peaks = _peaks()
+    # HBM floor of the decode: every step streams the weights once for the whole batch (+ the KV cache, ignored here)
+    decode_bytes = (T_new - 1) * weight_bytes
+    return {"value": k * T_new / (ms * 1e-3), "unit": "tokens/s", "ms_per_image": ms,
+            "config": {"workload": "cfg3 LLM leg: top-100 pairs x 32 new tokens, 49-token embedded prompt, random-init OPT-2.7B "
+                                   "(32 layers, d 2560), batched prefill + greedy decode as one CUDA graph", "pairs": k,
+                       "new_tokens": T_new},
+            "tokens_checksum": int(toks.long().sum()), "model_init_s": init_s,
+            "roofline": {"bound": "hbm", "achieved": decode_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": decode_bytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                         "note": "weight bytes of the 31 decode steps / whole prefill+decode time (lower bound on achieved)"}}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from openpsg_b200 import ops
@@ -166,24 +216,21 @@ def run_ours(args):
     host_inputs = [synth.make_image_inputs(wl, rank * ips + i) for i in range(ips)]
     for inp in host_inputs:   # pinned host copies for the e2e leg
         inp["mask_features"] = inp["mask_features"].pin_memory()
-        inp["object_info"][0]["pan_results"] = inp["object_info"][0]["pan_results"].pin_memory()
+        inp["object_info"][0]["pan_results"] = inp["object_info"][0]["pan_results"].to(torch.int32).pin_memory()
     dev_inputs = [synth.inputs_to(inp, dev) for inp in host_inputs]
 
     def step_resident():
         for inp in dev_inputs:
             head(inp)
 
-    def step_e2e():
+    def step_e2e():       # host buffers in, selected pair list out: H2D of image i+1 overlaps compute of image i
         res = []
-        for inp in host_inputs:
-            d = dict(inp)
-            d["mask_features"] = inp["mask_features"].to(dev, non_blocking=True)
-            oi = dict(inp["object_info"][0])
-            oi["pan_results"] = oi["pan_results"].to(dev, non_blocking=True)
-            d["object_info"] = [oi]
-            head(d)
-            res.append(head.last_output.topk.cpu())          # D2H of the selected pair list
+        outs = head.forward_batch(host_inputs, on_result=lambda h: res.append(h.last_output.topk.cpu()))
+        assert len(outs) == len(host_inputs) and len(res) == len(host_inputs)
         return res
+
+    def step_e2e_single():   # the reference-facing batch-1 call with host tensors, no prefetch
+        return [(head(inp), head.last_output.topk.cpu())[1] for inp in host_inputs]
 
     def barrier():
         if world > 1:
@@ -203,17 +250,15 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.profile_begin()
     l0 = ops.launch_count
     ms = timed(step_resident, args.steps)
     launches = ops.launch_count - l0
-    prof = ops.profile_end()
-    clocks = sampler.stop() if rank == 0 else None
     pairs_per_step = wl.ordered_pairs * ips * world
     value = pairs_per_step * args.steps / (ms * 1e-3)
 
@@ -221,10 +266,24 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = pairs_per_step * args.steps / (ms_e2e * 1e-3)
+    ms_e2e_single = timed(step_e2e_single, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    clocks = sampler.stop() if rank == 0 else None
     h2d = sum(inp["mask_features"].numel() * 4 + inp["object_info"][0]["pan_results"].numel() *
               inp["object_info"][0]["pan_results"].element_size() + wl.num_objects * 4 +
               2 * wl.queries * 16 * 4 for inp in host_inputs)
     d2h = ips * (20 * 4 + wl.num_objects * 4)
+
+    # per-kernel device times: same step, eager launches (CUDA graphs off while profiling) with an event pair around
+    # every C-ABI call on the launching stream
+    prof_steps = max(2, min(args.steps, 5))
+    step_resident()
+    ops.profile_begin()
+    timed(step_resident, prof_steps)
+    prof = ops.profile_end()
+
+    llm = None
+    if rank == 0 and world == 1 and not args.no_llm:
+        llm = _llm_leg(dev, head, head.last_output.hidden.clone(), max(2, args.steps // 4))
 
     if rank == 0:
         peaks = _peaks()
@@ -232,27 +291,34 @@ def run_ours(args):
         x = prof.get("xattn_pairs", {"ms": 0.0, "flops": 0.0, "n": 1})
         total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
 
-        def roof(rec, peak_tf):
+        def roof(name, rec, peak_tf):
             ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12 if rec["ms"] > 0 else 0.0
             return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": None, "launches": rec["n"], "avg_launch_ms": rec["ms"] / max(1, rec["n"]),
-                    "share_of_kernel_time": rec["ms"] / total_kernel_ms, "peak_source": peaks["src"] + " (sustained bf16)"}
+                    "traffic": NCU_TRAFFIC_BYTES.get(name), "launches": rec["n"], "avg_launch_ms": rec["ms"] / max(1, rec["n"]),
+                    "algorithmic_flops_per_launch": rec["flops"] / max(1, rec["n"]),
+                    "share_of_kernel_time": rec["ms"] / total_kernel_ms, "peak_source": peaks["src"] + " (sustained bf16 cuBLAS)"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"cfg2 x {ips} images per rank per step (cfg4 sharding): 1024x1024, 40 objects, "
                                    "1600 pair queries, 256 image tokens, relation-query Q-Former + existence filter (a2-a8)",
                        "images_per_step_per_rank": ips, "parallelism": f"image-shard x{world}",
-                       "l2": "inputs larger than L2 (4 x 67 MB feature maps + >100 MB activations per image)"},
+                       "l2": "inputs larger than L2 (4 x 67 MB feature maps + >100 MB activations per image)",
+                       "launch": "one CUDA-graph replay per image (per-kernel times below come from an eager pass of the same step)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "head.forward_batch(list of host input dicts): pinned-host H2D of image i+1 overlaps image i",
+                    "ms_per_step_single_calls": ms_e2e_single,
+                    "value_single_calls": pairs_per_step / (ms_e2e_single * 1e-3)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": roof(g, peaks["tf_sustained"]),
-            "roofline_xattn": roof(x, peaks["tf_sustained"]),
-            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+            "roofline": roof("gemm_bf16", g, peaks["tf_sustained"]),
+            "roofline_xattn": roof("xattn_pairs", x, peaks["tf_sustained"]),
+            "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
         }
+        if llm is not None:
+            line["relation_tokens_per_sec"] = llm
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
@@ -264,12 +330,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-step", type=int, default=4)
     ap.add_argument("--ref-sample", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-llm", action="store_true", help="skip the cfg3 LLM leg (relation_tokens_per_sec)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

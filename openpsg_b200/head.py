@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from .categories import INSTANCE_OFFSET, object_categories, relation_categories
 from .registry import HEADS, BaseModule
-from .relation_qformer import N_QUERY, PackedQFormer, RelationQueryTransformer
+from .relation_qformer import GraphedRelationQuery, N_QUERY, PackedQFormer, RelationQueryTransformer
 
 
 class _PatchEmbed(nn.Module):
@@ -116,6 +116,7 @@ class RelationTransformerHeadV4(BaseModule):
                  qformer_tokenizer=None,
                  llm_tokenizer=None,
                  language_model=None,
+                 use_cuda_graphs=True,
                  **kwargs):
         super().__init__()
         from transformers import InstructBlipQFormerConfig, InstructBlipQFormerModel
@@ -139,6 +140,7 @@ class RelationTransformerHeadV4(BaseModule):
         self.max_object_num = max_object_num
         self.topk_pairs = topk_pairs
         self.max_new_tokens = max_new_tokens
+        self.use_cuda_graphs = use_cuda_graphs
         if qformer_feature_size != 768 or object_feature_size != 256:
             raise NotImplementedError("libopsg_b200 kernels are built for the reference sizes (768 / 256)")
 
@@ -195,14 +197,16 @@ class RelationTransformerHeadV4(BaseModule):
         sd = {k: v for k, v in self.state_dict().items() if not k.startswith("language_model.")}
         self._packed = PackedQFormer(sd, device, num_layers=self.qformer_layer_num, patch=self.patch_size)
         self._engine = RelationQueryTransformer(self._packed)
+        self._graphs = GraphedRelationQuery(self._engine)
         self._llm_engine = None
         if self.language_model is not None:
             from .llm import build_llm_engine
-            self._llm_engine = build_llm_engine(self.language_model, self.language_projection, device)
+            self._llm_engine = build_llm_engine(self.language_model, self.language_projection, device,
+                                                use_cuda_graphs=self.use_cuda_graphs)
         return self
 
     def _load_from_state_dict(self, *a, **k):   # weights changed -> drop the packed copy
-        self._packed = self._engine = self._llm_engine = None
+        self._packed = self._engine = self._llm_engine = self._graphs = None
         return super()._load_from_state_dict(*a, **k)
 
     # ------------------------------------------------------------------------------------------------
@@ -220,25 +224,98 @@ class RelationTransformerHeadV4(BaseModule):
         with torch.no_grad():
             return self._forward_test(image_feature, meta_info, inputs['object_info'][0], is_generation)
 
-    def _forward_test(self, image_feature, meta_info, object_info, is_generation):
+    @torch.no_grad()
+    def forward_batch(self, inputs_list, is_generation=None, on_result=None):
+        """Extension of the batch-1 reference API: a list of test-mode input dicts -> list of result
+        dicts.  ALL host->device traffic of image i+1 (feature map, panoptic map, object ids, instruction token ids)
+        is issued on a side stream while image i computes; pin the host tensors to make the copies asynchronous.
+        ``on_result(head)`` is called after every image (e.g. to read ``head.last_output`` before the next image
+        overwrites it)."""
+        if is_generation is None:
+            is_generation = True
         if self._engine is None:
-            self.repack(image_feature.device)
-        dev = image_feature.device
+            self.repack(None)
+        dev = self._packed.device
+        cur = torch.cuda.current_stream(dev)
+        copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=dev)
+        self._copy_stream = copy_stream
+
+        def prefetch(inp):
+            prep = self._prepare_host(inp)
+            copy_stream.wait_stream(cur)
+            with torch.cuda.stream(copy_stream):
+                self._to_device(prep, dev)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return prep, ev
+
+        results = []
+        nxt = prefetch(inputs_list[0]) if inputs_list else None
+        for i in range(len(inputs_list)):
+            prep, ev = nxt
+            # the next image's copies go out before this image's kernels are enqueued: nothing of image i queues
+            # behind them on a copy engine (its inputs are already resident)
+            nxt = prefetch(inputs_list[i + 1]) if i + 1 < len(inputs_list) else None
+            cur.wait_event(ev)
+            for t in prep["device"].values():
+                t.record_stream(cur)
+            results.append(self._run(prep, is_generation))
+            if on_result is not None:
+                on_result(self)
+        return results
+
+    def _forward_test(self, image_feature, meta_info, object_info, is_generation):
+        prep = self._prepare_host(dict(mask_features=image_feature, img_metas=[meta_info], object_info=[object_info]))
+        self._to_device(prep, self._packed.device)
+        return self._run(prep, is_generation)
+
+    # -- stage 1 (host): object parse, pair enumeration, instruction ids (v4:134-152) -------------------------------
+    def _prepare_host(self, inputs):
+        image_feature = inputs['mask_features']
+        assert image_feature.shape[0] == 1, 'only support batch size 1 for now.'
+        if self._engine is None:
+            self.repack(image_feature.device if image_feature.is_cuda else None)
+        meta_info, object_info = inputs['img_metas'][0], inputs['object_info'][0]
         object_id_list = object_info['object_id_list'][:self.max_object_num]          # v4:136
         n = len(object_id_list)
-        ids_dev = torch.stack([torch.as_tensor(x).reshape(()) for x in object_id_list]).to(device=dev, dtype=torch.int32)
-        ids_host = ids_dev.cpu().numpy()                                                # one D2H (ref: N .item() calls)
+        ids_any = torch.stack([torch.as_tensor(x).reshape(()) for x in object_id_list])
+        ids_host = ids_any.cpu().numpy().astype(np.int32)                               # one D2H (ref: N .item() calls)
         cats = (ids_host % INSTANCE_OFFSET).astype(np.int64)                            # v4:138
-        B = n * n
-        p = np.arange(B)
-        sub, obj = p // n, p % n                                                        # v4:147-148
-        q_ids, q_mask = self._qformer_cache.lookup(cats[sub], cats[obj])
-        q_ids = q_ids.pin_memory().to(dev, non_blocking=True)
-        q_mask = q_mask.pin_memory().to(dev, non_blocking=True)
-        pan = object_info['pan_results'].to(device=dev, dtype=torch.int32)
-        feat = image_feature[0].float()
-        out = self._engine.forward(feat, pan, meta_info['img_shape'][:2], meta_info['pad_shape'][:2], ids_dev,
-                                   q_ids, q_mask, topk=self.topk_pairs, threshold=self.pair_selector_threshold)
+        p = np.arange(n * n)
+        q_ids, q_mask = self._qformer_cache.lookup(cats[p // n], cats[p % n])           # v4:147-152
+        # T padded to a multiple of 4 with masked tokens (weight exactly 0 as keys, dead rows as queries) so that
+        # images whose longest instruction differs by a token share a CUDA graph
+        pad_t = (-q_ids.shape[1]) % 4
+        if pad_t:
+            q_ids = torch.nn.functional.pad(q_ids, (0, pad_t), value=self._qformer_cache.pad_id)
+            q_mask = torch.nn.functional.pad(q_mask, (0, pad_t), value=0)
+        return dict(n=n, cats=cats, img_hw=meta_info['img_shape'][:2], pad_hw=meta_info['pad_shape'][:2],
+                    host=dict(feat=image_feature[0], pan=object_info['pan_results'], obj_ids=torch.from_numpy(ids_host),
+                              q_ids=q_ids, q_mask=q_mask))
+
+    # -- stage 2: every input on the device (on the CURRENT stream) --------------------------------------------------
+    def _to_device(self, prep, dev):
+        want = dict(feat=torch.float32, pan=torch.int32, obj_ids=torch.int32, q_ids=torch.int32, q_mask=torch.int32)
+        out = {}
+        for name, t in prep["host"].items():
+            if not t.is_cuda and not t.is_pinned() and t.numel() < (1 << 20):
+                t = t.pin_memory()                                                      # small id tensors: make the copy async
+            out[name] = t.to(device=dev, dtype=want[name], non_blocking=True)
+        prep["device"] = out
+        return prep
+
+    # -- stage 3: kernels ---------------------------------------------------------------------------------------------
+    def _run(self, prep, is_generation):
+        from . import ops as _ops
+        d = prep["device"]
+        n, cats = prep["n"], prep["cats"]
+        dev = self._packed.device
+        if self.use_cuda_graphs and _ops._profile is None:
+            out = self._graphs.run(d["feat"], d["pan"], prep["img_hw"], prep["pad_hw"], d["obj_ids"], d["q_ids"], d["q_mask"],
+                                   topk=self.topk_pairs, threshold=self.pair_selector_threshold)
+        else:
+            out = self._engine.forward(d["feat"], d["pan"], prep["img_hw"], prep["pad_hw"], d["obj_ids"], d["q_ids"],
+                                       d["q_mask"], topk=self.topk_pairs, threshold=self.pair_selector_threshold)
         self.last_output = out
         rel_pred: List[List[int]] = []
         rel_score: List[float] = []

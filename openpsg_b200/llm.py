@@ -86,11 +86,13 @@ class GenerationOutput:
 class OPTDecodeEngine:
     LN_EPS = 1e-5
 
-    def __init__(self, weights: PackedOPT, w_proj: torch.Tensor, b_proj: torch.Tensor):
+    def __init__(self, weights: PackedOPT, w_proj: torch.Tensor, b_proj: torch.Tensor, use_cuda_graphs: bool = True):
         self.w = weights
         self.w_proj, self.b_proj = w_proj, b_proj      # language_projection (v4:97): bf16 [d_llm, 768], fp32 [d_llm]
         if w_proj.shape[0] != weights.d:
             raise ValueError(f"language_projection out_features {w_proj.shape[0]} != LLM hidden size {weights.d}")
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs = {}          # (hidden shape, k, T, max_new_tokens) -> captured generate()
 
     # one decoder layer over `rows` = nseq * q_len token rows; h is updated in place
     def _layer(self, lw, h, k_cache, v_cache, key_mask, nseq, q_len, pos0):
@@ -116,9 +118,51 @@ class OPTDecodeEngine:
     def generate(self, hidden: torch.Tensor, selected: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,
                  max_new_tokens: int = 16, return_scores: bool = False,
                  forced_tokens: Optional[torch.Tensor] = None) -> GenerationOutput:
-        """hidden bf16 [B*33, 768] (Q-Former output rows, pair-major); selected int32 [k] pair indices;
-        llm_ids / llm_mask int32 [k, T] left-padded prompt tokens (v4:260-266).  ``forced_tokens`` int32 [k, T_new]
-        teacher-forces the fed-back ids (parity tests: keeps our run on the oracle's trajectory)."""
+        """Greedy relation decode for the selected pairs.  The plain call replays one CUDA graph holding the whole
+        prefill + decode loop (~300 launches per step; the loop has no host synchronisation); ``return_scores`` /
+        ``forced_tokens`` (parity tests) and profiling runs execute eagerly."""
+        if not self.use_cuda_graphs or return_scores or forced_tokens is not None or ops._profile is not None:
+            return self._generate(hidden, selected, llm_ids, llm_mask, max_new_tokens, return_scores, forced_tokens)
+        dev = hidden.device
+        key = (tuple(hidden.shape), tuple(llm_ids.shape), int(max_new_tokens))
+        e = self._graphs.get(key)
+        if e is None:
+            if len(self._graphs) >= 2:
+                self._graphs.pop(next(iter(self._graphs)))
+            e = dict(hidden=torch.empty_like(hidden),
+                     selected=torch.empty(tuple(selected.shape), dtype=torch.int32, device=dev),
+                     ids=torch.empty(tuple(llm_ids.shape), dtype=torch.int32, device=dev),
+                     mask=torch.empty(tuple(llm_mask.shape), dtype=torch.int32, device=dev))
+            for name, src in (("hidden", hidden), ("selected", selected), ("ids", llm_ids), ("mask", llm_mask)):
+                e[name].copy_(src)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._generate(e["hidden"], e["selected"], e["ids"], e["mask"], max_new_tokens, False, None)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count
+            with torch.cuda.graph(graph):
+                out = self._generate(e["hidden"], e["selected"], e["ids"], e["mask"], max_new_tokens, False, None)
+            e.update(graph=graph, out=out, launches=ops.launch_count - l0)
+            self._graphs[key] = e
+        if e["hidden"].data_ptr() != hidden.data_ptr():
+            e["hidden"].copy_(hidden, non_blocking=True)
+        e["selected"].copy_(selected, non_blocking=True)
+        e["ids"].copy_(llm_ids, non_blocking=True)
+        e["mask"].copy_(llm_mask, non_blocking=True)
+        e["graph"].replay()
+        ops._count(e["launches"])
+        return e["out"]
+
+    def _generate(self, hidden: torch.Tensor, selected: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,
+                  max_new_tokens: int = 16, return_scores: bool = False,
+                  forced_tokens: Optional[torch.Tensor] = None) -> GenerationOutput:
+        # hidden bf16 [B*33, 768] (Q-Former output rows, pair-major); selected int32 [k] pair indices;
+        # llm_ids / llm_mask int32 [k, T] left-padded prompt tokens (v4:260-266).  forced_tokens int32 [k, T_new]
+        # teacher-forces the fed-back ids (parity tests: keeps our run on the oracle's trajectory).
         w = self.w
         dev = hidden.device
         k, T = llm_ids.shape
@@ -176,7 +220,8 @@ class OPTDecodeEngine:
         return GenerationOutput(tokens=tokens.t().contiguous(), scores=scores, prefix=prefix)
 
 
-def build_llm_engine(language_model, language_projection, device):
+def build_llm_engine(language_model, language_projection, device, use_cuda_graphs: bool = True):
     """Pack ``language_model`` (HF OPTForCausalLM) and ``language_projection`` (nn.Linear) for the kernels."""
     weights = PackedOPT(language_model, device)
-    return OPTDecodeEngine(weights, _bf16(language_projection.weight, device), _f32(language_projection.bias, device))
+    return OPTDecodeEngine(weights, _bf16(language_projection.weight, device), _f32(language_projection.bias, device),
+                           use_cuda_graphs=use_cuda_graphs)

@@ -100,6 +100,79 @@ class RelationQueryOutput:
     intermediates: Optional[dict] = None
 
 
+class GraphedRelationQuery:
+    """CUDA-graph replay of ``RelationQueryTransformer.forward`` per input-shape signature.
+
+    The per-image pipeline is ~100 launches of 5-500 us kernels; replaying it as one graph removes the launch gaps
+    (measured 11 % of the step on cfg2) without touching the arithmetic.  Inputs are copied into static buffers
+    (``copy_`` also performs the host->device transfer / dtype conversion when the caller's tensors live on the
+    host), outputs are the static tensors of the captured run: they are overwritten by the next call with the same
+    signature, so callers that keep results across calls must clone them."""
+
+    def __init__(self, engine: "RelationQueryTransformer", max_entries: int = 4):
+        self.engine = engine
+        self.max_entries = max_entries
+        self.entries: Dict[tuple, dict] = {}
+
+    def run(self, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, *, topk: int, threshold: float):
+        dev = self.engine.w.device
+        key = (tuple(feat.shape), tuple(pan.shape), tuple(int(x) for x in img_hw), tuple(int(x) for x in pad_hw),
+               int(obj_ids.numel()), tuple(input_ids.shape), int(topk), float(threshold))
+        e = self.entries.get(key)
+        if e is None:
+            if len(self.entries) >= self.max_entries:          # drop the oldest signature (frees its private pool)
+                self.entries.pop(next(iter(self.entries)))
+            e = self._capture(key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev)
+            self.entries[key] = e
+        for name, src in (("feat", feat), ("pan", pan), ("obj_ids", obj_ids), ("input_ids", input_ids), ("text_mask", text_mask)):
+            self._stage(e[name], src)
+        e["graph"].replay()
+        ops._count(e["launches"])
+        return e["out"]
+
+    @staticmethod
+    def _stage(dst, src):
+        """Copy into a static graph input.  Device-resident sources of the same dtype go through an elementwise KERNEL
+        instead of cudaMemcpyAsync: a copy-engine D2D copy would queue behind an in-flight host->device prefetch of the
+        next image and serialise the pipeline of ``forward_batch``."""
+        if src.is_cuda and src.dtype == dst.dtype and src.shape == dst.shape:
+            if dst.is_floating_point():
+                torch.mul(src, 1.0, out=dst)
+            else:
+                torch.add(src, 0, out=dst)
+        else:
+            dst.copy_(src, non_blocking=True)
+
+    def _capture(self, key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev):
+        st = dict(
+            feat=torch.empty(tuple(feat.shape), dtype=torch.float32, device=dev),
+            pan=torch.empty(tuple(pan.shape), dtype=torch.int32, device=dev),
+            obj_ids=torch.empty(tuple(obj_ids.shape), dtype=torch.int32, device=dev),
+            input_ids=torch.empty(tuple(input_ids.shape), dtype=torch.int32, device=dev),
+            text_mask=torch.empty(tuple(text_mask.shape), dtype=torch.int32, device=dev),
+        )
+        for name, src in (("feat", feat), ("pan", pan), ("obj_ids", obj_ids), ("input_ids", input_ids), ("text_mask", text_mask)):
+            st[name].copy_(src)
+
+        def run():
+            return self.engine.forward(st["feat"], st["pan"], img_hw, pad_hw, st["obj_ids"], st["input_ids"], st["text_mask"],
+                                       topk=topk, threshold=threshold)
+
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up outside capture: first-use cudaFuncSetAttribute calls, allocator
+            run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count
+        with torch.cuda.graph(graph):
+            out = run()
+        st.update(graph=graph, out=out, launches=ops.launch_count - l0)
+        return st
+
+
 class RelationQueryTransformer:
     def __init__(self, weights: PackedQFormer):
         self.w = weights

@@ -130,3 +130,39 @@ def test_subset_of_pairs_equals_full_run(head):
                       pair_index=idx.cuda(), topk=5)
     sub = out.hidden.float().cpu().reshape(5, 33, 768)
     assert (sub - full[idx.long()]).abs().max() < 2e-2     # same arithmetic, different tile packing
+
+
+def test_graph_replay_and_forward_batch_equal_eager():
+    """CUDA-graph replay (default) and the pipelined host-input batch entry give the same results as eager launches.
+    (PatchEmbed's split-K uses fp32 atomics, so two runs agree to rounding, not bit-for-bit: a one-ulp flip of a bf16
+    activation in [2, 4) is already 0.016, hence max 6e-2 / mean 2e-3 on the output rows.)"""
+    eager = build_product_head(device="cuda:0")
+    eager.use_cuda_graphs = False
+    graphed = build_product_head(device="cuda:0")
+    wl = synth.WORKLOADS["cfg1"]
+    host = [synth.make_image_inputs(wl, i) for i in range(3)]
+    for inp in host:
+        inp["mask_features"] = inp["mask_features"].pin_memory()
+        inp["object_info"][0]["pan_results"] = inp["object_info"][0]["pan_results"].pin_memory()
+    ref = []
+    for inp in host:
+        eager(synth.inputs_to(inp, "cuda:0"))
+        o = eager.last_output
+        ref.append((o.hidden.float().cpu(), o.logits.cpu(), o.topk.cpu().tolist(), o.exist_mask.cpu()))
+    # device-resident inputs, one graph replayed for all three images (same signature)
+    for inp, (h, z, top, m) in zip(host, ref):
+        graphed(synth.inputs_to(inp, "cuda:0"))
+        o = graphed.last_output
+        dh = (o.hidden.float().cpu() - h).abs()
+        assert dh.max() < 6e-2 and dh.mean() < 2e-3, (dh.max(), dh.mean())
+        assert (o.logits.cpu() - z).abs().max() < 5e-3
+        assert torch.equal(o.exist_mask.cpu()[z.abs() > 1e-2], m[z.abs() > 1e-2])
+    assert len(graphed._graphs.entries) == 1
+    # host-resident (pinned) inputs through the pipelined batch entry
+    got = []
+    res = graphed.forward_batch(host, on_result=lambda hd: got.append((hd.last_output.logits.cpu(), hd.last_output.topk.cpu().tolist())))
+    assert len(res) == 3 and all(set(r) == {"rel_pred", "rel_score"} for r in res)
+    for (z, top), (h, zr, topr, m) in zip(got, ref):
+        assert (z - zr).abs().max() < 5e-3
+        ok, diff = margin_set_equal(top, zr, 20, 5e-3)
+        assert ok, diff
