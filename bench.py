@@ -181,6 +181,11 @@ def _llm_leg(dev, head, hidden, steps):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     peaks = _peaks()
+    # per-kernel device time of one image (eager launches, an event pair around every C-ABI call)
+    from openpsg_b200 import ops
+    ops.profile_begin()
+    eng.generate(hidden, sel, ids, mask, max_new_tokens=T_new)
+    prof = ops.profile_end()
     # HBM floor of the decode: every step streams the weights once for the whole batch (+ the KV cache, ignored here)
     decode_bytes = (T_new - 1) * weight_bytes
     return {"value": k * T_new / (ms * 1e-3), "unit": "tokens/s", "ms_per_image": ms,
@@ -188,6 +193,8 @@ def _llm_leg(dev, head, hidden, steps):
                                    "(32 layers, d 2560), batched prefill + greedy decode as one CUDA graph", "pairs": k,
                        "new_tokens": T_new},
             "tokens_checksum": int(toks.long().sum()), "model_init_s": init_s,
+            "kernel_ms_per_image": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+            "kernel_launches_per_image": {k: v["n"] for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "roofline": {"bound": "hbm", "achieved": decode_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                          "frac": decode_bytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
                          "note": "weight bytes of the 31 decode steps / whole prefill+decode time (lower bound on achieved)"}}

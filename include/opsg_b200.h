@@ -72,6 +72,17 @@ int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, voi
                    const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, int out_mode,
                    int k_splits, void* stream);
 
+/* Small-M variant for weight-streaming GEMMs (LLM decode: M = number of selected pairs <= 128, OPT q/k/v/out/fc1/
+ * fc2/lm_head of one decode step; v4:305-312).  Same operands and epilogue as opsg_gemm_bf16 (bias along N only),
+ * but the flattened (N-tile, K-block) space is cut into one equal contiguous range per SM ("stream-K"), so every SM
+ * streams the same number of weight bytes from HBM whatever N is; fp32 partial tiles go through a caller-provided
+ * workspace of opsg_gemm_streamk_workspace_bytes(N, K) bytes and a fix-up kernel applies bias / residual /
+ * activation.  Deterministic (no atomics).  out_mode: OPSG_OUT_BF16 or OPSG_OUT_F32. */
+size_t opsg_gemm_streamk_workspace_bytes(int N, int K);
+int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M, int N,
+                           int K, const float* bias, const opsg_bf16* residual, int ldr, int act, int out_mode,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* fp32 [rows, cols] (ld_in) -> bf16 (ld_out); init_rows_f32 broadcasts a row vector (bias) into [rows, cols]. */
 int opsg_cast_f32_bf16(const float* in, int ld_in, opsg_bf16* out, int ld_out, int rows, int cols, void* stream);
 int opsg_init_rows_f32(float* out, int ld_out, const float* row, int rows, int cols, void* stream);

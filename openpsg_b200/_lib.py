@@ -27,6 +27,8 @@ SIGNATURES = {
     "opsg_pair_mask_bits": [P, I, I, I, I, I, I, I, I, P, I, P, I, P],
     "opsg_patch_im2col": [P, I, I, I, I, P, P],
     "opsg_gemm_bf16": [P, I, P, I, P, I, I, I, I, P, I, P, I, I, I, I, P],
+    "opsg_gemm_streamk_workspace_bytes": [I, I],
+    "opsg_gemm_bf16_streamk": [P, I, P, I, P, I, I, I, I, P, P, I, I, I, P, ctypes.c_size_t, P],
     "opsg_cast_f32_bf16": [P, I, P, I, I, I, P],
     "opsg_init_rows_f32": [P, I, P, I, I, P],
     "opsg_qformer_embed_ln": [P, I, P, I, I, P, I, P, P, P, F, I, P, P],
@@ -71,7 +73,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = (c_char_p if name == "opsg_last_error_string"
-                      else ctypes.c_size_t if name == "opsg_xattn_bias_tiles_bytes" else c_int)
+                      else ctypes.c_size_t if name in ("opsg_xattn_bias_tiles_bytes", "opsg_gemm_streamk_workspace_bytes")
+                      else c_int)
     _lib = lib
     return lib
 

@@ -2,8 +2,9 @@
 // pair; OPT prefill / decode attention over a static KV cache, context <= 128).
 //
 // These problems are tiny and independent (B * heads of them, <= 64 x 128 scores each): one CTA per
-// (sequence, head), whole K / V^T / Q tile in shared memory, register-resident FlashAttention-2 style softmax
-// on warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  They carry ~1% of the path's FLOPs; the big
+// (sequence, head), whole K / V / Q tile in shared memory (row-major, 16-byte copies; the PV B fragments come
+// from ldmatrix.trans, so V is never transposed through memory), register-resident FlashAttention-2 style
+// softmax on warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  They carry ~1% of the path's FLOPs; the big
 // tensor-core work (GEMMs, pair cross-attention) is on tcgen05 — packing several sequences per 128-row tcgen05
 // tile with a block-diagonal mask is the planned upgrade for this kernel.
 #include "common.cuh"
@@ -36,6 +37,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// four transposed 8x8 b16 matrices: lanes 0-7 / 8-15 / 16-23 / 24-31 give the row addresses of matrix 0 / 1 / 2 / 3
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -47,12 +55,12 @@ template <int HD, int NK>
 __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p) {
   constexpr int QS = HD + 8;      // padded row strides (elements) -> conflict-free fragment loads
   constexpr int KS = HD + 8;
-  constexpr int VS = NK + 8;
+  constexpr int VS = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_dyn);      // [64][QS]
   __nv_bfloat16* sK = sQ + 64 * QS;                                     // [NK][KS]
-  __nv_bfloat16* sVt = sK + NK * KS;                                    // [HD][VS]
-  uint8_t* sValid = reinterpret_cast<uint8_t*>(sVt + HD * VS);          // [NK]
+  __nv_bfloat16* sV = sK + NK * KS;                                     // [NK][VS] row-major (keys x head dims)
+  uint8_t* sValid = reinterpret_cast<uint8_t*>(sV + NK * VS);           // [NK]
 
   const int seq = blockIdx.x, head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,9 +92,7 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
       }
     }
     *reinterpret_cast<uint4*>(sK + key * KS + v8 * 8) = ku;
-    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vu);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sVt[(v8 * 8 + e) * VS + key] = ve[e];
+    *reinterpret_cast<uint4*>(sV + key * VS + v8 * 8) = vu;
   }
   for (int key = threadIdx.x; key < NK; key += blockDim.x) {
     bool ok = key < n_keys;
@@ -176,10 +182,15 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
       a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
       a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      // B fragments of V[kk*16 .. +16][n*8 .. +8] for two adjacent n-tiles per ldmatrix.x4.trans:
+      // lanes 0-15 address the 16 key rows at column n0, lanes 16-31 the same rows at column n0 + 8
+      const __nv_bfloat16* vrow = sV + (kk * 16 + (lane & 15)) * VS + ((lane >> 4) << 3);
 #pragma unroll
-      for (int n = 0; n < HD / 8; ++n) {
-        const __nv_bfloat16* vr = sVt + (n * 8 + g) * VS + kk * 16 + 2 * t;
-        mma_bf16_16816(o[n], a, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+      for (int n = 0; n < HD / 8; n += 2) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, vrow + n * 8);
+        mma_bf16_16816(o[n], a, b[0], b[1]);
+        mma_bf16_16816(o[n + 1], a, b[2], b[3]);
       }
     }
     const float inv0 = 1.f / l0, inv1 = 1.f / l1;
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
 
 template <int HD, int NK>
 static int launch_small_attn(const SmallAttnParams& p, int nseq, cudaStream_t st) {
-  constexpr int smem = (64 * (HD + 8) + NK * (HD + 8) + HD * (NK + 8)) * 2 + NK;
+  constexpr int smem = (64 * (HD + 8) + 2 * NK * (HD + 8)) * 2 + NK;
   static bool configured = false;
   if (!configured) {
     int rc = check_cuda(cudaFuncSetAttribute(small_attn_kernel<HD, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
@@ -231,6 +242,126 @@ static int dispatch_hd(const SmallAttnParams& p, int nseq, int n_keys, int head_
     case 128: return dispatch_nk<128>(p, nseq, n_keys, st);
     default: return set_error(OPSG_E_UNSUPPORTED, "small attention: head_dim %d unsupported (64, 80, 128)", head_dim);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10b — decode attention (q_len == 1): one warp per (sequence, head), no tensor cores (a 1 x ctx x head_dim problem is
+// a pair of GEMVs).  HBM-bound: reads the sequence's K / V head slices once (ctx x head_dim x 2 x 2 bytes).
+// A key's head slice (HD bf16) is covered by HD/8 lanes with one 16-byte load each; LPK = 8 or 16 lanes form a key
+// group, so a warp handles 32/LPK keys per iteration and 16 iterations' loads are in flight at once (the first cut of
+// this kernel walked the keys one at a time in the PV phase and took 37 us per launch, latency-bound).
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams p) {
+  constexpr int kWarps = 8;
+  constexpr int kMaxCtx = 128;
+  constexpr int LPK = (HD / 8 <= 8) ? 8 : 16;              // lanes per key (power of two >= HD / 8)
+  constexpr int KPW = 32 / LPK;                             // keys per warp iteration
+  constexpr int CH = 16;                                    // iterations whose loads are issued back to back
+  __shared__ float s_p[kWarps][kMaxCtx];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarps + warp;             // (sequence, head)
+  const int nseq_heads = p.B;                               // field reused by the launcher: nseq * num_heads
+  if (item >= nseq_heads) return;
+  const int seq = item / p.num_heads, head = item % p.num_heads;
+  const int ctx = p.q_pos0 + 1;                             // keys 0 .. q_pos0 (causal, the new token included)
+  const int sub = lane % LPK, grp = lane / LPK;
+  const bool active = sub < HD / 8;
+  const __nv_bfloat16* kbase = p.k_cache + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD + sub * 8;
+  const __nv_bfloat16* vbase = p.v_cache + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD + sub * 8;
+  const uint8_t* kmask = p.key_mask + static_cast<size_t>(seq) * p.max_ctx;
+  float q8[8];
+  {
+    uint4 qv = make_uint4(0, 0, 0, 0);
+    if (active) qv = __ldg(reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(seq) * p.ld_q + head * HD + sub * 8));
+    q8[0] = bf16_lo(qv.x); q8[1] = bf16_hi(qv.x); q8[2] = bf16_lo(qv.y); q8[3] = bf16_hi(qv.y);
+    q8[4] = bf16_lo(qv.z); q8[5] = bf16_hi(qv.z); q8[6] = bf16_lo(qv.w); q8[7] = bf16_hi(qv.w);
+  }
+  // ---- scores ----------------------------------------------------------------------------------------
+  for (int k0 = 0; k0 < ctx; k0 += CH * KPW) {
+    uint4 kv[CH];
+    bool ok[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int key = k0 + i * KPW + grp;
+      // the K load does not wait for the mask byte: both are issued together, the mask only gates the score
+      kv[i] = (key < ctx && active) ? __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(key) * p.d_model))
+                                    : make_uint4(0, 0, 0, 0);
+      ok[i] = key < ctx && __ldg(kmask + min(key, p.max_ctx - 1)) != 0;
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      float d = bf16_lo(kv[i].x) * q8[0] + bf16_hi(kv[i].x) * q8[1] + bf16_lo(kv[i].y) * q8[2] + bf16_hi(kv[i].y) * q8[3] +
+                bf16_lo(kv[i].z) * q8[4] + bf16_hi(kv[i].z) * q8[5] + bf16_lo(kv[i].w) * q8[6] + bf16_hi(kv[i].w) * q8[7];
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      const int key = k0 + i * KPW + grp;
+      if (sub == 0 && key < kMaxCtx) s_p[warp][key] = ok[i] ? d : -INFINITY;
+    }
+  }
+  __syncwarp();
+  // ---- softmax over the ctx scores (lane-strided) --------------------------------------------------------
+  float sc[kMaxCtx / 32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < kMaxCtx / 32; ++r) {
+    const int key = r * 32 + lane;
+    sc[r] = key < ctx ? s_p[warp][key] : -INFINITY;
+    mx = fmaxf(mx, sc[r]);
+  }
+  mx = warp_max(mx);
+  if (mx == -INFINITY) mx = 0.f;
+  float sum = 0.f;
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < kMaxCtx / 32; ++r) {
+    const float e = ex2f((sc[r] - mx) * p.scale_log2e);      // exp2(-inf) = 0 for masked / out-of-range keys
+    // P is rounded to bf16 like the tensor-core path (and HF's bf16 softmax output) before multiplying V
+    s_p[warp][r * 32 + lane] = __bfloat162float(__float2bfloat16(e));
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  // ---- context ---------------------------------------------------------------------------------------
+  float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < ctx; k0 += CH * KPW) {
+    uint4 vv[CH];
+    float pj[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int key = k0 + i * KPW + grp;
+      pj[i] = key < ctx ? s_p[warp][key] : 0.f;
+      vv[i] = (pj[i] != 0.f && active) ? __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(key) * p.d_model))
+                                       : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      o8[0] = fmaf(pj[i], bf16_lo(vv[i].x), o8[0]); o8[1] = fmaf(pj[i], bf16_hi(vv[i].x), o8[1]);
+      o8[2] = fmaf(pj[i], bf16_lo(vv[i].y), o8[2]); o8[3] = fmaf(pj[i], bf16_hi(vv[i].y), o8[3]);
+      o8[4] = fmaf(pj[i], bf16_lo(vv[i].z), o8[4]); o8[5] = fmaf(pj[i], bf16_hi(vv[i].z), o8[5]);
+      o8[6] = fmaf(pj[i], bf16_lo(vv[i].w), o8[6]); o8[7] = fmaf(pj[i], bf16_hi(vv[i].w), o8[7]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) o8[e] += __shfl_xor_sync(0xffffffffu, o8[e], o);
+  }
+  if (grp == 0 && active) {
+    const float inv = 1.f / sum;
+    uint4 u;
+    u.x = pack_bf16x2(o8[0] * inv, o8[1] * inv); u.y = pack_bf16x2(o8[2] * inv, o8[3] * inv);
+    u.z = pack_bf16x2(o8[4] * inv, o8[5] * inv); u.w = pack_bf16x2(o8[6] * inv, o8[7] * inv);
+    *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq) * p.ld_out + head * HD + sub * 8) = u;
+  }
+}
+
+template <int HD>
+static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
+  p.B = nseq * p.num_heads;
+  decode_attn_kernel<HD><<<(p.B + 7) / 8, 256, 0, st>>>(p);
+  OPSG_CHECK_LAUNCH("decode_attn_kernel");
+  return OPSG_OK;
 }
 
 __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model,
@@ -286,6 +417,13 @@ extern "C" int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_ca
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ld_out = ld_out; p.num_heads = num_heads; p.d_model = num_heads * head_dim;
   p.scale_log2e = 1.4426950408889634f * scale;
+  if (q_len == 1 && q_pos0 + 1 <= 128 && (head_dim == 64 || head_dim == 80 || head_dim == 128) && (ld_q % 8) == 0 &&
+      (ld_out % 8) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)q & 15) == 0) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);     // decode step: GEMV-style kernel, one warp per (seq, head)
+    if (head_dim == 64) return launch_decode_attn<64>(p, nseq, st);
+    if (head_dim == 80) return launch_decode_attn<80>(p, nseq, st);
+    return launch_decode_attn<128>(p, nseq, st);
+  }
   return dispatch_hd(p, nseq, q_pos0 + q_len, head_dim, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -39,6 +39,54 @@ struct GemmParams {
   int k_splits;
   int m_tiles, n_tiles;
   int tma_store;
+  int stream_k;      // 1: contiguous (tile, k-block) ranges per CTA, fp32 partial tiles to `ws` (small-M weight streaming)
+  int max_segs;      // stream-K: partial-tile slots per CTA
+  float* ws;         // stream-K workspace: [grid * max_segs][128][BN] fp32
+};
+
+// One unit of work of a CTA: a (m_t, n_t) output tile and the K blocks [kb0, kb1) it accumulates.
+//  * static mode : whole tiles (or k_splits slices), tile index = blockIdx.x + i * gridDim.x;
+//  * stream-K    : the flattened (tile, k-block) space is cut into gridDim.x equal contiguous ranges, so every CTA
+//                  streams the same number of weight bytes whatever N is; a range that crosses tile boundaries yields
+//                  several segments, each stored as an fp32 partial tile in slot blockIdx.x * max_segs + j.
+struct GemmSeg { int m_t, n_t, kb0, kb1, slot; };
+struct GemmSegIter {
+  long long u, u_end;
+  int tile, j;
+  __device__ __forceinline__ void init(const GemmParams& p, int kb_total) {
+    j = 0;
+    if (p.stream_k) {
+      const long long U = static_cast<long long>(p.m_tiles) * p.n_tiles * kb_total;
+      u = U * blockIdx.x / gridDim.x;
+      u_end = U * (blockIdx.x + 1) / gridDim.x;
+    } else {
+      tile = blockIdx.x;
+    }
+  }
+  __device__ __forceinline__ bool next(const GemmParams& p, int kb_total, int kb_per_split, GemmSeg& s) {
+    if (p.stream_k) {
+      if (u >= u_end) return false;
+      const int t = static_cast<int>(u / kb_total);
+      s.kb0 = static_cast<int>(u % kb_total);
+      s.kb1 = static_cast<int>(min(static_cast<long long>(kb_total), s.kb0 + (u_end - u)));
+      s.n_t = t % p.n_tiles;
+      s.m_t = t / p.n_tiles;
+      s.slot = blockIdx.x * p.max_segs + j;
+      u += s.kb1 - s.kb0;
+      ++j;
+      return true;
+    }
+    if (tile >= p.m_tiles * p.n_tiles * p.k_splits) return false;
+    s.n_t = tile % p.n_tiles;
+    const int rest = tile / p.n_tiles;
+    s.m_t = rest % p.m_tiles;
+    const int split = rest / p.m_tiles;
+    s.kb0 = min(kb_total, split * kb_per_split);
+    s.kb1 = min(kb_total, s.kb0 + kb_per_split);
+    s.slot = 0;
+    tile += gridDim.x;
+    return true;
+  }
 };
 
 template <int BN, int STAGES>
@@ -94,7 +142,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int kb_total = (p.K + kBK - 1) / kBK;
   const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
 
@@ -102,13 +149,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_t = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      const int m_t = rest % p.m_tiles;
-      const int split = rest / p.m_tiles;
-      const int kb0 = split * kb_per_split;
-      const int kb1 = min(kb_total, kb0 + kb_per_split);
+    GemmSegIter it;
+    GemmSeg sg;
+    it.init(p, kb_total);
+    while (it.next(p, kb_total, kb_per_split, sg)) {
+      const int n_t = sg.n_t, m_t = sg.m_t, kb0 = sg.kb0, kb1 = sg.kb1;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
@@ -127,10 +172,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = (tile / p.n_tiles) / p.m_tiles;
-      const int kb0 = split * kb_per_split;
-      const int kb1 = min(kb_total, kb0 + kb_per_split);
+    GemmSegIter it;
+    GemmSeg sg;
+    it.init(p, kb_total);
+    while (it.next(p, kb_total, kb_per_split, sg)) {
+      const int kb0 = sg.kb0, kb1 = sg.kb1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -170,12 +216,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t buf = 0;
     const __nv_bfloat16* resid = p.residual;
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_t = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      const int m_t = rest % p.m_tiles;
-      const int split = rest / p.m_tiles;
-      const bool has_k = split * kb_per_split < kb_total;
+    GemmSegIter it;
+    GemmSeg sg;
+    it.init(p, kb_total);
+    while (it.next(p, kb_total, kb_per_split, sg)) {
+      const int n_t = sg.n_t, m_t = sg.m_t;
+      const bool has_k = sg.kb0 < sg.kb1;
       const int row = m_t * kBM + row_in_tile;
       const bool row_ok = row < p.M;
       const float bias_m = (p.bias && p.bias_along_m && row_ok) ? p.bias[row] : 0.f;
@@ -264,7 +310,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
 
-        if (p.tma_store) {
+        if (p.stream_k) {
+          // fp32 partial tile -> workspace slot (plain 16-byte stores; 128 contiguous bytes per thread)
+          if (row_ok && has_cols) {
+            float* d = p.ws + (static_cast<size_t>(sg.slot) * kBM + row_in_tile) * BN + slab * SLABW + half * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(d)[j] = make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+          }
+        } else if (p.tma_store) {
           // staging slab `buf`: its previous TMA store (two slabs ago) must have drained before we overwrite it
           if (elected) tma_store_wait_read<1>();
           named_bar_sync(1, kEpiThreads);
@@ -361,9 +415,125 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return OPSG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// stream-K fix-up: D[m, n] = act(bias[n] + sum over the partial tiles covering (tile n / 256) + residual[m, n]).
+// The CTA -> range mapping is recomputed with the same integer arithmetic as GemmSegIter.
+// ------------------------------------------------------------------------------------------------
+struct StreamKReduceParams {
+  const float* ws;
+  void* D;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int M, N, ldd, ldr, act, out_f32;
+  int n_tiles, kb_total, grid, max_segs;
+};
+
+__global__ void __launch_bounds__(256) streamk_reduce_kernel(const StreamKReduceParams p) {
+  constexpr int BN = 256;
+  const int n_t = blockIdx.x;
+  const int c4 = threadIdx.x & 63;                       // 4-column group inside the tile
+  const int col = n_t * BN + c4 * 4;
+  const long long U = static_cast<long long>(p.n_tiles) * p.kb_total;
+  const long long lo = static_cast<long long>(n_t) * p.kb_total, hi = lo + p.kb_total;
+  // CTAs whose range [u0, u1) intersects [lo, hi)
+  int c_first = static_cast<int>(lo * p.grid / U);
+  while (c_first > 0 && U * c_first / p.grid > lo) --c_first;
+  for (int row = blockIdx.y * 4 + (threadIdx.x >> 6); row < p.M; row += gridDim.y * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c_first; c < p.grid; ++c) {
+      const long long u0 = U * c / p.grid, u1 = U * (c + 1) / p.grid;
+      if (u0 >= hi) break;
+      if (u1 <= lo || u1 <= u0) continue;
+      const int j = n_t - static_cast<int>(u0 / p.kb_total);            // index of this tile among the CTA's segments
+      const float4 v = *reinterpret_cast<const float4*>(p.ws + (static_cast<size_t>(c * p.max_segs + j) * kBM + row) * BN + c4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (col >= p.N) continue;
+    float f[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (col + e >= p.N) break;
+      float x = f[e];
+      if (p.bias) x += __ldg(p.bias + col + e);
+      if (p.residual) x += __bfloat162float(p.residual[static_cast<size_t>(row) * p.ldr + col + e]);
+      if (p.act == OPSG_ACT_GELU) x = gelu_erf(x);
+      else if (p.act == OPSG_ACT_RELU) x = fmaxf(x, 0.f);
+      if (p.out_f32) reinterpret_cast<float*>(p.D)[static_cast<size_t>(row) * p.ldd + col + e] = x;
+      else reinterpret_cast<__nv_bfloat16*>(p.D)[static_cast<size_t>(row) * p.ldd + col + e] = __float2bfloat16(x);
+    }
+  }
+}
+
+static void streamk_shape(int N, int K, int sms, int* n_tiles, int* kb_total, int* grid, int* max_segs) {
+  *n_tiles = (N + 255) / 256;
+  *kb_total = (K + kBK - 1) / kBK;
+  const long long U = static_cast<long long>(*n_tiles) * *kb_total;
+  *grid = static_cast<int>(U < sms ? U : sms);
+  const long long per = (U + *grid - 1) / *grid;
+  *max_segs = static_cast<int>((per + *kb_total - 1) / *kb_total) + 1;
+}
+
 }  // namespace opsg
 
 using namespace opsg;
+
+extern "C" size_t opsg_gemm_streamk_workspace_bytes(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  int n_tiles, kb_total, grid, max_segs;
+  int sms = opsg_num_sms();
+  if (sms <= 0) sms = kNumSMsB200;
+  streamk_shape(N, K, sms, &n_tiles, &kb_total, &grid, &max_segs);
+  return static_cast<size_t>(grid) * max_segs * kBM * 256 * sizeof(float);
+}
+
+extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M,
+                                      int N, int K, const float* bias, const opsg_bf16* residual, int ldr, int act,
+                                      int out_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(A && W && D && workspace, "gemm_streamk: null pointer");
+  OPSG_CHECK_ARG(M > 0 && M <= kBM && N > 0 && K > 0, "gemm_streamk: needs 0 < M <= 128 (got M=%d N=%d K=%d)", M, N, K);
+  OPSG_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "gemm_streamk: leading dimension too small");
+  OPSG_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm_streamk: lda/ldw must be multiples of 8 elements (TMA)");
+  OPSG_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+                 "gemm_streamk: A/W/workspace must be 16-byte aligned");
+  OPSG_CHECK_ARG(out_mode == OPSG_OUT_BF16 || out_mode == OPSG_OUT_F32, "gemm_streamk: out_mode must be BF16 or F32");
+  OPSG_CHECK_ARG(act >= OPSG_ACT_NONE && act <= OPSG_ACT_RELU, "gemm_streamk: bad activation");
+  OPSG_CHECK_ARG(!residual || ldr >= N, "gemm_streamk: ldr too small");
+  int n_tiles, kb_total, grid, max_segs;
+  streamk_shape(N, K, opsg_num_sms(), &n_tiles, &kb_total, &grid, &max_segs);
+  OPSG_CHECK_ARG(workspace_bytes >= static_cast<size_t>(grid) * max_segs * kBM * 256 * sizeof(float),
+                 "gemm_streamk: workspace too small (%zu bytes)", workspace_bytes);
+  CUtensorMap tmA, tmB;
+  rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 256, kBK);
+  if (rc) return rc;
+  GemmParams p;
+  p.D = nullptr; p.bias = nullptr; p.residual = nullptr;
+  p.M = M; p.N = N; p.K = K; p.ldd = 0; p.ldr = 0; p.bias_along_m = 0; p.act = OPSG_ACT_NONE;
+  p.out_mode = OPSG_OUT_F32; p.k_splits = 1; p.m_tiles = 1; p.n_tiles = n_tiles; p.tma_store = 0;
+  p.stream_k = 1; p.max_segs = max_segs; p.ws = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  using S = GemmSmem<256, 4>;
+  static bool configured = false;
+  if (!configured) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_bf16_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+                    "cudaFuncSetAttribute(gemm streamk)");
+    if (rc) return rc;
+    configured = true;
+  }
+  gemm_bf16_kernel<256, 4><<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, tmA, p);
+  OPSG_CHECK_LAUNCH("gemm_bf16_kernel(stream-K)");
+  StreamKReduceParams r;
+  r.ws = p.ws; r.D = D; r.bias = bias; r.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  r.M = M; r.N = N; r.ldd = ldd; r.ldr = ldr; r.act = act; r.out_f32 = out_mode == OPSG_OUT_F32;
+  r.n_tiles = n_tiles; r.kb_total = kb_total; r.grid = grid; r.max_segs = max_segs;
+  const int gy = (M + 3) / 4 < 8 ? (M + 3) / 4 : 8;
+  streamk_reduce_kernel<<<dim3(n_tiles, gy), 256, 0, st>>>(r);
+  OPSG_CHECK_LAUNCH("streamk_reduce_kernel");
+  return OPSG_OK;
+}
 
 extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M, int N,
                               int K, const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act,
@@ -406,6 +576,7 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
   p.D = D; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.ldr = ldr; p.bias_along_m = bias_along_m; p.act = act;
   p.out_mode = out_mode; p.k_splits = k_splits; p.m_tiles = 0; p.n_tiles = 0; p.tma_store = tma_store;
+  p.stream_k = 0; p.max_segs = 0; p.ws = nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256: return launch_gemm<256, 4>(tmA, tmB, tmD, p, st);

@@ -15,6 +15,7 @@ fp32 softmax / LayerNorm statistics and fp32 logits.  Only ``do_layer_norm_befor
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -92,27 +93,33 @@ class OPTDecodeEngine:
         if w_proj.shape[0] != weights.d:
             raise ValueError(f"language_projection out_features {w_proj.shape[0]} != LLM hidden size {weights.d}")
         self.use_cuda_graphs = use_cuda_graphs
+        self.streamk = os.environ.get("OPSG_LLM_STREAMK", "0") == "1"
         self._graphs = {}          # (hidden shape, k, T, max_new_tokens) -> captured generate()
 
     # one decoder layer over `rows` = nseq * q_len token rows; h is updated in place
     def _layer(self, lw, h, k_cache, v_cache, key_mask, nseq, q_len, pos0):
         w = self.w
         d = w.d
+        # OPSG_LLM_STREAMK=1 routes decode steps (rows <= 128) through the stream-K GEMM.  Measured on B200 at k = 100
+        # (profiles/r1_llm_decode.md) it is slower than the tiled kernel: at ~10 K-blocks per CTA both are bound by
+        # per-launch latency (prologue, first TMA round trip, tail), and stream-K adds a fix-up launch.
+        gemm = ops.gemm_small_m if (self.streamk and h.shape[0] <= 128) else ops.gemm
         x = ops.layernorm(h, lw["ln1"][0], lw["ln1"][1], self.LN_EPS)
-        qkv = ops.gemm(x, lw["w_qkv"], lw["b_qkv"])                                    # [rows, 3d]
+        qkv = gemm(x, lw["w_qkv"], lw["b_qkv"])                                        # [rows, 3d]
         ops.kv_append(qkv, nseq, q_len, pos0, d, k_cache, v_cache)
         ctx = torch.empty((nseq * q_len, d), dtype=torch.bfloat16, device=h.device)
         ops.llm_attn(qkv, k_cache, v_cache, key_mask, nseq, q_len, pos0, w.heads, w.head_dim, w.head_dim ** -0.5, ctx)
-        ops.gemm(ctx, lw["w_o"], lw["b_o"], residual=h, out=h)                         # h += out_proj(ctx)
+        gemm(ctx, lw["w_o"], lw["b_o"], residual=h, out=h)                             # h += out_proj(ctx)
         x = ops.layernorm(h, lw["ln2"][0], lw["ln2"][1], self.LN_EPS)
-        f = ops.gemm(x, lw["w_fc1"], lw["b_fc1"], act=ops.ACT_RELU)
-        ops.gemm(f, lw["w_fc2"], lw["b_fc2"], residual=h, out=h)                       # h += fc2(relu(fc1(x)))
+        f = gemm(x, lw["w_fc1"], lw["b_fc1"], act=ops.ACT_RELU)
+        gemm(f, lw["w_fc2"], lw["b_fc2"], residual=h, out=h)                           # h += fc2(relu(fc1(x)))
         return h
 
     def _logits(self, h_last):
         w = self.w
         x = ops.layernorm(h_last, w.final_ln[0], w.final_ln[1], self.LN_EPS)
-        return ops.gemm(x, w.lm_head, out_dtype=torch.float32)                         # fp32 [k, V]
+        gemm = ops.gemm_small_m if (self.streamk and h_last.shape[0] <= 128) else ops.gemm
+        return gemm(x, w.lm_head, out_dtype=torch.float32)                             # fp32 [k, V]
 
     @torch.no_grad()
     def generate(self, hidden: torch.Tensor, selected: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,

@@ -131,6 +131,39 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+_streamk_ws = {}     # device -> uint8 workspace, grown on demand
+_streamk_ws_keep = []  # outgrown workspaces stay alive: captured CUDA graphs may still point at them
+
+
+def gemm_small_m(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+                 residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
+                 out_dtype=torch.bfloat16) -> torch.Tensor:
+    """Weight-streaming GEMM for M <= 128 rows (LLM decode): stream-K over (N-tile, K-block) + fix-up kernel."""
+    _cuda(a, torch.bfloat16, "a"); _cuda(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert M <= 128 and w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    lib = _lib.load()
+    need = lib.opsg_gemm_streamk_workspace_bytes(N, K)
+    ws = _streamk_ws.get(a.device)
+    if ws is None or ws.numel() < need:
+        if ws is not None:
+            _streamk_ws_keep.append(ws)
+        ws = torch.empty(max(need, 64 << 20), dtype=torch.uint8, device=a.device)
+        _streamk_ws[a.device] = ws
+    if residual is not None:
+        _cuda(residual, torch.bfloat16, "residual")
+    mode = OUT_BF16 if out.dtype == torch.bfloat16 else OUT_F32
+    with _timed("gemm_streamk", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)):
+        _lib.check(lib.opsg_gemm_bf16_streamk(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                              _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
+                                              act, mode, _ptr(ws), ws.numel(), _stream()))
+    _count(2)
+    return out
+
+
 def cast_f32_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x, torch.float32, "x")
     rows, cols = x.shape
@@ -255,7 +288,8 @@ def gather_rows(src: torch.Tensor, row_elems: int, idx: torch.Tensor, out=None):
     n = idx.numel()
     if out is None:
         out = torch.empty((n, row_elems), dtype=torch.bfloat16, device=src.device)
-    _lib.check(_lib.load().opsg_gather_rows_bf16(_ptr(src), row_elems, _ptr(idx), n, _ptr(out), _stream()))
+    with _timed("gather_rows", 0.0, 4.0 * n * row_elems):
+        _lib.check(_lib.load().opsg_gather_rows_bf16(_ptr(src), row_elems, _ptr(idx), n, _ptr(out), _stream()))
     _count()
     return out
 
@@ -263,8 +297,9 @@ def gather_rows(src: torch.Tensor, row_elems: int, idx: torch.Tensor, out=None):
 def embed_gather(table, ids, out, pos_table=None, pos=None):
     _cuda(table, torch.bfloat16, "table"); _cuda(ids, torch.int32, "ids")
     n, d = ids.numel(), table.shape[1]
-    _lib.check(_lib.load().opsg_embed_gather(_ptr(table), d, _ptr(ids), _ptr(pos_table), _ptr(pos), n, _ptr(out),
-                                            out.stride(0), _stream()))
+    with _timed("embed_gather", 0.0, 6.0 * n * d):
+        _lib.check(_lib.load().opsg_embed_gather(_ptr(table), d, _ptr(ids), _ptr(pos_table), _ptr(pos), n, _ptr(out),
+                                                out.stride(0), _stream()))
     _count()
     return out
 
@@ -275,23 +310,28 @@ def llm_build_prefix(proj, rows_per_seq, row0, n_prefix, table, ids, pos_table, 
     nseq, T = ids.shape
     d = table.shape[1]
     assert out.is_contiguous() and out.shape == (nseq, n_prefix + T, d)
-    _lib.check(_lib.load().opsg_llm_build_prefix(_ptr(proj), rows_per_seq, row0, n_prefix, _ptr(table), _ptr(ids), T,
-                                                _ptr(pos_table), _ptr(pos), nseq, d, _ptr(out), _stream()))
+    with _timed("llm_build_prefix", 0.0, 6.0 * out.numel()):
+        _lib.check(_lib.load().opsg_llm_build_prefix(_ptr(proj), rows_per_seq, row0, n_prefix, _ptr(table), _ptr(ids), T,
+                                                    _ptr(pos_table), _ptr(pos), nseq, d, _ptr(out), _stream()))
     _count()
     return out
 
 
 def llm_attn(q, k_cache, v_cache, key_mask, nseq, q_len, q_pos0, num_heads, head_dim, scale, out):
     max_ctx = k_cache.shape[1]
-    _lib.check(_lib.load().opsg_llm_attn(_ptr(q), q.stride(0), _ptr(k_cache), _ptr(v_cache), max_ctx, _ptr(key_mask), nseq,
-                                        q_len, q_pos0, num_heads, head_dim, float(scale), _ptr(out), out.stride(0), _stream()))
+    ctx = q_pos0 + q_len
+    with _timed("llm_attn", 4.0 * nseq * q_len * ctx * num_heads * head_dim,
+                4.0 * nseq * ctx * num_heads * head_dim + 4.0 * nseq * q_len * num_heads * head_dim):
+        _lib.check(_lib.load().opsg_llm_attn(_ptr(q), q.stride(0), _ptr(k_cache), _ptr(v_cache), max_ctx, _ptr(key_mask), nseq,
+                                            q_len, q_pos0, num_heads, head_dim, float(scale), _ptr(out), out.stride(0), _stream()))
     _count()
     return out
 
 
 def kv_append(qkv, nseq, q_len, pos0, d_model, k_cache, v_cache):
-    _lib.check(_lib.load().opsg_kv_append(_ptr(qkv), qkv.stride(0), nseq, q_len, pos0, d_model, _ptr(k_cache), _ptr(v_cache),
-                                         k_cache.shape[1], _stream()))
+    with _timed("kv_append", 0.0, 8.0 * nseq * q_len * d_model):
+        _lib.check(_lib.load().opsg_kv_append(_ptr(qkv), qkv.stride(0), nseq, q_len, pos0, d_model, _ptr(k_cache), _ptr(v_cache),
+                                             k_cache.shape[1], _stream()))
     _count()
 
 
@@ -300,6 +340,7 @@ def argmax_rows(logits: torch.Tensor, out=None):
     rows, cols = logits.shape
     if out is None:
         out = torch.empty(rows, dtype=torch.int32, device=logits.device)
-    _lib.check(_lib.load().opsg_argmax_rows(_ptr(logits), logits.stride(0), rows, cols, _ptr(out), _stream()))
+    with _timed("argmax_rows", 0.0, 4.0 * rows * cols):
+        _lib.check(_lib.load().opsg_argmax_rows(_ptr(logits), logits.stride(0), rows, cols, _ptr(out), _stream()))
     _count()
     return out

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_llm_gpu.py tests/test_kernels_gpu.py -q 2>&1 | tail -3
+timeout 1200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_w.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({k:d[k] for k in ('value','ms_per_step')}); r=d['relation_tokens_per_sec']; print(r['value'], r['ms_per_image']); print(r['kernel_ms_per_image'])"

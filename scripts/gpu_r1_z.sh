@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_llm_gpu.py -q 2>&1 | tail -3
+timeout 1200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_z.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({k:d[k] for k in ('value','ms_per_step')}); r=d['relation_tokens_per_sec']; print(r['value'], r['ms_per_image'])"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2100 -c 600 --csv --log-file gpurun_out/llm_launches3.csv python scripts/llm_probe.py 4 > gpurun_out/llm_probe3.log 2>&1
+grep -c decode_attn gpurun_out/llm_launches3.csv

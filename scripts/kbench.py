@@ -61,6 +61,20 @@ def bench_gemm(iters, flush):
         del a, w, res, out
 
 
+def bench_streamk(iters, flush):
+    for name, M, N, K in (("opt_qkv_decode", 100, 7680, 2560), ("opt_out_decode", 100, 2560, 2560),
+                          ("opt_fc1_decode", 100, 10240, 2560), ("opt_fc2_decode", 100, 2560, 10240),
+                          ("opt_lm_head", 100, 50272, 2560)):
+        a = torch.randn((M, K), device=DEV).to(torch.bfloat16)
+        w = (torch.randn((N, K), device=DEV) / K ** 0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device=DEV)
+        out = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+        for fn_name, fn in (("streamk", lambda: ops.gemm_small_m(a, w, bias, out=out)), ("tiled", lambda: ops.gemm(a, w, bias, out=out))):
+            med, best = timeit(fn, iters, flush)
+            print(json.dumps({"kernel": "gemm_" + fn_name, "case": name, "M": M, "N": N, "K": K, "ms_median": med,
+                              "weight_GBps_median": 2.0 * N * K / med / 1e6}), flush=True)
+
+
 def bench_xattn(iters, flush):
     for N, L in ((40, 256), (80, 256), (40, 252)):
         B = N * N
@@ -87,6 +101,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
     if "gemm" in args.which:
         bench_gemm(args.iters, flush)
+    if "streamk" in args.which:
+        bench_streamk(args.iters, flush)
     if "xattn" in args.which:
         bench_xattn(args.iters, flush)
 

@@ -100,6 +100,50 @@ def test_gemm_split_k_atomic(ops):
     assert (acc.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max()
 
 
+STREAMK_CASES = [
+    # M, N, K, bias, residual, act, out_dtype      (LLM decode shapes: OPT-2.7B qkv / out / fc1 / fc2 / lm_head)
+    (100, 7680, 2560, True, False, 0, torch.bfloat16),
+    (100, 2560, 2560, True, True, 0, torch.bfloat16),
+    (100, 10240, 2560, True, False, 2, torch.bfloat16),
+    (100, 2560, 10240, True, True, 0, torch.bfloat16),
+    (20, 50272, 2560, False, False, 0, torch.float32),
+    (1, 1024, 320, True, False, 1, torch.bfloat16),
+    (128, 72, 136, True, True, 0, torch.float32),
+    (37, 300, 64, False, False, 0, torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize("case", STREAMK_CASES, ids=lambda c: f"{c[0]}x{c[1]}x{c[2]}")
+def test_gemm_small_m_streamk(ops, case):
+    """Stream-K weight-streaming GEMM (M <= 128) + fix-up kernel against fp32 matmul; also deterministic."""
+    M, N, K, use_bias, use_res, act, odt = case
+    g = torch.Generator().manual_seed(M * 11 + N * 5 + K)
+    a = _rand_bf16((M, K), g)
+    w = _rand_bf16((N, K), g, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=g) if use_bias else None
+    res = _rand_bf16((M, N), g) if use_res else None
+    ref = a.float() @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    if res is not None:
+        ref = ref + res.float()
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    kw = dict(residual=res.cuda() if res is not None else None, act=act, out_dtype=odt)
+    out = ops.gemm_small_m(a.cuda(), w.cuda(), bias.cuda() if bias is not None else None, **kw)
+    out2 = ops.gemm_small_m(a.cuda(), w.cuda(), bias.cuda() if bias is not None else None, **kw)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 1.2e-2 * ref.abs().max().item(), err
+    assert torch.equal(out, out2)
+    if res is not None and odt == torch.bfloat16:      # in-place residual update as the decoder uses it
+        h = res.cuda().clone()
+        ops.gemm_small_m(a.cuda(), w.cuda(), bias.cuda() if bias is not None else None, residual=h, act=act, out=h)
+        assert torch.equal(h, out)
+
+
 def test_gemm_rejects_bad_arguments(ops):
     from openpsg_b200._lib import OpsgError
     a = torch.zeros((8, 12), dtype=torch.bfloat16, device="cuda")     # K=12 -> lda not multiple of 8
