@@ -21,6 +21,9 @@
 
 namespace opsg {
 
+int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, opsg_bf16* D, int ldd, int M, int N, int K,
+                     const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, cudaStream_t stream);
+
 constexpr int kBM = 128;
 constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
 constexpr int kGemmThreads = 384;
@@ -552,6 +555,14 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
     OPSG_CHECK_ARG(out_mode == OPSG_OUT_F32_ATOMIC && !bias && !residual && act == OPSG_ACT_NONE,
                    "gemm: split-K needs OPSG_OUT_F32_ATOMIC and no bias/residual/act");
   OPSG_CHECK_ARG(!residual || ldr >= N, "gemm: ldr too small");
+
+  // large bf16-output problems: CTA-pair kernel (cta_group::2, 256 x 256 tiles; gemm_2cta.cu)
+  static const int use_2cta = [] { const char* e = getenv("OPSG_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  if (use_2cta && out_mode == OPSG_OUT_BF16 && k_splits == 1) {
+    rc = launch_gemm_2cta(A, lda, W, ldw, reinterpret_cast<opsg_bf16*>(D), ldd, M, N, K, bias, bias_along_m, residual, ldr, act,
+                          reinterpret_cast<cudaStream_t>(stream));
+    if (rc != OPSG_E_UNSUPPORTED) return rc;
+  }
 
   // tile width: wide tiles for big problems, narrower ones when the grid would not fill the machine
   const int m_tiles = (M + kBM - 1) / kBM;

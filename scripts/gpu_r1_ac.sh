@@ -1,0 +1,3 @@
+set -x
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -x -k "gemm" 2>&1 | tail -3
+timeout 600 python scripts/kbench.py gemm 2>&1 | cut -c1-175
