@@ -258,7 +258,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&vbar_ready[b], 1);
     }
     mbar_init(k_full, 1); mbar_init(k_empty, 1);
-    mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(v_full, 1); mbar_init(v_empty, 2);     // v_empty: last PV of the head (tcgen05.commit) + the V-mean warp
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -388,6 +388,9 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 3) {
     // ===================== per-head mean of V over the L real keys (rows whose pair mask is empty) =====================
+    // This warp READS the resident V tile, so it is a second consumer of it: the producer may only overwrite V with the
+    // next head's tile after the head's last PV MMA *and* this warp have released it (v_empty counts both).  (Without
+    // that, a CTA whose first unit is the last tile of a head reloaded V while the mean was still being summed.)
     int v_waits = 0, cur_head = -1;
     for (int i = 0; i < n_units; ++i) {
       const int head = (u_begin + i) / p.m_tiles;
@@ -399,21 +402,27 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll 1
       for (int rr = 0; rr < 2; ++rr) {
         const int n = lane + rr * 32;                        // value dim; the swizzle only permutes chunks inside a row
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int kb = 0; kb < 4; ++kb) {
           const uint4* rowp = reinterpret_cast<const uint4*>(sV + kb * XaSmem::kVBlk + n * 128);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint4 x = rowp[c];
-            acc += bf16_lo(x.x) + bf16_hi(x.x) + bf16_lo(x.y) + bf16_hi(x.y) + bf16_lo(x.z) + bf16_hi(x.z) +
-                   bf16_lo(x.w) + bf16_hi(x.w);
+            a0 += bf16_lo(x.x) + bf16_hi(x.x);
+            a1 += bf16_lo(x.y) + bf16_hi(x.y);
+            a2 += bf16_lo(x.z) + bf16_hi(x.z);
+            a3 += bf16_lo(x.w) + bf16_hi(x.w);
           }
         }
-        sVbar[(hs & 1) * 64 + n] = acc / static_cast<float>(p.L);     // keys >= L are zero-filled by TMA
+        sVbar[(hs & 1) * 64 + n] = ((a0 + a1) + (a2 + a3)) / static_cast<float>(p.L);     // keys >= L are zero-filled by TMA
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&vbar_ready[hs & 1]);
-      // the next head's V may only be read after this head's last PV: v_full's next phase orders that for us
+      if (lane == 0) {
+        mbar_arrive(&vbar_ready[hs & 1]);
+        // release V if another head follows in this CTA's range (mirrors the MMA warp's release_v condition)
+        const int last_head = (u_begin + n_units - 1) / p.m_tiles;
+        if (head != last_head) mbar_arrive(v_empty);
+      }
     }
   } else if (warp >= 4) {
     // ===================== softmax + epilogue warps =====================
