@@ -103,8 +103,7 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
     sValid[key] = ok ? 1 : 0;
   }
 
-  for (int q0 = 0; q0 < n_q; q0 += 64) {
-    __syncthreads();
+  auto stage_q = [&](int q0) {
     for (int idx = threadIdx.x; idx < 64 * VEC; idx += blockDim.x) {
       const int r = idx / VEC, v8 = idx % VEC;
       const int qi = q0 + r;
@@ -114,6 +113,14 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
         else qu = __ldg(reinterpret_cast<const uint4*>(p.q + (static_cast<size_t>(seq) * p.q_len + qi) * p.ld_q + head * HD + v8 * 8));
       }
       *reinterpret_cast<uint4*>(sQ + r * QS + v8 * 8) = qu;
+    }
+  };
+  stage_q(0);       // the first 64 query rows travel with K / V: one global round trip, one barrier
+
+  for (int q0 = 0; q0 < n_q; q0 += 64) {
+    if (q0 > 0) {
+      __syncthreads();
+      stage_q(q0);
     }
     __syncthreads();
     if (q0 + warp * 16 >= n_q) continue;   // warp-uniform; no further block-wide barriers below in this pass
@@ -210,6 +217,171 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
       for (int n = 0; n < HD / 8; ++n)
         *reinterpret_cast<uint32_t*>(d + n * 8 + 2 * t) = pack_bf16x2(o[n][2] * inv1, o[n][3] * inv1);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 (Q-Former shape: head_dim 64, <= 64 rows per pair) — persistent, software-pipelined variant.
+// Profile of the one-CTA-per-(pair, head) kernel above (profiles/r1_launches_*.md): 355 us per cfg2 image for 480 MB of
+// qkv-in / ctx-out traffic (74 us at HBM speed) — every CTA pays two dependent global round trips before it computes.
+// Here a CTA walks a contiguous range of (pair, head) problems (consecutive heads of one pair = the same 49 rows of qkv,
+// so DRAM pages are fully used), cp.async fills stage i+1 while stage i is computed, and the context rows leave through
+// shared memory as full 128-byte rows.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t sz = valid ? 16u : 0u;           // src-size 0 -> 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kQfHD = 64, kQfNK = 64, kQfRS = kQfHD + 8;                 // padded row stride (elements)
+constexpr int kQfStageElems = 3 * 64 * kQfRS;                             // Q | K | V tiles of one problem
+constexpr int kQfStageBytes = kQfStageElems * 2 + 64;                     // + key validity bytes
+constexpr int kQfStages = 2;
+
+__global__ void __launch_bounds__(128) qformer_self_attn_kernel(const SmallAttnParams p, int num_problems) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_keys = p.n_query + p.T;
+  const int n_q = p.text_queries ? n_keys : p.n_query;
+  const long long pb = static_cast<long long>(num_problems) * blockIdx.x / gridDim.x;
+  const long long pe = static_cast<long long>(num_problems) * (blockIdx.x + 1) / gridDim.x;
+
+  auto row_of = [&](int pair, int i) -> size_t {
+    return i < p.n_query ? static_cast<size_t>(pair) * p.n_query + i
+                         : static_cast<size_t>(p.B) * p.n_query + static_cast<size_t>(pair) * p.T + (i - p.n_query);
+  };
+  auto stage_ptr = [&](int st) { return reinterpret_cast<__nv_bfloat16*>(smem_dyn + st * kQfStageBytes); };
+  auto issue_loads = [&](long long prob, int st) {
+    const int pair = static_cast<int>(prob / p.num_heads), head = static_cast<int>(prob % p.num_heads);
+    __nv_bfloat16* sQ = stage_ptr(st);
+    __nv_bfloat16* sK = sQ + 64 * kQfRS;
+    __nv_bfloat16* sV = sK + 64 * kQfRS;
+    uint8_t* sValid = reinterpret_cast<uint8_t*>(sV + 64 * kQfRS);
+    for (int idx = threadIdx.x; idx < 64 * 8; idx += 128) {
+      const int r = idx >> 3, v8 = idx & 7;
+      const bool ok = r < n_keys;
+      const __nv_bfloat16* base = p.qkv + row_of(pair, ok ? r : 0) * (3 * p.d_model) + head * kQfHD + v8 * 8;
+      cp_async16(sQ + r * kQfRS + v8 * 8, base, ok && r < n_q);
+      cp_async16(sK + r * kQfRS + v8 * 8, base + p.d_model, ok);
+      cp_async16(sV + r * kQfRS + v8 * 8, base + 2 * p.d_model, ok);
+    }
+    if (threadIdx.x < 64) {
+      const int key = threadIdx.x;
+      bool ok = key < n_keys;
+      if (ok && key >= p.n_query) ok = p.text_mask[static_cast<size_t>(pair) * p.T + (key - p.n_query)] != 0;
+      sValid[key] = ok ? 1 : 0;
+    }
+    cp_async_commit();
+  };
+
+  if (pb < pe) issue_loads(pb, 0);
+  for (long long prob = pb; prob < pe; ++prob) {
+    const int st = static_cast<int>((prob - pb) & 1);
+    if (prob + 1 < pe) {
+      issue_loads(prob + 1, st ^ 1);          // stage st^1 was released by the barrier at the end of the previous iteration
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int pair = static_cast<int>(prob / p.num_heads), head = static_cast<int>(prob % p.num_heads);
+    __nv_bfloat16* sQ = stage_ptr(st);
+    const __nv_bfloat16* sK = sQ + 64 * kQfRS;
+    const __nv_bfloat16* sV = sK + 64 * kQfRS;
+    const uint8_t* sValid = reinterpret_cast<const uint8_t*>(sV + 64 * kQfRS);
+
+    if (warp * 16 < n_q) {
+      // ---- S = Q K^T ----
+      float sc[kQfNK / 8][4];
+#pragma unroll
+      for (int n = 0; n < kQfNK / 8; ++n) { sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f; }
+      const __nv_bfloat16* qw = sQ + (warp * 16) * kQfRS;
+#pragma unroll
+      for (int kk = 0; kk < kQfHD / 16; ++kk) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t*>(qw + g * kQfRS + kk * 16 + 2 * t);
+        a[1] = *reinterpret_cast<const uint32_t*>(qw + (g + 8) * kQfRS + kk * 16 + 2 * t);
+        a[2] = *reinterpret_cast<const uint32_t*>(qw + g * kQfRS + kk * 16 + 8 + 2 * t);
+        a[3] = *reinterpret_cast<const uint32_t*>(qw + (g + 8) * kQfRS + kk * 16 + 8 + 2 * t);
+#pragma unroll
+        for (int n = 0; n < kQfNK / 8; ++n) {
+          const __nv_bfloat16* kr = sK + (n * 8 + g) * kQfRS + kk * 16 + 2 * t;
+          mma_bf16_16816(sc[n], a, *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+        }
+      }
+      // ---- mask + softmax (rows g and g+8 of this warp's 16) ----
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < kQfNK / 8; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (sValid[n * 8 + 2 * t + e] == 0) { sc[n][e] = -INFINITY; sc[n][2 + e] = -INFINITY; }
+          m0 = fmaxf(m0, sc[n][e]);
+          m1 = fmaxf(m1, sc[n][2 + e]);
+        }
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      if (m0 == -INFINITY) m0 = 0.f;
+      if (m1 == -INFINITY) m1 = 0.f;
+      const float ms0 = m0 * p.scale_log2e, ms1 = m1 * p.scale_log2e;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < kQfNK / 8; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          sc[n][e] = ex2f(fmaf(sc[n][e], p.scale_log2e, -ms0));
+          sc[n][2 + e] = ex2f(fmaf(sc[n][2 + e], p.scale_log2e, -ms1));
+          l0 += sc[n][e];
+          l1 += sc[n][2 + e];
+        }
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      // ---- O = P V ----
+      float o[kQfHD / 8][4];
+#pragma unroll
+      for (int n = 0; n < kQfHD / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < kQfNK / 16; ++kk) {
+        uint32_t a[4];
+        a[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+        a[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+        a[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        a[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+        const __nv_bfloat16* vrow = sV + (kk * 16 + (lane & 15)) * kQfRS + ((lane >> 4) << 3);
+#pragma unroll
+        for (int n = 0; n < kQfHD / 8; n += 2) {
+          uint32_t b[4];
+          ldmatrix_x4_trans(b, vrow + n * 8);
+          mma_bf16_16816(o[n], a, b[0], b[1]);
+          mma_bf16_16816(o[n + 1], a, b[2], b[3]);
+        }
+      }
+      // ---- context rows -> this warp's own Q rows in shared memory -> 128-byte row stores ----
+      const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+      __syncwarp();                               // all lanes are done reading this warp's Q rows
+      __nv_bfloat16* ow = sQ + (warp * 16) * kQfRS;
+#pragma unroll
+      for (int n = 0; n < kQfHD / 8; ++n) {
+        *reinterpret_cast<uint32_t*>(ow + g * kQfRS + n * 8 + 2 * t) = pack_bf16x2(o[n][0] * inv0, o[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(ow + (g + 8) * kQfRS + n * 8 + 2 * t) = pack_bf16x2(o[n][2] * inv1, o[n][3] * inv1);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = i * 32 + lane, r = idx >> 3, v8 = idx & 7;
+        const int qi = warp * 16 + r;
+        if (qi < n_q)
+          *reinterpret_cast<uint4*>(p.out + row_of(pair, qi) * p.ld_out + head * kQfHD + v8 * 8) =
+              *reinterpret_cast<const uint4*>(ow + r * kQfRS + v8 * 8);
+      }
+    }
+    __syncthreads();                              // stage st may be refilled by the next iteration's prefetch
   }
 }
 
@@ -396,6 +568,23 @@ extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_ma
   p.out = reinterpret_cast<__nv_bfloat16*>(ctx_out);
   p.num_heads = num_heads; p.d_model = num_heads * head_dim; p.ld_out = p.d_model;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+  static const int use_pipelined = [] { const char* e = getenv("OPSG_SELF_ATTN_PIPELINED"); return e ? atoi(e) : 1; }();
+  if (use_pipelined && head_dim == kQfHD && n_query + T <= kQfNK && (((uintptr_t)qkv | (uintptr_t)ctx_out) & 15) == 0) {
+    constexpr int smem = kQfStages * kQfStageBytes;
+    static bool configured = false;
+    if (!configured) {
+      rc = check_cuda(cudaFuncSetAttribute(qformer_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                      "cudaFuncSetAttribute(qformer_self_attn)");
+      if (rc) return rc;
+      configured = true;
+    }
+    const int problems = B * num_heads;
+    int grid = opsg_num_sms() * 4;                 // 4 resident CTAs per SM (55 KB of smem each)
+    if (grid > problems) grid = problems;
+    qformer_self_attn_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, problems);
+    OPSG_CHECK_LAUNCH("qformer_self_attn_kernel");
+    return OPSG_OK;
+  }
   return dispatch_hd(p, B, n_query + T, head_dim, reinterpret_cast<cudaStream_t>(stream));
 }
 

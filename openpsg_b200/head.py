@@ -14,6 +14,7 @@ Extra, opt-in constructor kwargs (defaults = the reference's hard-coded values):
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -140,7 +141,7 @@ class RelationTransformerHeadV4(BaseModule):
         self.max_object_num = max_object_num
         self.topk_pairs = topk_pairs
         self.max_new_tokens = max_new_tokens
-        self.use_cuda_graphs = use_cuda_graphs
+        self.use_cuda_graphs = bool(use_cuda_graphs) and os.environ.get("OPSG_CUDA_GRAPHS", "1") != "0"
         if qformer_feature_size != 768 or object_feature_size != 256:
             raise NotImplementedError("libopsg_b200 kernels are built for the reference sizes (768 / 256)")
 
