@@ -52,6 +52,7 @@ constexpr int kXaSlots = 8;        // tile-local pair slots carried by the mask 
 struct XattnParams {
   const uint8_t* tiles;      // [m_tiles][kXaTileBytes] A_aug | B_aug in core-matrix order (xattn_bias_tiles_kernel)
   const uint8_t* row_flags;  // [m_tiles * 128] 1 = the row's pair has an empty union mask (uniform attention)
+  const uint8_t* chunk_vis;  // [m_tiles * 4] per 32-row quarter: bit c = some row of the quarter sees a key of chunk c
   int L, num_heads, d_model;
   int rows;          // B * n_query
   int m_tiles;
@@ -151,7 +152,7 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
 __global__ void __launch_bounds__(256)
 xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int32_t* __restrict__ pair_index,
                         int num_objects, int num_pairs, int n_query, int L, int rows, uint8_t* __restrict__ tiles,
-                        uint8_t* __restrict__ row_flags) {
+                        uint8_t* __restrict__ row_flags, uint8_t* __restrict__ chunk_vis) {
   const int mt = blockIdx.x;
   const int t = threadIdx.x;
   const int first_pair = (mt * 128) / n_query;
@@ -179,6 +180,17 @@ xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int3
     s_any[t] = any;
   }
   __syncthreads();
+  if (t < 4) {   // key chunks (32 keys) in which any row of 32-row quarter t sees at least one key
+    uint32_t vis = 0;
+    for (int r = t * 32; r < t * 32 + 32; ++r) {
+      const int row = mt * 128 + r;
+      if (row >= rows) break;
+      const int slot = row / n_query - first_pair;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) vis |= (s_union[slot][w] != 0u) ? (1u << w) : 0u;
+    }
+    chunk_vis[mt * 4 + t] = static_cast<uint8_t>(vis);
+  }
   uint8_t* tile = tiles + static_cast<size_t>(mt) * kXaTileBytes;
   {  // B_aug: thread = key
     const int key = t;
@@ -496,9 +508,14 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
         }
       } else {
+        // Key chunks in which no row of this warp sees a key (chunk_vis) contribute exact zeros: no tcgen05.ld, no max,
+        // no exponentials — their P columns are just cleared.  Panoptic masks are compact, so on the cfg2 images about
+        // half of the chunks fall away; the MMAs stay dense.
+        const uint32_t vis4 = (static_cast<uint32_t>(__ldg(p.chunk_vis + mt * 4 + q)) >> (half * 4)) & 0xFu;
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          if (!((vis4 >> c) & 1u)) continue;
           uint32_t v[32];
           tmem_ld32(tS + (half * 4 + c) * 32, v);
           tmem_ld_wait();
@@ -514,20 +531,26 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         *my_max = mx;
         named_bar_sync(1 + b, 256);
         mx = fmaxf(mx, *other_max);
+        if (mx == -INFINITY) mx = 0.f;                     // no visible key in either half: uniform / out-of-range rows only
         const float mxs = mx * p.scale_log2e;
         if (tr) p.trace[i * 8 + 3] = clock64();
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int c = half ? 3 - cc : cc;                // half 1 walks its chunks downwards (in-place safety)
-          uint32_t v[32];
-          tmem_ld32(tS + (half * 4 + c) * 32, v);
-          tmem_ld_wait();
           uint32_t pk[16];
+          if ((vis4 >> c) & 1u) {
+            uint32_t v[32];
+            tmem_ld32(tS + (half * 4 + c) * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = exp2_sel(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs), 2 * j);
-            const float e1 = exp2_sel(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
-            pk[j] = pack_bf16x2(e0, e1);
+            for (int j = 0; j < 16; ++j) {
+              const float e0 = exp2_sel(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs), 2 * j);
+              const float e1 = exp2_sel(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
+              pk[j] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
           }
           tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
         }
@@ -599,7 +622,7 @@ extern "C" void opsg_debug_xattn_trace(void* dev_buffer) { g_xattn_trace = reint
 extern "C" size_t opsg_xattn_bias_tiles_bytes(int B, int n_query) {
   if (B <= 0 || n_query <= 0) return 0;
   const size_t m_tiles = (static_cast<size_t>(B) * n_query + 127) / 128;
-  return m_tiles * (kXaTileBytes + 128);
+  return m_tiles * (kXaTileBytes + 128 + 16);       // tiles | row flags | chunk visibility (4 bytes per tile, padded)
 }
 
 extern "C" int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
@@ -617,7 +640,8 @@ extern "C" int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int3
   const int m_tiles = (rows + 127) / 128;
   uint8_t* tiles = reinterpret_cast<uint8_t*>(tiles_out);
   xattn_bias_tiles_kernel<<<m_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      bits, words, pair_index, num_objects, B, n_query, L, rows, tiles, tiles + static_cast<size_t>(m_tiles) * kXaTileBytes);
+      bits, words, pair_index, num_objects, B, n_query, L, rows, tiles, tiles + static_cast<size_t>(m_tiles) * kXaTileBytes,
+      tiles + static_cast<size_t>(m_tiles) * (kXaTileBytes + 128));
   OPSG_CHECK_LAUNCH("xattn_bias_tiles_kernel");
   return OPSG_OK;
 }
@@ -672,6 +696,7 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   p.m_tiles = (rows + 127) / 128;
   p.tiles = reinterpret_cast<const uint8_t*>(bias_tiles);
   p.row_flags = p.tiles + static_cast<size_t>(p.m_tiles) * kXaTileBytes;
+  p.chunk_vis = p.tiles + static_cast<size_t>(p.m_tiles) * (kXaTileBytes + 128);
   p.L = L; p.num_heads = num_heads; p.d_model = d_model;
   p.rows = rows; p.total_units = p.m_tiles * num_heads;
   p.desc_swap = desc_swap;

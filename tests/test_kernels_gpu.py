@@ -321,6 +321,7 @@ def test_xattn_bias_tiles_bit_exact(ops):
     rows = B * nq
     m_tiles = (rows + 127) // 128
     tiles, flags = got[:m_tiles * 12288].reshape(m_tiles, 12288), got[m_tiles * 12288:]
+    vis = got[m_tiles * (12288 + 128):]
     pm = restated.pair_masks(masks.numpy())                       # [B, L]
     NEG, ONE = 0xC680, 0x3F80
     for mt in range(m_tiles):
@@ -336,12 +337,39 @@ def test_xattn_bias_tiles_bit_exact(ops):
                 exp[row // nq - first] = ONE
                 assert flags[row] == (0 if pm[row // nq].any() else 1)
             assert np.array_equal(a[r // 8, 0, r % 8], exp)
+        for quarter in range(4):       # chunk visibility of each 32-row quarter
+            exp_vis = 0
+            for r in range(quarter * 32, quarter * 32 + 32):
+                row = mt * 128 + r
+                if row < rows:
+                    m = np.zeros(256, bool)
+                    m[:L] = pm[row // nq]
+                    exp_vis |= sum(1 << w for w in range(8) if m[32 * w:32 * w + 32].any())
+            assert vis[mt * 4 + quarter] == exp_vis, (mt, quarter)
         for key in range(256):
             exp = np.zeros(8, np.uint16)
             for s in range(last - first + 1):
                 if not (key < L and pm[first + s, key]):
                     exp[s] = NEG
             assert np.array_equal(b[key // 8, 0, key % 8], exp), (mt, key)
+
+
+def test_xattn_pairs_sparse_masks_skip_chunks(ops):
+    """Compact masks (few visible key chunks per row group, as panoptic segments give) exercise the chunk-skipping
+    path; an object with no tokens and rows with all keys in one half are included."""
+    g = torch.Generator().manual_seed(21)
+    L, N, nq, d = 256, 12, 33, 768
+    B = N * N
+    q, k, v = _rand_bf16((B * nq, d), g), _rand_bf16((L, d), g), _rand_bf16((L, d), g)
+    masks = torch.zeros(N, L, dtype=torch.bool)
+    for o in range(N - 1):                       # object o owns 5 consecutive tokens; the last object owns none
+        start = int(torch.randint(0, L - 5, (1,), generator=g))
+        masks[o, start:start + 5] = True
+    bits = torch.from_numpy(restated.pack_mask_bits(masks.numpy()).view(np.int32))
+    out = ops.xattn_pairs(q.cuda(), k.cuda(), v.t().contiguous().cuda(), bits.cuda(), N, B, nq, L, 12, 64).float().cpu()
+    ref = _xattn_ref(q, k, v, masks, N, None, nq)
+    assert (out - ref).abs().max() < 2e-2
+    assert torch.isfinite(out).all()
 
 
 def test_xattn_pairs_with_pair_index(ops):

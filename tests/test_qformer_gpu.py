@@ -166,3 +166,37 @@ def test_graph_replay_and_forward_batch_equal_eager():
         assert (z - zr).abs().max() < 5e-3
         ok, diff = margin_set_equal(top, zr, 20, 5e-3)
         assert ok, diff
+
+
+def test_relation_queries_80_objects_subset_vs_oracle(head):
+    """cfg5's image shape (80 objects, 6400 pair queries): the full run must agree with the fp32 oracle on a sample of
+    pairs (the oracle evaluates only the sampled pairs through its pair_index argument)."""
+    wl = synth.WORKLOADS["cfg5"]
+    inputs = synth.make_image_inputs(wl, 1)
+    head(synth.inputs_to(inputs, "cuda:0"), is_generation=False)
+    out = head.last_output
+    n = wl.num_objects
+    assert out.logits.numel() == n * n
+    sd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
+    meta, info = inputs["img_metas"][0], inputs["object_info"][0]
+    ids = [int(i) for i in info["object_id_list"]]
+    m = torch.from_numpy(restated.object_token_masks(info["pan_results"].numpy(), meta["img_shape"][:2], meta["pad_shape"][:2],
+                                                     inputs["mask_features"].shape[-2:], 16, ids))
+    tokens = restated.patch_embed(inputs["mask_features"], sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], 16)
+    from openpsg_b200.categories import object_categories
+    names = [object_categories[i % 1000] for i in ids]
+    sample = torch.tensor([0, 79, 80, 81, 3333, 6399, 6398, 4040, 1234, 2500, 5000, 6320], dtype=torch.long)
+    enc = synth.SyntheticTokenizer("qformer")(
+        ['Is there a relation between {} and {}?'.format(names[p // n], names[p % n]) for p in sample.tolist()])
+    query = torch.cat([sd["rel_cls_query"], sd["relation_query"]], dim=1)[0]
+    ref = restated.qformer_forward(sd, query, enc["input_ids"], enc["attention_mask"], tokens, m, pair_index=sample)
+    got = out.hidden.float().cpu().reshape(n * n, 33, 768)[sample]
+    d = (got - ref).abs()
+    assert d.max() <= TOL_O_MAX and d.mean() <= TOL_O_MEAN, (d.max(), d.mean())
+    z_ref = restated.existence_logits(ref[:, 0], sd["binary_rel_cls_pred.weight"], sd["binary_rel_cls_pred.bias"])
+    assert (out.logits.cpu()[sample] - z_ref).abs().max() <= 4e-2
+    # mask bits of all 80 objects: bit-exact
+    bits = out.mask_bits.cpu().numpy().view(np.uint32)
+    L = m.shape[1]
+    obj = ((bits[:, np.arange(L) // 32] >> (np.arange(L) % 32).astype(np.uint32)) & 1).astype(bool)
+    assert np.array_equal(obj, m.numpy())
