@@ -72,6 +72,22 @@ int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, voi
                    const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, int out_mode,
                    int k_splits, void* stream);
 
+/* LayerNorm-folding variant (CTA-pair kernel) for the Q-Former's Linear -> (+residual) -> LayerNorm -> Linear chains
+ * (HF :542-553, 598-610, 687-695): activations stay UN-normalised in memory together with per-row (sum, sum of
+ * squares) statistics and every consumer applies the pending LayerNorm itself, so no separate LayerNorm pass runs:
+ *   a_stats  != NULL : A holds un-normalised rows x with statistics a_stats[M, 2] over their K features; W must be the
+ *                      consumer weight with the LayerNorm's gamma folded in (W'[n,k] = gamma[k] W[n,k]), a_colsum[n] =
+ *                      sum_k W'[n,k], and bias[n] must already include sum_k beta[k] W[n,k].  The kernel computes
+ *                      rstd_m (acc[m,n] - mean_m a_colsum[n]) + bias[n]  ==  LayerNorm(x_m) . W^T + bias.
+ *   r_stats  != NULL : the residual tensor is un-normalised too; (residual - mean) rstd r_gamma[n] + r_beta[n] is added.
+ *   stats_out != NULL: (sum, sum of squares) of every output row (fp32, before the bf16 rounding) are accumulated with
+ *                      atomics into stats_out[M, 2], which the caller zeroes beforehand.
+ * bf16 output only; N, lda, ldw, ldd, ldr multiples of 8; eps = the LayerNorm epsilon. */
+int opsg_gemm_bf16_ln(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, opsg_bf16* D, int ldd, int M, int N, int K,
+                      const float* bias, const opsg_bf16* residual, int ldr, int act, const float* a_stats,
+                      const float* a_colsum, const float* r_stats, const float* r_gamma, const float* r_beta,
+                      float* stats_out, float eps, void* stream);
+
 /* Small-M variant for weight-streaming GEMMs (LLM decode: M = number of selected pairs <= 128, OPT q/k/v/out/fc1/
  * fc2/lm_head of one decode step; v4:305-312).  Same operands and epilogue as opsg_gemm_bf16 (bias along N only),
  * but the flattened (N-tile, K-block) space is cut into one equal contiguous range per SM ("stream-K"), so every SM

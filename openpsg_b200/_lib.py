@@ -27,6 +27,7 @@ SIGNATURES = {
     "opsg_pair_mask_bits": [P, I, I, I, I, I, I, I, I, P, I, P, I, P],
     "opsg_patch_im2col": [P, I, I, I, I, P, P],
     "opsg_gemm_bf16": [P, I, P, I, P, I, I, I, I, P, I, P, I, I, I, I, P],
+    "opsg_gemm_bf16_ln": [P, I, P, I, P, I, I, I, I, P, P, I, I, P, P, P, P, P, P, F, P],
     "opsg_gemm_streamk_workspace_bytes": [I, I],
     "opsg_gemm_bf16_streamk": [P, I, P, I, P, I, I, I, I, P, P, I, I, I, P, ctypes.c_size_t, P],
     "opsg_cast_f32_bf16": [P, I, P, I, I, I, P],

@@ -248,22 +248,23 @@ __device__ __forceinline__ float warp_max(float v) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-// erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 rounding of the
-// result): 2 MUFU (rcp, ex2) + ~12 FMA-pipe instructions instead of erff()'s two-branch polynomial.
+// erf-GELU with ONE MUFU op:  gelu(x) = x Phi(x) = relu(x) - |x| * 0.5 erfc(|x| / sqrt2) = relu(x) - |x| * 2^q(|x|),
+// q(t) = log2(0.5 erfc(t / sqrt2)) as a degree-6 polynomial (weighted minimax fit on [0, 6], scripts/fit_gelu.py:
+// |error| <= 3.2e-7 absolute and <= 9e-5 relative for |gelu| >= 1e-3 in fp32 -- the bf16 rounding of the result is 4e-3).
+// The exponential form has no cancellation on the negative side.  6 FMA + FMNMX x2 + FFMA + 1 MUFU.EX2; the previous
+// Abramowitz-Stegun 7.1.26 form needed rcp + ex2 and made the GELU epilogue MUFU-bound (8 cycles per warp instruction).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float a = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
+  const float t = fminf(fabsf(x), 6.0f);
+  float p = 2.992444387928117e-05f;
+  p = fmaf(p, t, -0.0007398762973025441f);
+  p = fmaf(p, t, 0.007977468892931938f);
+  p = fmaf(p, t, -0.053238194435834885f);
+  p = fmaf(p, t, -0.45891568064689636f);
+  p = fmaf(p, t, -1.1511471271514893f);
+  p = fmaf(p, t, -1.0f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * a * -1.4426950408889634f));
-  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2)
-  const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), erf_abs, hx);                 // 0.5x(1 + sign(x) erf_abs) = hx + |hx| erf_abs
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
+  return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 }
 
 }  // namespace opsg

@@ -22,7 +22,8 @@
 namespace opsg {
 
 int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, opsg_bf16* D, int ldd, int M, int N, int K,
-                     const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, cudaStream_t stream);
+                     const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, const GemmLnFold* ln,
+                     cudaStream_t stream);
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
@@ -480,6 +481,28 @@ static void streamk_shape(int N, int K, int sms, int* n_tiles, int* kb_total, in
 
 using namespace opsg;
 
+extern "C" int opsg_gemm_bf16_ln(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, opsg_bf16* D, int ldd, int M, int N,
+                                 int K, const float* bias, const opsg_bf16* residual, int ldr, int act, const float* a_stats,
+                                 const float* a_colsum, const float* r_stats, const float* r_gamma, const float* r_beta,
+                                 float* stats_out, float eps, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(A && W && D, "gemm_ln: null pointer");
+  OPSG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_ln: bad shape M=%d N=%d K=%d", M, N, K);
+  OPSG_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "gemm_ln: leading dimension too small");
+  OPSG_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && (ldd % 8) == 0 && (N % 8) == 0, "gemm_ln: lda/ldw/ldd/N must be multiples of 8");
+  OPSG_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)D & 15) == 0, "gemm_ln: A/W/D must be 16-byte aligned");
+  OPSG_CHECK_ARG(act >= OPSG_ACT_NONE && act <= OPSG_ACT_RELU, "gemm_ln: bad activation");
+  OPSG_CHECK_ARG(!a_stats || a_colsum, "gemm_ln: a_stats without a_colsum");
+  OPSG_CHECK_ARG(!r_stats || (residual && r_gamma && r_beta), "gemm_ln: r_stats needs residual, r_gamma and r_beta");
+  OPSG_CHECK_ARG(!residual || (ldr >= N && (ldr % 8) == 0 && ((uintptr_t)residual & 15) == 0), "gemm_ln: bad residual layout");
+  OPSG_CHECK_ARG(!r_stats || ((((uintptr_t)r_gamma | (uintptr_t)r_beta) & 15) == 0), "gemm_ln: r_gamma / r_beta must be 16-byte aligned");
+  GemmLnFold ln{a_stats, a_colsum, r_stats, r_gamma, r_beta, stats_out, eps};
+  rc = launch_gemm_2cta(A, lda, W, ldw, D, ldd, M, N, K, bias, 0, residual, ldr, act, &ln, reinterpret_cast<cudaStream_t>(stream));
+  if (rc == OPSG_E_UNSUPPORTED) return set_error(rc, "gemm_ln: unsupported layout");
+  return rc;
+}
+
 extern "C" size_t opsg_gemm_streamk_workspace_bytes(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
   int n_tiles, kb_total, grid, max_segs;
@@ -560,7 +583,7 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
   static const int use_2cta = [] { const char* e = getenv("OPSG_GEMM_2CTA"); return e ? atoi(e) : 1; }();
   if (use_2cta && out_mode == OPSG_OUT_BF16 && k_splits == 1) {
     rc = launch_gemm_2cta(A, lda, W, ldw, reinterpret_cast<opsg_bf16*>(D), ldd, M, N, K, bias, bias_along_m, residual, ldr, act,
-                          reinterpret_cast<cudaStream_t>(stream));
+                          nullptr, reinterpret_cast<cudaStream_t>(stream));
     if (rc != OPSG_E_UNSUPPORTED) return rc;
   }
 

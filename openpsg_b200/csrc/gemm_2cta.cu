@@ -12,9 +12,10 @@
 //   warp 1  MMA issuer   : leader only — tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16), accumulator rows 0-127 in
 //                          the leader's TMEM, rows 128-255 in the peer's; tcgen05.commit multicasts to both CTAs' barriers
 //   warp 2  TMEM allocator (tcgen05.alloc.cta_group::2, both CTAs)
-//   warps 4-11 epilogue  : own 128 rows: tcgen05.ld -> bias / residual / activation -> bf16 -> swizzled smem -> TMA store;
-//                          the accumulator stage is handed back by arriving on the LEADER's tmem_empty barrier (remote
-//                          mbarrier arrive from the peer)
+//   warp 3  slab warp    : ring of [128 x 64] staging slabs: TMA-loads the residual slab, TMA-stores the packed result
+//   warps 4-11 epilogue  : own 128 rows: tcgen05.ld -> LayerNorm fold / bias / residual / activation -> bf16 -> swizzled
+//                          smem; column vectors of the next tile are prefetched into shared memory; the accumulator stage
+//                          is handed back by arriving on the LEADER's tmem_empty barrier (remote arrive from the peer)
 #include "common.cuh"
 #include "host_util.h"
 
@@ -26,13 +27,16 @@ constexpr int kBN = 256;           // tile N (each CTA stages 128 of the 256 W^T
 constexpr int kBK = 64;
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
-constexpr int kStages = 6;
 constexpr int kABytes = kBM * kBK * 2;          // 16384
 constexpr int kBBytes = (kBN / 2) * kBK * 2;    // 16384
 constexpr int kStageBytes = kABytes + kBBytes;  // 32768 per CTA
 constexpr int kSlabBytes = kBM * 128;           // [128 rows x 64 bf16] staging slab
-constexpr int kSmemTotal = kStages * kStageBytes + 2 * kSlabBytes + 1024 + 1024;
-static_assert(kSmemTotal <= 232448, "shared memory budget exceeded");
+constexpr int kVecBytes = 2 * 4 * kBN * 4;      // [tile parity][bias | colsum | gamma | beta][256] fp32
+constexpr int kAugBytes = kBM * 16 * 2;         // [128 rows x 16 k] bf16, no-swizzle core-matrix order (bias as one more MMA)
+// STAGES operand stages + NB staging slabs (output, and the TMA-loaded residual it is accumulated onto in place)
+template <int STAGES, int NB>
+constexpr int smem_total() { return STAGES * kStageBytes + NB * kSlabBytes + kVecBytes + 2 * kAugBytes + 256 + 1024; }
+constexpr int kBarVec = 2;                      // named barrier of the 256 epilogue threads (0 = __syncthreads)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even (leader) CTA
 
 struct Params {
@@ -40,9 +44,20 @@ struct Params {
   const __nv_bfloat16* residual;
   int M, N, K;
   int ldr;
+  int res_tma;                // residual rows are 16-byte aligned: the slab warp loads them with TMA
   int bias_along_m;
+  int bias_mma;               // the per-column bias is added by the tensor core (one extra K = 16 step per tile)
   int act;
   int m2_tiles, n_tiles;
+  // ---- LayerNorm folding (all optional; see opsg_gemm_bf16_ln in include/opsg_b200.h) ----
+  const float2* a_stats;      // per row of A: (sum, sum of squares) over the K features of the UN-normalised A row
+  const float* a_colsum;      // per output column n: sum_k W'[n, k]   (W' = W with the pending LayerNorm's gamma folded in)
+  const float2* r_stats;      // per row of the residual: (sum, sum of squares) over its N features
+  const float* r_gamma;       // the pending LayerNorm of the residual tensor
+  const float* r_beta;
+  float2* stats_out;          // per output row: accumulates (sum, sum of squares) of the stored values (fp32 atomics)
+  float ln_eps;
+  long long* trace;           // debug: clock64 stamps of CTA 0's epilogue ([tile][slab][8]); NULL in production
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -86,6 +101,9 @@ __device__ __forceinline__ void tc_commit_2cta_mcast(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
                : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // arrive on the barrier at this smem offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
@@ -96,30 +114,75 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       : "memory");
 }
 
+// remote arrive that also publishes this thread's earlier shared-memory writes to the other CTA of the pair
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > OPSG_WAIT_LIMIT_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+template <int STAGES, int NB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmD, const Params p) {
+                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const Params p) {
+  static_assert(smem_total<STAGES, NB>() <= 232448, "shared memory budget exceeded");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* staging = smem + kStages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kSlabBytes);   // used in the leader CTA only
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;   // [2]
+  uint8_t* smem_b = smem + STAGES * kABytes;
+  uint8_t* staging = smem + STAGES * kStageBytes;
+  float* sVec = reinterpret_cast<float*>(staging + NB * kSlabBytes);
+  uint8_t* aug_a = staging + NB * kSlabBytes + kVecBytes;   // ones in k = 0, 1
+  uint8_t* aug_b = aug_a + kAugBytes;                       // this CTA's 128 W^T rows: (bias_hi, bias_lo, 0, ...)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aug_b + kAugBytes);   // used in the leader CTA only
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2] used in the leader CTA only (both CTAs' epilogues arrive there)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* slab_ready = tmem_empty + 2;       // [NB] store warp -> epilogue: slab free (and its residual loaded)
+  uint64_t* slab_full = slab_ready + NB;       // [NB] epilogue -> store warp: slab packed
+  uint64_t* bias_full = slab_full + NB;        // leader only: both CTAs' halves of the bias operand are written
+  uint64_t* bias_empty = bias_full + 1;        // both CTAs: the bias MMA of the tile has read them
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bias_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  // residual through TMA needs 16-byte rows; anything else takes the per-element path
+  const bool res_tma = p.residual && p.res_tma;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
-    for (int s = 0; s < kStages; ++s) {
+    if (res_tma) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -127,6 +190,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * (kEpiThreads / 32));     // one arrival per epilogue warp of both CTAs
     }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&slab_ready[s], 1);
+      mbar_init(&slab_full[s], kEpiThreads / 32);            // one arrival per epilogue warp
+    }
+    mbar_init(bias_full, 2);
+    mbar_init(bias_empty, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -143,6 +212,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int pair = blockIdx.x >> 1;
   const int total_tiles = p.m2_tiles * p.n_tiles;
   const int kb_total = (p.K + kBK - 1) / kBK;
+  constexpr int NSLAB = kBN / 64;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -160,7 +230,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_2d_2cta(smem_b + stage * kBBytes, &tmB, &full_bar[stage], kb * kBK, row_b);
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && leader) {
@@ -169,7 +239,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, bias_phase = 0;
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -184,70 +254,179 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < kBK / 16; ++k)
             umma_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           tc_commit_2cta_mcast(&empty_bar[stage]);                     // frees the stage in both CTAs
-          if (kb + 1 == kb_total) tc_commit_2cta_mcast(&tmem_full[acc]);
+          if (kb + 1 == kb_total && !p.bias_mma) tc_commit_2cta_mcast(&tmem_full[acc]);
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (p.bias_mma) {
+        // + bias[n]: A_aug = ones in k = 0, 1; B_aug row n = (bias_hi[n], bias_lo[n], 0 ...) -- one K = 16 step instead of
+        // 256 broadcast shared-memory reads + 128 FADDs per epilogue thread (the LSU wavefronts compete with the tensor
+        // core's operand reads for the same shared-memory data pipe, profiles/r1_ncu_gemm2_epilogue.md)
+        mbar_wait_cluster_acquire(bias_full, bias_phase);
+        bias_phase ^= 1;
+        tc_fence_after();
+        if (elect_one_sync()) {
+          umma_ss_2cta(d_tmem, umma_desc_k_noswz(smem_u32(aug_a), 128, 256), umma_desc_k_noswz(smem_u32(aug_b), 128, 256),
+                       idesc, 1u);
+          tc_commit_2cta_mcast(bias_empty);
+          tc_commit_2cta_mcast(&tmem_full[acc]);
+        }
+        __syncwarp();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  } else if (warp == 2 && p.bias_mma) {
+    // ===================== bias operand builder (both CTAs) =====================
+    for (int i = lane; i < 2 * kAugBytes / 16; i += 32) reinterpret_cast<uint4*>(aug_a)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    for (int r = lane; r < kBM; r += 32)                        // 1.0 (bf16 0x3F80) in k = 0 and k = 1 of every row
+      *reinterpret_cast<uint32_t*>(aug_a + (r >> 3) * 256 + (r & 7) * 16) = 0x3F803F80u;
+    uint32_t ph = 0;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int n0 = (tile % p.n_tiles) * kBN + static_cast<int>(rank) * (kBN / 2);
+      float bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = n0 + i * 32 + lane;
+        bv[i] = col < p.N ? __ldg(p.bias + col) : 0.f;
+      }
+      mbar_wait(bias_empty, ph ^ 1);                            // the previous tile's bias MMA has read the operand
+      ph ^= 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 32 + lane;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(bv[i]);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(bv[i] - __bfloat162float(hi));
+        *reinterpret_cast<uint32_t*>(aug_b + (r >> 3) * 256 + (r & 7) * 16) =
+            static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_release(bias_full, 0);
+    }
+  } else if (warp == 3) {
+    // ===================== slab warp (both CTAs, one thread) =====================
+    // Owns the ring of NB staging slabs.  For slab number g (global over this CTA's tiles) in buffer g % NB:
+    //   hand-out : TMA-load the residual slab into the buffer (or just arrive when there is no residual)  -> slab_ready
+    //   epilogue : accumulates onto it in place, packs bf16, fence.proxy.async                            -> slab_full
+    //   here     : TMA store; once the PREVIOUS store has been read out of shared memory its buffer is handed out again
+    // Residual rows used to be fetched by the epilogue threads with 16-byte __ldg: with ~220 KB of shared memory the L1
+    // holds only a few KB of in-flight lines and the 16 KB slab took 2-3 dependent round trips (~3000 cycles per slab).
+    if (lane == 0) {
+      const int my_tiles = pair < total_tiles ? (total_tiles - pair + num_pairs - 1) / num_pairs : 0;
+      const int total_slabs = my_tiles * NSLAB;
+      auto coords = [&](int g, int& c0, int& r0) {
+        const int tile = pair + (g / NSLAB) * num_pairs;
+        const int n_t = tile % p.n_tiles, m2_t = tile / p.n_tiles;
+        c0 = n_t * kBN + (g % NSLAB) * 64;
+        r0 = m2_t * 2 * kBM + static_cast<int>(rank) * kBM;
+      };
+      auto hand_out = [&](int g) {
+        const int b = g % NB;
+        int c0, r0;
+        coords(g, c0, r0);
+        if (res_tma && c0 < p.N && r0 < p.M) {
+          mbar_expect_tx(&slab_ready[b], kSlabBytes);
+          tma_load_2d(staging + b * kSlabBytes, &tmR, &slab_ready[b], c0, r0);
+        } else {
+          mbar_arrive(&slab_ready[b]);
+        }
+      };
+      for (int g = 0; g < NB && g < total_slabs; ++g) hand_out(g);
+      for (int g = 0; g < total_slabs; ++g) {
+        const int b = g % NB;
+        mbar_wait(&slab_full[b], (g / NB) & 1);
+        int c0, r0;
+        coords(g, c0, r0);
+        if (c0 < p.N && r0 < p.M) tma_store_2d(staging + b * kSlabBytes, &tmD, c0, r0);
+        tma_store_commit();                    // always commit (possibly empty): one bulk group per slab
+        tma_store_wait_read<1>();              // every store but the one just issued has left shared memory
+        if (g >= 1 && g - 1 + NB < total_slabs) hand_out(g - 1 + NB);
+      }
+      tma_store_wait_all<0>();
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
-    constexpr int NSLAB = kBN / 64;
     const int ew = warp - 4;
     const int q = ew & 3;
     const int half = ew >> 2;
     const int row_in_tile = q * 32 + lane;
-    const bool elected = (threadIdx.x == 4 * 32);
+    const int et = threadIdx.x - 4 * 32;                       // 0..255 inside the epilogue
+    const bool tracer = (et == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t buf = 0;
+    int g = 0;                                                 // slab number (same sequence as the slab warp's)
     const __nv_bfloat16* resid = p.residual;
 
-    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+    // Column vectors of a tile (bias, LayerNorm-fold column sums, residual LayerNorm gamma / beta).  Thread et fetches
+    // column et of the NEXT tile's vectors while the current tile is processed and parks them in sVec[parity]; slabs read
+    // them from shared memory (a per-slab __ldg is an L2 round trip here: the L1 is a few KB).
+    auto load_vec = [&](int n_t) {
+      const int col = n_t * kBN + et;
+      const bool ok = col < p.N;
+      float4 v;
+      v.x = (p.bias && !p.bias_along_m && ok) ? __ldg(p.bias + col) : 0.f;
+      v.y = (p.a_stats && ok) ? __ldg(p.a_colsum + col) : 0.f;
+      v.z = (p.r_stats && ok) ? __ldg(p.r_gamma + col) : 1.f;
+      v.w = (p.r_stats && ok) ? __ldg(p.r_beta + col) : 0.f;
+      return v;
+    };
+    auto park_vec = [&](int parity, const float4& v) {
+      float* dst = sVec + parity * 4 * kBN + et;
+      dst[0] = v.x; dst[kBN] = v.y; dst[2 * kBN] = v.z; dst[3 * kBN] = v.w;
+    };
+    int tile_seq = 0;
+    if (pair < total_tiles) park_vec(0, load_vec(pair % p.n_tiles));
+#define G2_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && tracer && tile_seq < 24) p.trace[(tile_seq * 5 + (slab_for_trace)) * 8 + (slot)] = clock64(); } while (0)
+    for (int tile = pair; tile < total_tiles; tile += num_pairs, ++tile_seq) {
       const int n_t = tile % p.n_tiles, m2_t = tile / p.n_tiles;
       const int row0 = m2_t * 2 * kBM + static_cast<int>(rank) * kBM;
       const int row = row0 + row_in_tile;
+      int slab_for_trace = 4;
       const bool row_ok = row < p.M;
-      const float bias_m = (p.bias && p.bias_along_m && row_ok) ? p.bias[row] : 0.f;
+      const float* vec = sVec + (tile_seq & 1) * 4 * kBN;       // [bias | colsum | gamma | beta][256] of this tile
+      const bool has_next = tile + num_pairs < total_tiles;
+      float4 vnext = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_next) vnext = load_vec((tile + num_pairs) % p.n_tiles);
+      const float bias_m = (p.bias && p.bias_along_m && row_ok) ? __ldg(p.bias + row) : 0.f;
+      // LayerNorm folding: y = rstd_a * (acc - mean_a * colsum[n]) + bias'[n]  ==  LN(A row) . W^T + bias
+      float a_rstd = 1.f, a_mean = 0.f, r_rstd = 1.f, r_mean = 0.f;
+      if (p.a_stats && row_ok) {
+        const float2 st = __ldg(p.a_stats + row);
+        a_mean = st.x / static_cast<float>(p.K);
+        a_rstd = rsqrtf(fmaxf(st.y / static_cast<float>(p.K) - a_mean * a_mean, 0.f) + p.ln_eps);
+      }
+      if (p.r_stats && row_ok) {
+        const float2 st = __ldg(p.r_stats + row);
+        r_mean = st.x / static_cast<float>(p.N);
+        r_rstd = rsqrtf(fmaxf(st.y / static_cast<float>(p.N) - r_mean * r_mean, 0.f) + p.ln_eps);
+      }
+      float s_sum = 0.f, s_sq = 0.f;             // this thread's share of the output row statistics
+      named_bar_sync(kBarVec, kEpiThreads);      // this tile's column vectors are parked (all threads left the last tile)
 
-      // Residual slab [128 rows x 64 cols] of this CTA: loaded COOPERATIVELY (8 consecutive threads = one 128-byte row
-      // segment, 4 x 16 bytes per thread) one slab ahead into registers, parked in the staging slab, then every thread
-      // picks up its own row from shared memory.  (Each thread loading 64 bytes of its own row — the first version —
-      // made every load instruction touch 32 different rows: 128 L1 wavefronts per warp and slab instead of 16, and the
-      // residual GEMMs ran at 790 TFLOP/s while the plain ones reached 1540.)
-      const int et = threadIdx.x - 4 * 32;                       // 0..255 inside the epilogue
-      const bool res_fast = resid && (p.ldr % 8) == 0 && (p.N % 8) == 0 && ((reinterpret_cast<uintptr_t>(resid) & 15) == 0);
-      uint4 rres[4];
-      auto fetch_residual = [&](int slab) {
-        if (!res_fast) return;
-        const int c0 = n_t * kBN + slab * 64;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int idx = j * kEpiThreads + et, r = idx >> 3, ch = idx & 7;
-          const int grow = row0 + r, gcol = c0 + ch * 8;
-          rres[j] = (grow < p.M && gcol + 8 <= p.N)
-                        ? __ldg(reinterpret_cast<const uint4*>(resid + static_cast<size_t>(grow) * p.ldr + gcol))
-                        : make_uint4(0, 0, 0, 0);
-        }
-      };
-      fetch_residual(0);
-
+      G2_TRACE(0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      G2_TRACE(1);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBN;
 
 #pragma unroll 1
-      for (int slab = 0; slab < NSLAB; ++slab) {
-        const int col0 = n_t * kBN + slab * 64 + half * 32;
+      for (int slab = 0; slab < NSLAB; ++slab, ++g) {
+        const int lc = slab * 64 + half * 32;                    // column inside the tile
+        const int col0 = n_t * kBN + lc;
+        const int b = g % NB;
+        slab_for_trace = slab;
+        G2_TRACE(0);
         float f[32];
         {
           uint32_t v[32];
-          tmem_ld32(taddr + slab * 64 + half * 32, v);
+          tmem_ld32(taddr + lc, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         }
+        G2_TRACE(1);
         if (slab == NSLAB - 1) {            // accumulator fully read -> hand the TMEM stage back to the leader's MMA warp
           tc_fence_before();
           __syncwarp();
@@ -255,51 +434,56 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         const bool col_ok = col0 < p.N;
         const bool full = col0 + 32 <= p.N;
+        uint8_t* rowp = staging + b * kSlabBytes + row_in_tile * 128;
         if (col_ok) {
-          if (p.bias) {
+          if (p.a_stats) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 c4 = *reinterpret_cast<const float4*>(vec + 1 * kBN + lc + j * 4);
+              f[j * 4 + 0] = a_rstd * fmaf(-a_mean, c4.x, f[j * 4 + 0]); f[j * 4 + 1] = a_rstd * fmaf(-a_mean, c4.y, f[j * 4 + 1]);
+              f[j * 4 + 2] = a_rstd * fmaf(-a_mean, c4.z, f[j * 4 + 2]); f[j * 4 + 3] = a_rstd * fmaf(-a_mean, c4.w, f[j * 4 + 3]);
+            }
+          }
+          if (p.bias && !p.bias_mma) {
             if (p.bias_along_m) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] += bias_m;
-            } else if (full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-                f[j * 4 + 0] += b4.x; f[j * 4 + 1] += b4.y; f[j * 4 + 2] += b4.z; f[j * 4 + 3] += b4.w;
-              }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = *reinterpret_cast<const float4*>(vec + lc + j * 4);
+                f[j * 4 + 0] += b4.x; f[j * 4 + 1] += b4.y; f[j * 4 + 2] += b4.z; f[j * 4 + 3] += b4.w;
+              }
             }
           }
-          if (resid && !res_fast && row_ok) {
+          if (resid && !res_tma && row_ok) {
             const __nv_bfloat16* r = resid + static_cast<size_t>(row) * p.ldr + col0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) f[j] += __bfloat162float(r[j]);
           }
         }
-        uint8_t* rowp = staging + buf * kSlabBytes + row_in_tile * 128;
-        // staging slab `buf`: its previous TMA store (two slabs ago) must have drained before we overwrite it
-        if (elected) tma_store_wait_read<1>();
-        named_bar_sync(1, kEpiThreads);
-        if (res_fast) {
+        G2_TRACE(2);
+        mbar_wait(&slab_ready[b], (g / NB) & 1);                 // buffer drained by its last store (+ residual landed)
+        G2_TRACE(3);
+        if (res_tma && col_ok) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                          // park the prefetched residual slab (swizzled like the output)
-            const int idx = j * kEpiThreads + et, r = idx >> 3, ch = idx & 7;
-            *reinterpret_cast<uint4*>(staging + buf * kSlabBytes + r * 128 + ((ch ^ (r & 7)) * 16)) = rres[j];
-          }
-          if (slab + 1 < NSLAB) fetch_residual(slab + 1);
-          named_bar_sync(3, kEpiThreads);
-          if (col_ok) {
+          for (int gq = 0; gq < 4; ++gq) {                       // this thread's 64 bytes of its own row, in place
+            const uint4 u = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + gq) ^ (row_in_tile & 7)) * 16));
+            float rv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                           bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+            if (p.r_stats) {         // the residual tensor is stored un-normalised: apply its pending LayerNorm here
+              const float4 g0 = *reinterpret_cast<const float4*>(vec + 2 * kBN + lc + gq * 8);
+              const float4 g1 = *reinterpret_cast<const float4*>(vec + 2 * kBN + lc + gq * 8 + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(vec + 3 * kBN + lc + gq * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(vec + 3 * kBN + lc + gq * 8 + 4);
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + g) ^ (row_in_tile & 7)) * 16));
-              f[g * 8 + 0] += bf16_lo(u.x); f[g * 8 + 1] += bf16_hi(u.x);
-              f[g * 8 + 2] += bf16_lo(u.y); f[g * 8 + 3] += bf16_hi(u.y);
-              f[g * 8 + 4] += bf16_lo(u.z); f[g * 8 + 5] += bf16_hi(u.z);
-              f[g * 8 + 6] += bf16_lo(u.w); f[g * 8 + 7] += bf16_hi(u.w);
+              for (int e = 0; e < 8; ++e) rv[e] = fmaf((rv[e] - r_mean) * r_rstd, gg[e], bb[e]);
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[gq * 8 + e] += rv[e];
           }
         }
         if (col_ok) {
@@ -311,30 +495,36 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
         }
-        {
+        if (p.stats_out && col_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = (half * 4 + g) ^ (row_in_tile & 7);
-            uint4 u;
-            u.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-            u.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-            u.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-            u.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
-          }
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) { s_sum += f[j]; s_sq = fmaf(f[j], f[j], s_sq); }
         }
+        G2_TRACE(4);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const int chunk = (half * 4 + gq) ^ (row_in_tile & 7);
+          uint4 u;
+          u.x = pack_bf16x2(f[gq * 8 + 0], f[gq * 8 + 1]);
+          u.y = pack_bf16x2(f[gq * 8 + 2], f[gq * 8 + 3]);
+          u.z = pack_bf16x2(f[gq * 8 + 4], f[gq * 8 + 5]);
+          u.w = pack_bf16x2(f[gq * 8 + 6], f[gq * 8 + 7]);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
+        }
+        G2_TRACE(5);
         fence_proxy_async_smem();
-        named_bar_sync(2, kEpiThreads);
-        if (elected) {     // always commit (possibly empty) so that group counting stays one-per-slab
-          if (n_t * kBN + slab * 64 < p.N && row0 < p.M)
-            tma_store_2d(staging + buf * kSlabBytes, &tmD, n_t * kBN + slab * 64, row0);
-          tma_store_commit();
-        }
-        buf ^= 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slab_full[b]);               // the slab warp stores it
+        G2_TRACE(6);
+      }
+      slab_for_trace = 4;
+      if (has_next) park_vec((tile_seq + 1) & 1, vnext);         // read after the barrier at the top of the next tile
+      if (p.stats_out && row_ok) {
+        atomicAdd(&p.stats_out[row].x, s_sum);
+        atomicAdd(&p.stats_out[row].y, s_sq);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (elected) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -348,36 +538,66 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 }  // namespace g2
 
+static long long* g_gemm2_trace = nullptr;
+}  // namespace opsg
+// debug hook (not part of the public header): device buffer of >= 24*5*8 int64 for epilogue clock stamps of CTA 0
+extern "C" void opsg_debug_gemm2_trace(void* dev_buffer) { opsg::g_gemm2_trace = reinterpret_cast<long long*>(dev_buffer); }
+namespace opsg {
+
 // Launch helper used by opsg_gemm_bf16 (gemm.cu).  Returns OPSG_E_UNSUPPORTED when the shape should use the 1-CTA kernel.
 int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, opsg_bf16* D, int ldd, int M, int N, int K,
-                     const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, cudaStream_t stream) {
+                     const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, const GemmLnFold* ln,
+                     cudaStream_t stream) {
   using namespace g2;
   const int sms = opsg_num_sms();
   const int m2_tiles = (M + 2 * kBM - 1) / (2 * kBM);
   const int n_tiles = (N + kBN - 1) / kBN;
-  if (N < kBN || m2_tiles * n_tiles < sms / 2 || (ldd % 8) != 0 || (reinterpret_cast<uintptr_t>(D) & 15) != 0)
-    return OPSG_E_UNSUPPORTED;
-  CUtensorMap tmA, tmB, tmD;
+  if ((ldd % 8) != 0 || (reinterpret_cast<uintptr_t>(D) & 15) != 0) return OPSG_E_UNSUPPORTED;
+  if (!ln && (N < kBN || m2_tiles * n_tiles < sms / 2)) return OPSG_E_UNSUPPORTED;     // small problems: 1-CTA kernel
+  CUtensorMap tmA, tmB, tmD, tmR;
   int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, kBN / 2, kBK);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmD, D, (uint64_t)M, (uint64_t)N, (uint64_t)ldd, kBM, 64);
   if (rc) return rc;
+  const bool res_tma = residual && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0;
+  tmR = tmD;
+  if (res_tma) {
+    rc = make_tmap_bf16_2d(&tmR, residual, (uint64_t)M, (uint64_t)N, (uint64_t)ldr, kBM, 64);
+    if (rc) return rc;
+  }
+  // operand stages x staging slabs: a residual wants a deeper slab ring (its loads are in flight for a slab period or two)
+  static const int forced = [] { const char* e = getenv("OPSG_GEMM2_VARIANT"); return e ? atoi(e) : 0; }();
+  const bool deep_ring = forced == 2;      // measured: <5,3> is at least as fast as <4,4> with a residual too
+  auto kernel = deep_ring ? gemm2_bf16_kernel<4, 4> : gemm2_bf16_kernel<5, 3>;
+  const int smem_bytes = deep_ring ? smem_total<4, 4>() : smem_total<5, 3>();
   static bool configured = false;
   if (!configured) {
-    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal),
-                    "cudaFuncSetAttribute(gemm 2cta)");
+    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<4, 4>()),
+                    "cudaFuncSetAttribute(gemm 2cta <4,4>)");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<5, 3>()),
+                    "cudaFuncSetAttribute(gemm 2cta <5,3>)");
     if (rc) return rc;
     configured = true;
   }
   Params p;
   p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.M = M; p.N = N; p.K = K; p.ldr = ldr; p.bias_along_m = bias_along_m; p.act = act;
+  p.M = M; p.N = N; p.K = K; p.ldr = ldr; p.bias_along_m = bias_along_m; p.act = act; p.res_tma = res_tma ? 1 : 0;
+  static const int bias_mma_on = [] { const char* e = getenv("OPSG_GEMM2_BIAS_MMA"); return e ? atoi(e) : 1; }();
+  p.bias_mma = (bias && !bias_along_m && !(ln && ln->a_stats) && bias_mma_on) ? 1 : 0;
   p.m2_tiles = m2_tiles; p.n_tiles = n_tiles;
+  p.a_stats = nullptr; p.a_colsum = nullptr; p.r_stats = nullptr; p.r_gamma = nullptr; p.r_beta = nullptr;
+  p.stats_out = nullptr; p.ln_eps = 0.f; p.trace = g_gemm2_trace;
+  if (ln) {
+    p.a_stats = reinterpret_cast<const float2*>(ln->a_stats); p.a_colsum = ln->a_colsum;
+    p.r_stats = reinterpret_cast<const float2*>(ln->r_stats); p.r_gamma = ln->r_gamma; p.r_beta = ln->r_beta;
+    p.stats_out = reinterpret_cast<float2*>(ln->stats_out); p.ln_eps = ln->eps;
+  }
   int pairs = sms / 2;
   if (m2_tiles * n_tiles < pairs) pairs = m2_tiles * n_tiles;
-  gemm2_bf16_kernel<<<2 * pairs, kThreads, kSmemTotal, stream>>>(tmA, tmB, tmD, p);
+  kernel<<<2 * pairs, kThreads, smem_bytes, stream>>>(tmA, tmB, tmD, tmR, p);
   OPSG_CHECK_LAUNCH("gemm2_bf16_kernel");
   return OPSG_OK;
 }

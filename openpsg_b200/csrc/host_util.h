@@ -16,6 +16,17 @@ int check_cuda(cudaError_t e, const char* what);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// LayerNorm-folding arguments of the CTA-pair GEMM (opsg_gemm_bf16_ln); any group may be null
+struct GemmLnFold {
+  const float* a_stats;    // [M, 2] (sum, sumsq) of the un-normalised A rows, or null
+  const float* a_colsum;   // [N]
+  const float* r_stats;    // [M, 2] of the un-normalised residual rows, or null
+  const float* r_gamma;    // [N]
+  const float* r_beta;     // [N]
+  float* stats_out;        // [M, 2] accumulated (sum, sumsq) of the output rows, or null
+  float eps;
+};
+
 #define OPSG_CHECK_ARG(cond, ...)                                   \
   do {                                                              \
     if (!(cond)) return ::opsg::set_error(OPSG_E_INVALID, __VA_ARGS__); \

@@ -131,6 +131,30 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, residual: Optional[torch.Tensor] = None,
+            act: int = ACT_NONE, out: Optional[torch.Tensor] = None, a_stats: Optional[torch.Tensor] = None,
+            a_colsum: Optional[torch.Tensor] = None, r_stats: Optional[torch.Tensor] = None,
+            r_gamma: Optional[torch.Tensor] = None, r_beta: Optional[torch.Tensor] = None,
+            stats_out: Optional[torch.Tensor] = None, eps: float = 1e-12) -> torch.Tensor:
+    """LayerNorm-folding GEMM (opsg_gemm_bf16_ln): a / residual may be un-normalised tensors with fp32 [rows, 2]
+    (sum, sumsq) statistics; stats_out (zeroed by the caller) receives the statistics of the output rows."""
+    _cuda(a, torch.bfloat16, "a"); _cuda(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    for t, n in ((a_stats, M), (r_stats, M), (stats_out, M)):
+        assert t is None or (t.dtype == torch.float32 and t.shape == (n, 2) and t.is_contiguous())
+    with _timed("gemm_bf16", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)):
+        _lib.check(_lib.load().opsg_gemm_bf16_ln(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                                _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
+                                                act, _ptr(a_stats), _ptr(a_colsum), _ptr(r_stats), _ptr(r_gamma), _ptr(r_beta),
+                                                _ptr(stats_out), float(eps), _stream()))
+    _count()
+    return out
+
+
 _streamk_ws = {}     # device -> uint8 workspace, grown on demand
 _streamk_ws_keep = []  # outgrown workspaces stay alive: captured CUDA graphs may still point at them
 

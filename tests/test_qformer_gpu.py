@@ -129,7 +129,12 @@ def test_subset_of_pairs_equals_full_run(head):
                       enc["input_ids"].to(torch.int32).cuda(), enc["attention_mask"].to(torch.int32).cuda(),
                       pair_index=idx.cuda(), topk=5)
     sub = out.hidden.float().cpu().reshape(5, 33, 768)
-    assert (sub - full[idx.long()]).abs().max() < 2e-2     # same arithmetic, different tile packing
+    # Same arithmetic up to rounding: 5 pairs take the single-CTA GEMM (fp32 bias add in the epilogue), 64 pairs the
+    # CTA-pair GEMM (bias through the tensor core as bf16 hi + lo), so a few bf16 activations flip by one ulp
+    # (0.016 in [2, 4), 0.031 in [4, 8)) and the flips spread through the two layers: measured max 0.031 / mean 0.0025,
+    # well inside the parity budget against the reference (max 8e-2 / mean 8e-3).
+    d = (sub - full[idx.long()]).abs()
+    assert d.max() < 6e-2 and d.mean() < 4e-3, (float(d.max()), float(d.mean()))
 
 
 def test_graph_replay_and_forward_batch_equal_eager():
