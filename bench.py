@@ -236,6 +236,33 @@ def run_ours(args):
         assert len(outs) == len(host_inputs) and len(res) == len(host_inputs)
         return res
 
+    # result buffers of the streamed e2e leg: pinned, one slot per image of the timed region, filled by asynchronous D2H
+    # copies on the compute stream (ordered before the next image overwrites head.last_output)
+    res_slots = [torch.empty(20, dtype=torch.int32).pin_memory() for _ in range(ips * max(args.steps, 2))]
+
+    def run_e2e_stream(steps):
+        """ONE forward_batch call over the images of `steps` consecutive steps (a stream of host images, as a serving
+        loop feeds them): the H2D of every image, the first of a step included, overlaps the previous image's kernels."""
+        k = [0]
+
+        def grab(h):
+            res_slots[k[0]].copy_(h.last_output.topk.reshape(-1)[:20], non_blocking=True)
+            k[0] += 1
+        outs = head.forward_batch(host_inputs * steps, on_result=grab)
+        assert len(outs) == ips * steps and k[0] == ips * steps
+
+    def timed_call(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
     def step_e2e_single():   # the reference-facing batch-1 call with host tensors, no prefetch
         return [(head(inp), head.last_output.topk.cpu())[1] for inp in host_inputs]
 
@@ -263,22 +290,32 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # value: the images of K steps, resident in HBM, through ONE forward_batch call (host-side parsing of image i+1
+    # overlaps the kernels of image i; separate head(inputs) calls read the object ids back with a stream-wide sync
+    # per image, as the reference does, and are reported as ms_per_step_separate_calls)
+    def run_resident(steps):
+        outs = head.forward_batch(dev_inputs * steps)
+        assert len(outs) == ips * steps
+    run_resident(2)
     l0 = ops.launch_count
-    ms = timed(step_resident, args.steps)
+    ms = timed_call(lambda: run_resident(args.steps))
     launches = ops.launch_count - l0
+    ms_separate = timed(step_resident, args.steps) / args.steps
     pairs_per_step = wl.ordered_pairs * ips * world
     value = pairs_per_step * args.steps / (ms * 1e-3)
 
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    run_e2e_stream(2)
+    ms_e2e = timed_call(lambda: run_e2e_stream(args.steps))
     e2e_value = pairs_per_step * args.steps / (ms_e2e * 1e-3)
+    ms_e2e_calls = timed(step_e2e, args.steps) / args.steps
     ms_e2e_single = timed(step_e2e_single, max(2, args.steps // 2)) / max(2, args.steps // 2)
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(inp["mask_features"].numel() * 4 + inp["object_info"][0]["pan_results"].numel() *
               inp["object_info"][0]["pan_results"].element_size() + wl.num_objects * 4 +
               2 * wl.queries * 16 * 4 for inp in host_inputs)
-    d2h = ips * (20 * 4 + wl.num_objects * 4)
+    d2h = ips * 20 * 4          # the selected pair indices of every image
 
     # per-kernel device times: same step, eager launches (CUDA graphs off while profiling) with an event pair around
     # every C-ABI call on the launching stream
@@ -313,9 +350,13 @@ def run_ours(args):
                        "images_per_step_per_rank": ips, "parallelism": f"image-shard x{world}",
                        "l2": "inputs larger than L2 (4 x 67 MB feature maps + >100 MB activations per image)",
                        "launch": "one CUDA-graph replay per image (per-kernel times below come from an eager pass of the same step)"},
+            "ms_per_step_separate_calls": ms_separate,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
-                    "api": "head.forward_batch(list of host input dicts): pinned-host H2D of image i+1 overlaps image i",
+                    "api": "one head.forward_batch(stream of host input dicts) call over the K steps' images: pinned-host H2D "
+                           "of image i+1 overlaps image i, results read back asynchronously into pinned buffers",
+                    "ms_per_step_one_call_per_step": ms_e2e_calls,
+                    "value_one_call_per_step": pairs_per_step / (ms_e2e_calls * 1e-3),
                     "ms_per_step_single_calls": ms_e2e_single,
                     "value_single_calls": pairs_per_step / (ms_e2e_single * 1e-3)},
             "gpu_launches": launches,

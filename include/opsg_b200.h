@@ -89,11 +89,13 @@ int opsg_gemm_bf16_ln(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, 
                       float* stats_out, float eps, void* stream);
 
 /* Small-M variant for weight-streaming GEMMs (LLM decode: M = number of selected pairs <= 128, OPT q/k/v/out/fc1/
- * fc2/lm_head of one decode step; v4:305-312).  Same operands and epilogue as opsg_gemm_bf16 (bias along N only),
- * but the flattened (N-tile, K-block) space is cut into one equal contiguous range per SM ("stream-K"), so every SM
- * streams the same number of weight bytes from HBM whatever N is; fp32 partial tiles go through a caller-provided
- * workspace of opsg_gemm_streamk_workspace_bytes(N, K) bytes and a fix-up kernel applies bias / residual /
- * activation.  Deterministic (no atomics).  out_mode: OPSG_OUT_BF16 or OPSG_OUT_F32. */
+ * fc2 of one decode step; v4:305-312).  Same operands and epilogue as opsg_gemm_bf16 (bias along N only).  K is cut
+ * into slices of <= 12 K-blocks; a CTA keeps its slice of the activations resident in tensor memory (the MMA's A
+ * operand) and streams only weights, 64 rows x 64 columns per pipeline stage; the fp32 partial rows of the slices go
+ * through a caller-provided workspace of opsg_gemm_streamk_workspace_bytes(N, K) bytes and a second kernel sums them in
+ * a fixed order and applies bias / activation / residual (csrc/gemm_skinny.cu).  Deterministic (no atomics).
+ * Layouts that kernel does not take (N, ldd or ldr not a multiple of 4) and OPSG_SKINNY=0 use the older stream-K
+ * decomposition over 256-wide tiles (gemm.cu) behind the same entry.  out_mode: OPSG_OUT_BF16 or OPSG_OUT_F32. */
 size_t opsg_gemm_streamk_workspace_bytes(int N, int K);
 int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M, int N,
                            int K, const float* bias, const opsg_bf16* residual, int ldr, int act, int out_mode,

@@ -53,6 +53,7 @@ __device__ __forceinline__ float ex2f(float x) {
 // HD = head dim (multiple of 16), NK = padded key capacity (multiple of 16), 4 warps x 16 query rows per pass.
 template <int HD, int NK>
 __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p) {
+  pdl_wait_then_trigger();
   constexpr int QS = HD + 8;      // padded row strides (elements) -> conflict-free fragment loads
   constexpr int KS = HD + 8;
   constexpr int VS = HD + 8;
@@ -242,6 +243,7 @@ constexpr int kQfStageBytes = kQfStageElems * 2 + 64;                     // + k
 constexpr int kQfStages = 2;
 
 __global__ void __launch_bounds__(128) qformer_self_attn_kernel(const SmallAttnParams p, int num_problems) {
+  pdl_wait_then_trigger();
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -395,7 +397,7 @@ static int launch_small_attn(const SmallAttnParams& p, int nseq, cudaStream_t st
     if (rc) return rc;
     configured = true;
   }
-  small_attn_kernel<HD, NK><<<dim3(nseq, p.num_heads), 128, smem, st>>>(p);
+  launch_kernel(small_attn_kernel<HD, NK>, dim3(nseq, p.num_heads), 128, smem, st, p);
   OPSG_CHECK_LAUNCH("small_attn_kernel");
   return OPSG_OK;
 }
@@ -425,6 +427,7 @@ static int dispatch_hd(const SmallAttnParams& p, int nseq, int n_keys, int head_
 // ------------------------------------------------------------------------------------------------
 template <int HD>
 __global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams p) {
+  pdl_wait_then_trigger();
   constexpr int kWarps = 8;
   constexpr int kMaxCtx = 128;
   constexpr int LPK = (HD / 8 <= 8) ? 8 : 16;              // lanes per key (power of two >= HD / 8)
@@ -531,13 +534,14 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams 
 template <int HD>
 static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
   p.B = nseq * p.num_heads;
-  decode_attn_kernel<HD><<<(p.B + 7) / 8, 256, 0, st>>>(p);
+  launch_kernel(decode_attn_kernel<HD>, (p.B + 7) / 8, 256, 0, st, p);
   OPSG_CHECK_LAUNCH("decode_attn_kernel");
   return OPSG_OK;
 }
 
 __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model,
                                  __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int max_ctx) {
+  pdl_wait_then_trigger();
   const int vec = d_model / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(nseq) * q_len * vec) return;
@@ -581,7 +585,7 @@ extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_ma
     const int problems = B * num_heads;
     int grid = opsg_num_sms() * 4;                 // 4 resident CTAs per SM (55 KB of smem each)
     if (grid > problems) grid = problems;
-    qformer_self_attn_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, problems);
+    launch_kernel(qformer_self_attn_kernel, grid, 128, smem, reinterpret_cast<cudaStream_t>(stream), p, problems);
     OPSG_CHECK_LAUNCH("qformer_self_attn_kernel");
     return OPSG_OK;
   }
@@ -624,7 +628,7 @@ extern "C" int opsg_kv_append(const opsg_bf16* qkv, int ld_qkv, int nseq, int q_
   OPSG_CHECK_ARG(nseq > 0 && q_len > 0 && pos0 >= 0 && pos0 + q_len <= max_ctx && d_model % 8 == 0 && ld_qkv % 8 == 0,
                  "kv_append: bad shape");
   const long long total = static_cast<long long>(nseq) * q_len * (d_model / 8);
-  kv_append_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(kv_append_kernel, static_cast<int>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv, nseq, q_len, pos0, d_model,
       reinterpret_cast<__nv_bfloat16*>(k_cache), reinterpret_cast<__nv_bfloat16*>(v_cache), max_ctx);
   OPSG_CHECK_LAUNCH("kv_append_kernel");

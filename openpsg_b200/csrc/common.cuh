@@ -39,6 +39,17 @@ __device__ __forceinline__ bool elect_one_sync() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (see launch_kernel in host_util.h)
+// ------------------------------------------------------------------------------------------------
+// Blocks until the preceding kernel of the stream has completed and its writes are visible.  Must precede the first
+// global-memory access of every thread that makes one.  No-op when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the NEXT kernel of the stream be scheduled (it still blocks in its own pdl_wait until this grid completes).
+// Called right after pdl_wait: one kernel of look-ahead, no pile-up of waiting grids.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_then_trigger() { pdl_wait(); pdl_trigger(); }
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

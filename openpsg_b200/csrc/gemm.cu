@@ -21,6 +21,10 @@
 
 namespace opsg {
 
+size_t gemm_skinny_workspace_bytes(int N, int K);
+int launch_gemm_skinny(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M, int N, int K,
+                       const float* bias, const opsg_bf16* residual, int ldr, int act, int out_mode, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
 int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, opsg_bf16* D, int ldd, int M, int N, int K,
                      const float* bias, int bias_along_m, const opsg_bf16* residual, int ldr, int act, const GemmLnFold* ln,
                      cudaStream_t stream);
@@ -146,6 +150,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  pdl_wait_then_trigger();          // everything above overlaps the previous kernel (programmatic dependent launch)
   const int kb_total = (p.K + kBK - 1) / kBK;
   const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
 
@@ -414,7 +419,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   p.m_tiles = (p.M + kBM - 1) / kBM;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = total < opsg_num_sms() ? total : opsg_num_sms();
-  gemm_bf16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmD, p);
+  launch_kernel(gemm_bf16_kernel<BN, STAGES>, grid, kGemmThreads, S::kTotal, stream, tmA, tmB, tmD, p);
   OPSG_CHECK_LAUNCH("gemm_bf16_kernel");
   return OPSG_OK;
 }
@@ -433,6 +438,7 @@ struct StreamKReduceParams {
 };
 
 __global__ void __launch_bounds__(256) streamk_reduce_kernel(const StreamKReduceParams p) {
+  pdl_wait_then_trigger();
   constexpr int BN = 256;
   const int n_t = blockIdx.x;
   const int c4 = threadIdx.x & 63;                       // 4-column group inside the tile
@@ -509,7 +515,9 @@ extern "C" size_t opsg_gemm_streamk_workspace_bytes(int N, int K) {
   int sms = opsg_num_sms();
   if (sms <= 0) sms = kNumSMsB200;
   streamk_shape(N, K, sms, &n_tiles, &kb_total, &grid, &max_segs);
-  return static_cast<size_t>(grid) * max_segs * kBM * 256 * sizeof(float);
+  const size_t a = static_cast<size_t>(grid) * max_segs * kBM * 256 * sizeof(float);
+  const size_t b = gemm_skinny_workspace_bytes(N, K);
+  return a > b ? a : b;
 }
 
 extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M,
@@ -526,6 +534,14 @@ extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf
   OPSG_CHECK_ARG(out_mode == OPSG_OUT_BF16 || out_mode == OPSG_OUT_F32, "gemm_streamk: out_mode must be BF16 or F32");
   OPSG_CHECK_ARG(act >= OPSG_ACT_NONE && act <= OPSG_ACT_RELU, "gemm_streamk: bad activation");
   OPSG_CHECK_ARG(!residual || ldr >= N, "gemm_streamk: ldr too small");
+  // default: K-sliced kernel with the activation slice resident in shared memory (gemm_skinny.cu); OPSG_SKINNY=0 or a
+  // layout it does not take (N or a leading dimension not a multiple of 4) falls through to stream-K below
+  static const bool skinny = [] { const char* e = getenv("OPSG_SKINNY"); return e ? atoi(e) != 0 : true; }();
+  if (skinny) {
+    rc = launch_gemm_skinny(A, lda, W, ldw, D, ldd, M, N, K, bias, residual, ldr, act, out_mode, workspace, workspace_bytes,
+                            reinterpret_cast<cudaStream_t>(stream));
+    if (rc != OPSG_E_UNSUPPORTED) return rc;
+  }
   int n_tiles, kb_total, grid, max_segs;
   streamk_shape(N, K, opsg_num_sms(), &n_tiles, &kb_total, &grid, &max_segs);
   OPSG_CHECK_ARG(workspace_bytes >= static_cast<size_t>(grid) * max_segs * kBM * 256 * sizeof(float),
@@ -549,14 +565,14 @@ extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf
     if (rc) return rc;
     configured = true;
   }
-  gemm_bf16_kernel<256, 4><<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, tmA, p);
+  launch_kernel(gemm_bf16_kernel<256, 4>, grid, kGemmThreads, S::kTotal, st, tmA, tmB, tmA, p);
   OPSG_CHECK_LAUNCH("gemm_bf16_kernel(stream-K)");
   StreamKReduceParams r;
   r.ws = p.ws; r.D = D; r.bias = bias; r.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   r.M = M; r.N = N; r.ldd = ldd; r.ldr = ldr; r.act = act; r.out_f32 = out_mode == OPSG_OUT_F32;
   r.n_tiles = n_tiles; r.kb_total = kb_total; r.grid = grid; r.max_segs = max_segs;
   const int gy = (M + 3) / 4 < 8 ? (M + 3) / 4 : 8;
-  streamk_reduce_kernel<<<dim3(n_tiles, gy), 256, 0, st>>>(r);
+  launch_kernel(streamk_reduce_kernel, dim3(n_tiles, gy), 256, 0, st, r);
   OPSG_CHECK_LAUNCH("streamk_reduce_kernel");
   return OPSG_OK;
 }

@@ -25,8 +25,6 @@ namespace g2 {
 constexpr int kBM = 128;           // rows per CTA (256 per pair)
 constexpr int kBN = 256;           // tile N (each CTA stages 128 of the 256 W^T rows)
 constexpr int kBK = 64;
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
 constexpr int kABytes = kBM * kBK * 2;          // 16384
 constexpr int kBBytes = (kBN / 2) * kBK * 2;    // 16384
 constexpr int kStageBytes = kABytes + kBBytes;  // 32768 per CTA
@@ -138,6 +136,16 @@ __device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t* bar, uint32_
     if (clock64() - t0 > OPSG_WAIT_LIMIT_CYCLES) __trap();
   }
 }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
@@ -147,11 +155,14 @@ __device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32
   return d;
 }
 
-template <int STAGES, int NB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int STAGES, int NB, int EPIW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EPIW * 32, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const Params p) {
   static_assert(smem_total<STAGES, NB>() <= 232448, "shared memory budget exceeded");
+  static_assert(EPIW == 8 || EPIW == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
+  constexpr int kEpiThreads = EPIW * 32;
+  constexpr int CW = 64 / (EPIW / 4);          // accumulator columns per warp per slab (32 or 16)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -208,6 +219,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  pdl_wait_then_trigger();          // everything above overlaps the previous kernel (programmatic dependent launch)
   const int num_pairs = gridDim.x >> 1;
   const int pair = blockIdx.x >> 1;
   const int total_tiles = p.m2_tiles * p.n_tiles;
@@ -350,7 +362,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int ew = warp - 4;
     const int q = ew & 3;
-    const int half = ew >> 2;
+    const int part = ew >> 2;                                  // which CW-column part of a 64-column slab
     const int row_in_tile = q * 32 + lane;
     const int et = threadIdx.x - 4 * 32;                       // 0..255 inside the epilogue
     const bool tracer = (et == 0);
@@ -364,7 +376,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // them from shared memory (a per-slab __ldg is an L2 round trip here: the L1 is a few KB).
     auto load_vec = [&](int n_t) {
       const int col = n_t * kBN + et;
-      const bool ok = col < p.N;
+      const bool ok = col < p.N && et < kBN;
       float4 v;
       v.x = (p.bias && !p.bias_along_m && ok) ? __ldg(p.bias + col) : 0.f;
       v.y = (p.a_stats && ok) ? __ldg(p.a_colsum + col) : 0.f;
@@ -373,6 +385,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       return v;
     };
     auto park_vec = [&](int parity, const float4& v) {
+      if (et >= kBN) return;
       float* dst = sVec + parity * 4 * kBN + et;
       dst[0] = v.x; dst[kBN] = v.y; dst[2 * kBN] = v.z; dst[3 * kBN] = v.w;
     };
@@ -413,18 +426,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 #pragma unroll 1
       for (int slab = 0; slab < NSLAB; ++slab, ++g) {
-        const int lc = slab * 64 + half * 32;                    // column inside the tile
+        const int lc = slab * 64 + part * CW;                    // column inside the tile
         const int col0 = n_t * kBN + lc;
         const int b = g % NB;
         slab_for_trace = slab;
         G2_TRACE(0);
-        float f[32];
+        float f[CW];
         {
-          uint32_t v[32];
-          tmem_ld32(taddr + lc, v);
+          uint32_t v[CW];
+          tmem_ld_cols(taddr + lc, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
         }
         G2_TRACE(1);
         if (slab == NSLAB - 1) {            // accumulator fully read -> hand the TMEM stage back to the leader's MMA warp
@@ -433,12 +446,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
         }
         const bool col_ok = col0 < p.N;
-        const bool full = col0 + 32 <= p.N;
+        const bool full = col0 + CW <= p.N;
         uint8_t* rowp = staging + b * kSlabBytes + row_in_tile * 128;
         if (col_ok) {
           if (p.a_stats) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < CW / 4; ++j) {
               const float4 c4 = *reinterpret_cast<const float4*>(vec + 1 * kBN + lc + j * 4);
               f[j * 4 + 0] = a_rstd * fmaf(-a_mean, c4.x, f[j * 4 + 0]); f[j * 4 + 1] = a_rstd * fmaf(-a_mean, c4.y, f[j * 4 + 1]);
               f[j * 4 + 2] = a_rstd * fmaf(-a_mean, c4.z, f[j * 4 + 2]); f[j * 4 + 3] = a_rstd * fmaf(-a_mean, c4.w, f[j * 4 + 3]);
@@ -447,10 +460,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.bias && !p.bias_mma) {
             if (p.bias_along_m) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += bias_m;
+              for (int j = 0; j < CW; ++j) f[j] += bias_m;
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < CW / 4; ++j) {
                 const float4 b4 = *reinterpret_cast<const float4*>(vec + lc + j * 4);
                 f[j * 4 + 0] += b4.x; f[j * 4 + 1] += b4.y; f[j * 4 + 2] += b4.z; f[j * 4 + 3] += b4.w;
               }
@@ -459,7 +472,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (resid && !res_tma && row_ok) {
             const __nv_bfloat16* r = resid + static_cast<size_t>(row) * p.ldr + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CW; ++j)
               if (col0 + j < p.N) f[j] += __bfloat162float(r[j]);
           }
         }
@@ -468,8 +481,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         G2_TRACE(3);
         if (res_tma && col_ok) {
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {                       // this thread's 64 bytes of its own row, in place
-            const uint4 u = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + gq) ^ (row_in_tile & 7)) * 16));
+          for (int gq = 0; gq < CW / 8; ++gq) {                       // this thread's 64 bytes of its own row, in place
+            const uint4 u = *reinterpret_cast<const uint4*>(rowp + (((part * (CW / 8) + gq) ^ (row_in_tile & 7)) * 16));
             float rv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
                            bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
             if (p.r_stats) {         // the residual tensor is stored un-normalised: apply its pending LayerNorm here
@@ -489,21 +502,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (col_ok) {
           if (p.act == OPSG_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+            for (int j = 0; j < CW; ++j) f[j] = gelu_erf_fast(f[j]);
           } else if (p.act == OPSG_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
           }
         }
         if (p.stats_out && col_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < CW; ++j)
             if (full || col0 + j < p.N) { s_sum += f[j]; s_sq = fmaf(f[j], f[j], s_sq); }
         }
         G2_TRACE(4);
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const int chunk = (half * 4 + gq) ^ (row_in_tile & 7);
+        for (int gq = 0; gq < CW / 8; ++gq) {
+          const int chunk = (part * (CW / 8) + gq) ^ (row_in_tile & 7);
           uint4 u;
           u.x = pack_bf16x2(f[gq * 8 + 0], f[gq * 8 + 1]);
           u.y = pack_bf16x2(f[gq * 8 + 2], f[gq * 8 + 3]);
@@ -570,15 +583,20 @@ int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, o
   // operand stages x staging slabs: a residual wants a deeper slab ring (its loads are in flight for a slab period or two)
   static const int forced = [] { const char* e = getenv("OPSG_GEMM2_VARIANT"); return e ? atoi(e) : 0; }();
   const bool deep_ring = forced == 2;      // measured: <5,3> is at least as fast as <4,4> with a residual too
-  auto kernel = deep_ring ? gemm2_bf16_kernel<4, 4> : gemm2_bf16_kernel<5, 3>;
+  static const int epiw = [] { const char* e = getenv("OPSG_GEMM2_EPIW"); return e ? atoi(e) : 8; }();
+  auto kernel = deep_ring ? gemm2_bf16_kernel<4, 4, 8> : (epiw == 16 ? gemm2_bf16_kernel<5, 3, 16> : gemm2_bf16_kernel<5, 3, 8>);
+  const int threads = 128 + ((!deep_ring && epiw == 16) ? 16 : 8) * 32;
   const int smem_bytes = deep_ring ? smem_total<4, 4>() : smem_total<5, 3>();
   static bool configured = false;
   if (!configured) {
-    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<4, 4>()),
-                    "cudaFuncSetAttribute(gemm 2cta <4,4>)");
+    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<4, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<4, 4>()),
+                    "cudaFuncSetAttribute(gemm 2cta <4,4,8>)");
     if (rc) return rc;
-    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<5, 3>()),
-                    "cudaFuncSetAttribute(gemm 2cta <5,3>)");
+    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<5, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<5, 3>()),
+                    "cudaFuncSetAttribute(gemm 2cta <5,3,8>)");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<5, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<5, 3>()),
+                    "cudaFuncSetAttribute(gemm 2cta <5,3,16>)");
     if (rc) return rc;
     configured = true;
   }
@@ -597,7 +615,7 @@ int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, o
   }
   int pairs = sms / 2;
   if (m2_tiles * n_tiles < pairs) pairs = m2_tiles * n_tiles;
-  kernel<<<2 * pairs, kThreads, smem_bytes, stream>>>(tmA, tmB, tmD, tmR, p);
+  launch_kernel(kernel, 2 * pairs, threads, smem_bytes, stream, tmA, tmB, tmD, tmR, p);
   OPSG_CHECK_LAUNCH("gemm2_bf16_kernel");
   return OPSG_OK;
 }

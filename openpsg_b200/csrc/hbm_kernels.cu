@@ -22,6 +22,7 @@ __device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
 __global__ void pair_mask_bits_kernel(const int32_t* __restrict__ pan, int pan_h, int pan_w, int img_h, int img_w,
                                       int pad_h, int pad_w, int tok_h, int tok_w, const int32_t* __restrict__ obj_ids,
                                       int num_objects, uint32_t* __restrict__ bits, int words) {
+  pdl_wait_then_trigger();
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= num_objects * words) return;
@@ -51,6 +52,7 @@ __global__ void pair_mask_bits_kernel(const int32_t* __restrict__ pan, int pan_h
 // ------------------------------------------------------------------------------------------------
 __global__ void patch_im2col_kernel(const float* __restrict__ feat, int C, int h, int w, int patch, int th, int tw,
                                     __nv_bfloat16* __restrict__ out) {
+  pdl_wait_then_trigger();
   const int x8_per_row = (tw * patch) / 8;
   const long long total = static_cast<long long>(C) * (th * patch) * x8_per_row;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -81,6 +83,7 @@ __global__ void patch_im2col_kernel(const float* __restrict__ feat, int C, int h
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out, int ld_out,
                                      int rows, int cols) {
+  pdl_wait_then_trigger();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx % cols);
@@ -88,6 +91,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, int ld_in, __
 }
 
 __global__ void init_rows_f32_kernel(float* __restrict__ out, int ld_out, const float* __restrict__ row, int rows, int cols) {
+  pdl_wait_then_trigger();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx % cols);
@@ -144,6 +148,7 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps,
                                                              __nv_bfloat16* __restrict__ y, int rows, int cols) {
+  pdl_wait_then_trigger();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -168,6 +173,7 @@ __global__ void __launch_bounds__(256) qformer_embed_ln_kernel(const float* __re
                                                                const float* __restrict__ pos_emb,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                float eps, int d, __nv_bfloat16* __restrict__ out) {
+  pdl_wait_then_trigger();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int n_query_rows = B * nq;
@@ -209,6 +215,7 @@ __global__ void __launch_bounds__(256) exist_logits_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ w, const float* __restrict__ b,
                                                            float logit_threshold, float* __restrict__ logits,
                                                            float* __restrict__ probs, uint8_t* __restrict__ mask) {
+  pdl_wait_then_trigger();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(256) exist_logits_kernel(const __nv_bfloat16* 
 // rank(i) = #{j : z_j > z_i or (z_j == z_i and j < i)};  rank < k  ->  topk[rank] = i.
 __global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict__ logits, int B, int k,
                                                         int32_t* __restrict__ topk) {
+  pdl_wait_then_trigger();
   __shared__ float tile[2048];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const float zi = i < B ? logits[i] : 0.f;
@@ -260,6 +268,7 @@ __global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) mask_pool_accum_kernel(const float* __restrict__ feat, int C, int hw,
                                                               const int32_t* __restrict__ label, int N,
                                                               float* __restrict__ obj_sum, float* __restrict__ count) {
+  pdl_wait_then_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int c_per_block_y = (C + gridDim.y - 1) / gridDim.y;
@@ -287,12 +296,14 @@ __global__ void __launch_bounds__(256) mask_pool_accum_kernel(const float* __res
 }
 
 __global__ void mask_pool_normalize_kernel(float* __restrict__ obj, const float* __restrict__ count, int N, int C) {
+  pdl_wait_then_trigger();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(N) * C) return;
   obj[idx] = obj[idx] / (count[idx / C] + 1e-8f);
 }
 
 __global__ void pair_concat_kernel(const float* __restrict__ obj, int N, int C, float* __restrict__ pair_out) {
+  pdl_wait_then_trigger();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(N) * N * 2 * C) return;
   const int col = static_cast<int>(idx % (2 * C));
@@ -306,6 +317,7 @@ __global__ void pair_concat_kernel(const float* __restrict__ obj, int N, int C, 
 // ------------------------------------------------------------------------------------------------
 __global__ void gather_rows_bf16_kernel(const uint4* __restrict__ src, int row_vec, const int32_t* __restrict__ idx, int n_rows,
                                         uint4* __restrict__ out) {
+  pdl_wait_then_trigger();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(n_rows) * row_vec) return;
   const int r = static_cast<int>(t / row_vec), c = static_cast<int>(t % row_vec);
@@ -315,6 +327,7 @@ __global__ void gather_rows_bf16_kernel(const uint4* __restrict__ src, int row_v
 __global__ void embed_gather_kernel(const __nv_bfloat16* __restrict__ table, int d, const int32_t* __restrict__ ids,
                                     const __nv_bfloat16* __restrict__ pos_table, const int32_t* __restrict__ pos, int n_rows,
                                     __nv_bfloat16* __restrict__ out, int ld_out) {
+  pdl_wait_then_trigger();
   const int vec = d / 8;
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(n_rows) * vec) return;
@@ -335,6 +348,7 @@ __global__ void llm_build_prefix_kernel(const __nv_bfloat16* __restrict__ proj, 
                                         const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ ids, int T,
                                         const __nv_bfloat16* __restrict__ pos_table, const int32_t* __restrict__ pos,
                                         int nseq, int d, __nv_bfloat16* __restrict__ out) {
+  pdl_wait_then_trigger();
   const int vec = d / 8;
   const int Tp = n_prefix + T;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -357,6 +371,7 @@ __global__ void llm_build_prefix_kernel(const __nv_bfloat16* __restrict__ proj, 
 
 __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
                                                           int32_t* __restrict__ out) {
+  pdl_wait_then_trigger();
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   const int row = blockIdx.x;
@@ -398,7 +413,7 @@ extern "C" int opsg_pair_mask_bits(const int32_t* pan, int pan_h, int pan_w, int
   OPSG_CHECK_ARG(pad_h >= img_h && pad_w >= img_w, "pair_mask_bits: pad_shape smaller than img_shape");
   OPSG_CHECK_ARG(words * 32 >= tok_h * tok_w, "pair_mask_bits: words too small for %d tokens", tok_h * tok_w);
   const long long threads = static_cast<long long>(num_objects) * words * 32;
-  pair_mask_bits_kernel<<<ceil_div(threads, 256), 256, 0, ST(stream)>>>(pan, pan_h, pan_w, img_h, img_w, pad_h, pad_w,
+  launch_kernel(pair_mask_bits_kernel, ceil_div(threads, 256), 256, 0, ST(stream), pan, pan_h, pan_w, img_h, img_w, pad_h, pad_w,
                                                                         tok_h, tok_w, obj_ids, num_objects, bits_out, words);
   OPSG_CHECK_LAUNCH("pair_mask_bits_kernel");
   return OPSG_OK;
@@ -411,7 +426,7 @@ extern "C" int opsg_patch_im2col(const float* feat, int channels, int h, int w, 
   OPSG_CHECK_ARG(patch > 0 && patch % 8 == 0 && h >= patch && w >= patch, "patch_im2col: patch must be a multiple of 8");
   const int th = h / patch, tw = w / patch;
   const long long total = static_cast<long long>(channels) * (th * patch) * ((tw * patch) / 8);
-  patch_im2col_kernel<<<ceil_div(total, 256), 256, 0, ST(stream)>>>(feat, channels, h, w, patch, th, tw,
+  launch_kernel(patch_im2col_kernel, ceil_div(total, 256), 256, 0, ST(stream), feat, channels, h, w, patch, th, tw,
                                                                     reinterpret_cast<__nv_bfloat16*>(out));
   OPSG_CHECK_LAUNCH("patch_im2col_kernel");
   return OPSG_OK;
@@ -421,7 +436,7 @@ extern "C" int opsg_cast_f32_bf16(const float* in, int ld_in, opsg_bf16* out, in
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(in && out && rows > 0 && cols > 0, "cast_f32_bf16: bad argument");
-  cast_f32_bf16_kernel<<<ceil_div(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(cast_f32_bf16_kernel, ceil_div(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream), 
       in, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
   OPSG_CHECK_LAUNCH("cast_f32_bf16_kernel");
   return OPSG_OK;
@@ -431,7 +446,7 @@ extern "C" int opsg_init_rows_f32(float* out, int ld_out, const float* row, int 
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(out && rows > 0 && cols > 0, "init_rows_f32: bad argument");
-  init_rows_f32_kernel<<<ceil_div(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream)>>>(out, ld_out, row, rows, cols);
+  launch_kernel(init_rows_f32_kernel, ceil_div(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream), out, ld_out, row, rows, cols);
   OPSG_CHECK_LAUNCH("init_rows_f32_kernel");
   return OPSG_OK;
 }
@@ -445,11 +460,76 @@ extern "C" int opsg_qformer_embed_ln(const float* query, int n_query, const int3
   OPSG_CHECK_ARG(T == 0 || input_ids, "qformer_embed_ln: null input_ids");
   OPSG_CHECK_ARG(d % 8 == 0 && d <= 1024 && B > 0 && n_query > 0 && T >= 0, "qformer_embed_ln: bad shape (d=%d)", d);
   const long long rows = static_cast<long long>(B) * (n_query + T);
-  qformer_embed_ln_kernel<<<ceil_div(rows * 32, 256), 256, 0, ST(stream)>>>(query, n_query, input_ids, B, T, word_emb, vocab,
+  launch_kernel(qformer_embed_ln_kernel, ceil_div(rows * 32, 256), 256, 0, ST(stream), query, n_query, input_ids, B, T, word_emb, vocab,
                                                                            pos_emb, gamma, beta, eps, d,
                                                                            reinterpret_cast<__nv_bfloat16*>(h_out));
   OPSG_CHECK_LAUNCH("qformer_embed_ln_kernel");
   return OPSG_OK;
+}
+
+// Few rows (LLM decode: 100 rows of 2560): one CTA per row instead of one warp per row -- 256 threads issue the row's
+// loads (x, gamma, beta) at once, so the kernel is one memory round trip deep instead of ten chunks per lane.
+__global__ void __launch_bounds__(256) layernorm_row_cta_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps,
+                                                                __nv_bfloat16* __restrict__ y, int cols) {
+  pdl_wait_then_trigger();
+  __shared__ float red[2][8];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const __nv_bfloat16* xr = x + static_cast<size_t>(blockIdx.x) * cols;
+  constexpr int CH = 2;                                   // 2 x 256 x 8 = 4096 columns max
+  float v[CH][8], g[CH][8], b[CH][8];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c0 = (i * 256 + t) * 8;
+    if (c0 < cols) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + c0));
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+      v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
+      v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
+      g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+      b[i][0] = b0.x; b[i][1] = b0.y; b[i][2] = b0.z; b[i][3] = b0.w; b[i][4] = b1.x; b[i][5] = b1.y; b[i][6] = b1.z; b[i][7] = b1.w;
+    }
+  }
+  auto block_sum = [&](float s, int slot) {
+    s = warp_sum(s);
+    if (lane == 0) red[slot][warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[slot][w];
+    return tot;
+  };
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+    if ((i * 256 + t) * 8 < cols) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  const float mean = block_sum(s, 0) / cols;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+    if ((i * 256 + t) * 8 < cols) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+    }
+  const float rstd = rsqrtf(block_sum(ss, 1) / cols + eps);
+  __nv_bfloat16* yr = y + static_cast<size_t>(blockIdx.x) * cols;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c0 = (i * 256 + t) * 8;
+    if (c0 < cols) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[i][j] + b[i][j];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + c0) = u;
+    }
+  }
 }
 
 extern "C" int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const float* beta, float eps, opsg_bf16* y,
@@ -461,8 +541,10 @@ extern "C" int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const
   const int grid = ceil_div(static_cast<long long>(rows) * 32, 256);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
-  if (cols <= 1024) layernorm_bf16_kernel<4><<<grid, 256, 0, ST(stream)>>>(xp, gamma, beta, eps, yp, rows, cols);
-  else layernorm_bf16_kernel<kMaxChunks><<<grid, 256, 0, ST(stream)>>>(xp, gamma, beta, eps, yp, rows, cols);
+  if (rows <= 512 && cols >= 1024)
+    launch_kernel(layernorm_row_cta_kernel, rows, 256, 0, ST(stream), xp, gamma, beta, eps, yp, cols);
+  else if (cols <= 1024) launch_kernel(layernorm_bf16_kernel<4>, grid, 256, 0, ST(stream), xp, gamma, beta, eps, yp, rows, cols);
+  else launch_kernel(layernorm_bf16_kernel<kMaxChunks>, grid, 256, 0, ST(stream), xp, gamma, beta, eps, yp, rows, cols);
   OPSG_CHECK_LAUNCH("layernorm_bf16_kernel");
   return OPSG_OK;
 }
@@ -477,11 +559,11 @@ extern "C" int opsg_exist_filter_topk(const opsg_bf16* x, int ld_x, int B, int d
   OPSG_CHECK_ARG(k >= 0 && k <= B && (k == 0 || topk_out), "exist_filter_topk: bad k");
   OPSG_CHECK_ARG(threshold > 0.f && threshold < 1.f, "exist_filter_topk: threshold must be in (0,1)");
   const float logit_thr = logf(threshold / (1.f - threshold));
-  exist_logits_kernel<<<ceil_div(static_cast<long long>(B) * 32, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(exist_logits_kernel, ceil_div(static_cast<long long>(B) * 32, 256), 256, 0, ST(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), ld_x, B, d, w, b, logit_thr, logits_out, probs_out, mask_out);
   OPSG_CHECK_LAUNCH("exist_logits_kernel");
   if (k > 0) {
-    topk_rank_kernel<<<ceil_div(B, 256), 256, 0, ST(stream)>>>(logits_out, B, k, topk_out);
+    launch_kernel(topk_rank_kernel, ceil_div(B, 256), 256, 0, ST(stream), logits_out, B, k, topk_out);
     OPSG_CHECK_LAUNCH("topk_rank_kernel");
   }
   return OPSG_OK;
@@ -502,14 +584,14 @@ extern "C" int opsg_mask_pool_pairs(const float* feat, int channels, int h, int 
   const int hw = h * w;
   const int warps = ceil_div(hw, 32);
   dim3 grid(ceil_div(static_cast<long long>(warps) * 32, 256), channels >= 64 ? 8 : 1);
-  mask_pool_accum_kernel<<<grid, 256, 0, ST(stream)>>>(feat, channels, hw, label, num_objects, obj_out, count_scratch);
+  launch_kernel(mask_pool_accum_kernel, grid, 256, 0, ST(stream), feat, channels, hw, label, num_objects, obj_out, count_scratch);
   OPSG_CHECK_LAUNCH("mask_pool_accum_kernel");
-  mask_pool_normalize_kernel<<<ceil_div(static_cast<long long>(num_objects) * channels, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(mask_pool_normalize_kernel, ceil_div(static_cast<long long>(num_objects) * channels, 256), 256, 0, ST(stream), 
       obj_out, count_scratch, num_objects, channels);
   OPSG_CHECK_LAUNCH("mask_pool_normalize_kernel");
   if (pair_out) {
     const long long total = static_cast<long long>(num_objects) * num_objects * 2 * channels;
-    pair_concat_kernel<<<ceil_div(total, 256), 256, 0, ST(stream)>>>(obj_out, num_objects, channels, pair_out);
+    launch_kernel(pair_concat_kernel, ceil_div(total, 256), 256, 0, ST(stream), obj_out, num_objects, channels, pair_out);
     OPSG_CHECK_LAUNCH("pair_concat_kernel");
   }
   return OPSG_OK;
@@ -521,7 +603,7 @@ extern "C" int opsg_gather_rows_bf16(const opsg_bf16* src, int row_elems, const 
   if (rc) return rc;
   OPSG_CHECK_ARG(src && idx && out && n_rows > 0 && row_elems > 0 && row_elems % 8 == 0, "gather_rows: bad argument");
   const int row_vec = row_elems / 8;
-  gather_rows_bf16_kernel<<<ceil_div(static_cast<long long>(n_rows) * row_vec, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(gather_rows_bf16_kernel, ceil_div(static_cast<long long>(n_rows) * row_vec, 256), 256, 0, ST(stream), 
       reinterpret_cast<const uint4*>(src), row_vec, idx, n_rows, reinterpret_cast<uint4*>(out));
   OPSG_CHECK_LAUNCH("gather_rows_bf16_kernel");
   return OPSG_OK;
@@ -533,7 +615,7 @@ extern "C" int opsg_embed_gather(const opsg_bf16* table, int d, const int32_t* i
   if (rc) return rc;
   OPSG_CHECK_ARG(table && ids && out && n_rows > 0 && d % 8 == 0 && ld_out % 8 == 0, "embed_gather: bad argument");
   OPSG_CHECK_ARG(!pos_table || pos, "embed_gather: pos_table without pos");
-  embed_gather_kernel<<<ceil_div(static_cast<long long>(n_rows) * (d / 8), 256), 256, 0, ST(stream)>>>(
+  launch_kernel(embed_gather_kernel, ceil_div(static_cast<long long>(n_rows) * (d / 8), 256), 256, 0, ST(stream), 
       reinterpret_cast<const __nv_bfloat16*>(table), d, ids, reinterpret_cast<const __nv_bfloat16*>(pos_table), pos, n_rows,
       reinterpret_cast<__nv_bfloat16*>(out), ld_out);
   OPSG_CHECK_LAUNCH("embed_gather_kernel");
@@ -551,7 +633,7 @@ extern "C" int opsg_llm_build_prefix(const opsg_bf16* proj, int proj_rows_per_se
   OPSG_CHECK_ARG(proj_row0 >= 0 && proj_row0 + n_prefix <= proj_rows_per_seq, "llm_build_prefix: prefix rows out of range");
   OPSG_CHECK_ARG(!pos_table || pos, "llm_build_prefix: pos_table without pos");
   const long long total = static_cast<long long>(nseq) * (n_prefix + T) * (d / 8);
-  llm_build_prefix_kernel<<<ceil_div(total, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(llm_build_prefix_kernel, ceil_div(total, 256), 256, 0, ST(stream), 
       reinterpret_cast<const __nv_bfloat16*>(proj), proj_rows_per_seq, proj_row0, n_prefix,
       reinterpret_cast<const __nv_bfloat16*>(table), ids, T, reinterpret_cast<const __nv_bfloat16*>(pos_table), pos, nseq, d,
       reinterpret_cast<__nv_bfloat16*>(out));
@@ -563,7 +645,7 @@ extern "C" int opsg_argmax_rows(const float* logits, int ld, int rows, int cols,
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(logits && out && rows > 0 && cols > 0 && ld >= cols, "argmax_rows: bad argument");
-  argmax_rows_kernel<<<rows, 256, 0, ST(stream)>>>(logits, ld, rows, cols, out);
+  launch_kernel(argmax_rows_kernel, rows, 256, 0, ST(stream), logits, ld, rows, cols, out);
   OPSG_CHECK_LAUNCH("argmax_rows_kernel");
   return OPSG_OK;
 }

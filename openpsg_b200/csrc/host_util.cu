@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace opsg {
@@ -15,6 +16,11 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("OPSG_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
 }
 
 int check_cuda(cudaError_t e, const char* what) {

@@ -38,4 +38,28 @@ struct GemmLnFold {
     if (_rc) return _rc;                                            \
   } while (0)
 
+// Every kernel goes out through here.  With programmatic dependent launch (default; OPSG_PDL=0 turns it off) kernel
+// N+1 may be scheduled as soon as every CTA of kernel N has executed griddepcontrol.launch_dependents, and blocks in
+// griddepcontrol.wait until kernel N has completed and flushed: its launch latency, CTA rasterisation and prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap kernel N instead of following it.  Every kernel
+// therefore calls pdl_wait() (common.cuh) before its first global-memory access.  Captured into CUDA graphs the
+// attribute becomes a programmatic dependency edge.
+bool pdl_enabled();
+inline dim3 to_dim3(dim3 d) { return d; }
+inline dim3 to_dim3(long long v) { return dim3(static_cast<unsigned>(v)); }
+template <typename... KArgs, typename G, typename B, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), G grid, B block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = to_dim3(grid);
+  cfg.blockDim = to_dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // the error is picked up by OPSG_CHECK_LAUNCH
+}
+
 }  // namespace opsg

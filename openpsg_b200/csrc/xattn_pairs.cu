@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256)
 xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int32_t* __restrict__ pair_index,
                         int num_objects, int num_pairs, int n_query, int L, int rows, uint8_t* __restrict__ tiles,
                         uint8_t* __restrict__ row_flags, uint8_t* __restrict__ chunk_vis) {
+  pdl_wait_then_trigger();
   const int mt = blockIdx.x;
   const int t = threadIdx.x;
   const int first_pair = (mt * 128) / n_query;
@@ -289,6 +290,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait_then_trigger();          // everything above overlaps the previous kernel (programmatic dependent launch)
 
   // contiguous, head-major unit range of this CTA
   const int per = (p.total_units + gridDim.x - 1) / gridDim.x;
@@ -639,7 +641,7 @@ extern "C" int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int3
   const int rows = B * n_query;
   const int m_tiles = (rows + 127) / 128;
   uint8_t* tiles = reinterpret_cast<uint8_t*>(tiles_out);
-  xattn_bias_tiles_kernel<<<m_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(xattn_bias_tiles_kernel, m_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       bits, words, pair_index, num_objects, B, n_query, L, rows, tiles, tiles + static_cast<size_t>(m_tiles) * kXaTileBytes,
       tiles + static_cast<size_t>(m_tiles) * (kXaTileBytes + 128));
   OPSG_CHECK_LAUNCH("xattn_bias_tiles_kernel");
@@ -703,7 +705,7 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   p.trace = g_xattn_trace;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   const int grid = p.total_units < opsg_num_sms() ? p.total_units : opsg_num_sms();
-  kernel<<<grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmVt, tmO, p);
+  launch_kernel(kernel, grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream), tmQ, tmK, tmVt, tmO, p);
   OPSG_CHECK_LAUNCH("xattn_pairs_kernel");
   return OPSG_OK;
 }

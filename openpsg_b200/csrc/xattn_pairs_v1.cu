@@ -57,6 +57,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(kXaThreads, 1)
 xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmVt, const XattnParams p) {
+  pdl_wait_then_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + XattnSmem::kOffK;
@@ -322,7 +323,7 @@ extern "C" int opsg_xattn_pairs_v1(const opsg_bf16* q, const opsg_bf16* k, int l
   p.rows = rows; p.m_tiles = (rows + 127) / 128; p.total_units = p.m_tiles * num_heads;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   const int grid = p.total_units < opsg_num_sms() ? p.total_units : opsg_num_sms();
-  xattn_pairs_kernel<<<grid, kXaThreads, XattnSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmVt, p);
+  launch_kernel(xattn_pairs_kernel, grid, kXaThreads, XattnSmem::kTotal, reinterpret_cast<cudaStream_t>(stream), tmQ, tmK, tmVt, p);
   OPSG_CHECK_LAUNCH("xattn_pairs_kernel");
   return OPSG_OK;
 }

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kXaThreads, 1)
 xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmO,
                    const XattnParams p) {
+  pdl_wait_then_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + XaSmem::kOffK;
@@ -381,7 +382,7 @@ extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int l
   // each CTA's contiguous unit range must span at most two heads (two resident K/V sets)
   const int per = (p.total_units + grid - 1) / grid;
   if (per > p.m_tiles) return set_error(OPSG_E_UNSUPPORTED, "xattn_pairs: unit range %d spans more than two heads", per);
-  xattn_pairs_kernel<<<grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmVt, tmO, p);
+  launch_kernel(xattn_pairs_kernel, grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream), tmQ, tmK, tmVt, tmO, p);
   OPSG_CHECK_LAUNCH("xattn_pairs_kernel");
   return OPSG_OK;
 }

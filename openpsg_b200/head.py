@@ -241,9 +241,14 @@ class RelationTransformerHeadV4(BaseModule):
         copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=dev)
         self._copy_stream = copy_stream
 
+        copy_stream.wait_stream(cur)           # the caller's inputs are ready on the current stream at call time
+
         def prefetch(inp):
-            prep = self._prepare_host(inp)
-            copy_stream.wait_stream(cur)
+            # object ids that live on the device are read back on the copy stream: the host waits for that stream only
+            # (the previous image's copies), never for the kernels of the image in flight
+            with torch.cuda.stream(copy_stream):
+                prep = self._prepare_host(inp)
+            copy_stream.wait_stream(cur)       # bounds the run-ahead of the staging copies to one image
             with torch.cuda.stream(copy_stream):
                 self._to_device(prep, dev)
                 ev = torch.cuda.Event()

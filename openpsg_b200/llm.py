@@ -93,17 +93,18 @@ class OPTDecodeEngine:
         if w_proj.shape[0] != weights.d:
             raise ValueError(f"language_projection out_features {w_proj.shape[0]} != LLM hidden size {weights.d}")
         self.use_cuda_graphs = use_cuda_graphs
-        self.streamk = os.environ.get("OPSG_LLM_STREAMK", "0") == "1"
+        # decode steps (rows <= 128) take the K-sliced small-M GEMM (csrc/gemm_skinny.cu); OPSG_LLM_SMALL_M=0 keeps the tiled one
+        self.small_m = os.environ.get("OPSG_LLM_SMALL_M", "1") == "1"
         self._graphs = {}          # (hidden shape, k, T, max_new_tokens) -> captured generate()
 
     # one decoder layer over `rows` = nseq * q_len token rows; h is updated in place
     def _layer(self, lw, h, k_cache, v_cache, key_mask, nseq, q_len, pos0):
         w = self.w
         d = w.d
-        # OPSG_LLM_STREAMK=1 routes decode steps (rows <= 128) through the stream-K GEMM.  Measured on B200 at k = 100
-        # (profiles/r1_llm_decode.md) it is slower than the tiled kernel: at ~10 K-blocks per CTA both are bound by
-        # per-launch latency (prologue, first TMA round trip, tail), and stream-K adds a fix-up launch.
-        gemm = ops.gemm_small_m if (self.streamk and h.shape[0] <= 128) else ops.gemm
+        # Decode steps (rows <= 128) stream the weights through the K-sliced kernel with the activations resident in TMEM:
+        # 17 / 11 / 21 / 20 us for qkv / out / fc1 / fc2 at k = 100 inside a graph against 22 / 13 / 24 / 40 us for the tiled
+        # kernel (scripts/kbench.py streamk, profiles/r1_llm_decode.md).
+        gemm = ops.gemm_small_m if (self.small_m and h.shape[0] <= 128) else ops.gemm
         x = ops.layernorm(h, lw["ln1"][0], lw["ln1"][1], self.LN_EPS)
         qkv = gemm(x, lw["w_qkv"], lw["b_qkv"])                                        # [rows, 3d]
         ops.kv_append(qkv, nseq, q_len, pos0, d, k_cache, v_cache)
@@ -118,8 +119,8 @@ class OPTDecodeEngine:
     def _logits(self, h_last):
         w = self.w
         x = ops.layernorm(h_last, w.final_ln[0], w.final_ln[1], self.LN_EPS)
-        gemm = ops.gemm_small_m if (self.streamk and h_last.shape[0] <= 128) else ops.gemm
-        return gemm(x, w.lm_head, out_dtype=torch.float32)                             # fp32 [k, V]
+        # lm_head (N = 50272): the tiled kernel's 256-wide tiles stream it at 4.8 TB/s; K slicing would add 80 MB of partials
+        return ops.gemm(x, w.lm_head, out_dtype=torch.float32)                         # fp32 [k, V]
 
     @torch.no_grad()
     def generate(self, hidden: torch.Tensor, selected: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,

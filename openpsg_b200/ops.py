@@ -162,7 +162,8 @@ _streamk_ws_keep = []  # outgrown workspaces stay alive: captured CUDA graphs ma
 def gemm_small_m(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
                  residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
                  out_dtype=torch.bfloat16) -> torch.Tensor:
-    """Weight-streaming GEMM for M <= 128 rows (LLM decode): stream-K over (N-tile, K-block) + fix-up kernel."""
+    """Weight-streaming GEMM for M <= 128 rows (LLM decode): K-sliced, activations resident in TMEM, deterministic
+    fp32 partial reduction in a second kernel (csrc/gemm_skinny.cu)."""
     _cuda(a, torch.bfloat16, "a"); _cuda(w, torch.bfloat16, "w")
     M, K = a.shape
     N = w.shape[0]

@@ -62,17 +62,95 @@ def bench_gemm(iters, flush):
 
 
 def bench_streamk(iters, flush):
+    """Decode-shaped GEMMs (M = 100).  Event timing of single launches measures the host's enqueue latency for kernels this
+    short, so each case is a CUDA graph of `reps` calls cycling over `reps` different weight matrices (> L2 in total:
+    every call streams its weights from HBM, as consecutive decoder layers do), replayed and timed as a whole."""
     for name, M, N, K in (("opt_qkv_decode", 100, 7680, 2560), ("opt_out_decode", 100, 2560, 2560),
                           ("opt_fc1_decode", 100, 10240, 2560), ("opt_fc2_decode", 100, 2560, 10240),
                           ("opt_lm_head", 100, 50272, 2560)):
+        reps = max(4, min(32, int(600e6 // (2 * N * K))))
         a = torch.randn((M, K), device=DEV).to(torch.bfloat16)
-        w = (torch.randn((N, K), device=DEV) / K ** 0.5).to(torch.bfloat16)
+        ws = [(torch.randn((N, K), device=DEV) / K ** 0.5).to(torch.bfloat16) for _ in range(reps)]
         bias = torch.randn(N, device=DEV)
         out = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
-        for fn_name, fn in (("streamk", lambda: ops.gemm_small_m(a, w, bias, out=out)), ("tiled", lambda: ops.gemm(a, w, bias, out=out))):
-            med, best = timeit(fn, iters, flush)
-            print(json.dumps({"kernel": "gemm_" + fn_name, "case": name, "M": M, "N": N, "K": K, "ms_median": med,
-                              "weight_GBps_median": 2.0 * N * K / med / 1e6}), flush=True)
+        for fn_name, fn in (("skinny", lambda w: ops.gemm_small_m(a, w, bias, out=out)),
+                            ("tiled", lambda w: ops.gemm(a, w, bias, out=out))):
+            for w in ws[:2]:
+                fn(w)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for w in ws:
+                    fn(w)
+            graph.replay()
+            torch.cuda.synchronize()
+            ms = []
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1) / reps)
+            ms.sort()
+            med = ms[len(ms) // 2]
+            print(json.dumps({"kernel": "gemm_" + fn_name, "case": name, "M": M, "N": N, "K": K, "reps_in_graph": reps,
+                              "us_per_call_median": med * 1e3, "weight_GBps_median": 2.0 * N * K / med / 1e6}), flush=True)
+        del ws
+
+
+def bench_layers(iters, flush):
+    """Decode-step GEMM chain of OPT-2.7B layers (qkv -> out -> fc1 -> fc2 with the real data dependencies, M = 100),
+    16 layers of distinct weights (2.5 GB) in one CUDA graph: us per layer for the small-M kernel and the tiled one."""
+    import os
+    d, ffn, M, L = 2560, 10240, 100, int(os.environ.get('KB_L', '16'))
+    nodep = os.environ.get('KB_NODEP', '0') == '1'
+    layers = []
+    for _ in range(L):
+        layers.append(dict(
+            w_qkv=(torch.randn((3 * d, d), device=DEV) * 0.02).to(torch.bfloat16), b_qkv=torch.zeros(3 * d, device=DEV),
+            w_o=(torch.randn((d, d), device=DEV) * 0.02).to(torch.bfloat16), b_o=torch.zeros(d, device=DEV),
+            w_fc1=(torch.randn((ffn, d), device=DEV) * 0.02).to(torch.bfloat16), b_fc1=torch.zeros(ffn, device=DEV),
+            w_fc2=(torch.randn((d, ffn), device=DEV) * 0.02).to(torch.bfloat16), b_fc2=torch.zeros(d, device=DEV)))
+    h0 = torch.randn((M, d), device=DEV).to(torch.bfloat16)
+    for fn_name, gemm in (("skinny", ops.gemm_small_m), ("tiled", ops.gemm)):
+        def run():
+            h = h0.clone()
+            if nodep:
+                f0 = torch.zeros((M, ffn), device=DEV, dtype=torch.bfloat16)
+                o1 = torch.empty((M, 3 * d), device=DEV, dtype=torch.bfloat16)
+                o2 = torch.empty((M, d), device=DEV, dtype=torch.bfloat16)
+                o3 = torch.empty((M, ffn), device=DEV, dtype=torch.bfloat16)
+                for lw in layers:
+                    gemm(h0, lw["w_qkv"], lw["b_qkv"], out=o1)
+                    gemm(h0, lw["w_o"], lw["b_o"], out=o2)
+                    gemm(h0, lw["w_fc1"], lw["b_fc1"], act=2, out=o3)
+                    gemm(f0, lw["w_fc2"], lw["b_fc2"], out=o2)
+                return h
+            for lw in layers:
+                qkv = gemm(h, lw["w_qkv"], lw["b_qkv"])
+                gemm(qkv[:, :d], lw["w_o"], lw["b_o"], residual=h, out=h)
+                f = gemm(h, lw["w_fc1"], lw["b_fc1"], act=2)
+                gemm(f, lw["w_fc2"], lw["b_fc2"], residual=h, out=h)
+            return h
+        run()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run()
+        graph.replay()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1) / L)
+        ms.sort()
+        print(json.dumps({"kernel": "layer_gemms_" + fn_name, "layers": L, "us_per_layer_median": ms[len(ms) // 2] * 1e3,
+                          "weight_GBps": 2.0 * (3 * d * d + d * d + 2 * d * ffn) / ms[len(ms) // 2] / 1e6}), flush=True)
 
 
 def bench_xattn(iters, flush):
@@ -103,6 +181,8 @@ def main():
         bench_gemm(args.iters, flush)
     if "streamk" in args.which:
         bench_streamk(args.iters, flush)
+    if "layers" in args.which:
+        bench_layers(args.iters, flush)
     if "xattn" in args.which:
         bench_xattn(args.iters, flush)
 

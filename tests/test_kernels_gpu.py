@@ -216,10 +216,11 @@ def test_qformer_embed_ln(ops):
     assert (out - ref).abs().max() < 2.5e-2       # bf16 output rounding of O(4) values
 
 
-@pytest.mark.parametrize("cols", [768, 320, 2560])
-def test_layernorm(ops, cols):
+@pytest.mark.parametrize("rows,cols", [(333, 768), (333, 320), (333, 2560), (5000, 2560), (100, 3072), (1, 1024)])
+def test_layernorm(ops, rows, cols):
+    """Warp-per-row kernel (many rows) and CTA-per-row kernel (<= 512 rows of >= 1024 columns: LLM decode)."""
     g = torch.Generator().manual_seed(3)
-    x = _rand_bf16((333, cols), g, 2.0)
+    x = _rand_bf16((rows, cols), g, 2.0)
     gamma = 1 + 0.1 * torch.randn(cols, generator=g)
     beta = 0.1 * torch.randn(cols, generator=g)
     out = ops.layernorm(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5).float().cpu()
