@@ -20,6 +20,8 @@
 //   * the epilogue warps write this slice's fp32 partial rows to a workspace [S][M][N] with plain stores, and
 //     skinny_finalize_kernel sums the S partials in a fixed order (deterministic, no atomics) and applies
 //     bias / activation / residual.  The workspace (<= 16 MB for the decoder GEMMs) lives in L2 between the two kernels.
+//     (Tried: the CTA that delivers a tile's last partial reduces it in place of the second kernel -- fence + atomic +
+//     fence per tile on the epilogue's critical path made the GEMMs 3x slower; it would need its own warps.)
 #include "common.cuh"
 #include "host_util.h"
 

@@ -369,19 +369,39 @@ __global__ void llm_build_prefix_kernel(const __nv_bfloat16* __restrict__ proj, 
   *(reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * d) + c) = u;
 }
 
-__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
-                                                          int32_t* __restrict__ out) {
+// First maximum of every row (ties -> lower index).  One CTA of 1024 threads per row; 16-byte loads, four of them in
+// flight per thread (the first cut walked the row with dependent 4-byte loads: 94 us for 100 x 50272 logits).
+__global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
+                                                           int32_t* __restrict__ out) {
   pdl_wait_then_trigger();
-  __shared__ float s_val[8];
-  __shared__ int s_idx[8];
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
   const int row = blockIdx.x;
   const float* x = logits + static_cast<size_t>(row) * ld;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float v = x[c];
+  auto take = [&](float v, int c) {
     if (v > best || (v == best && c < best_i)) { best = v; best_i = c; }
+  };
+  const bool vec = (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+  const int n4 = vec ? cols / 4 : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  int i = threadIdx.x;
+  for (; i + 3 * static_cast<int>(blockDim.x) < n4; i += 4 * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(x4 + i + u * blockDim.x);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = (i + u * blockDim.x) * 4;
+      take(v[u].x, c); take(v[u].y, c + 1); take(v[u].z, c + 2); take(v[u].w, c + 3);
+    }
   }
+  for (; i < n4; i += blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    take(v.x, i * 4); take(v.y, i * 4 + 1); take(v.z, i * 4 + 2); take(v.w, i * 4 + 3);
+  }
+  for (int c = n4 * 4 + threadIdx.x; c < cols; c += blockDim.x) take(x[c], c);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -390,10 +410,17 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
   }
   if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = best_i; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
-      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < best_i)) { best = s_val[w]; best_i = s_idx[w]; }
-    out[row] = best_i;
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    best = threadIdx.x < nw ? s_val[threadIdx.x] : -INFINITY;
+    best_i = threadIdx.x < nw ? s_idx[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (threadIdx.x == 0) out[row] = best_i;
   }
 }
 
@@ -645,7 +672,7 @@ extern "C" int opsg_argmax_rows(const float* logits, int ld, int rows, int cols,
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(logits && out && rows > 0 && cols > 0 && ld >= cols, "argmax_rows: bad argument");
-  launch_kernel(argmax_rows_kernel, rows, 256, 0, ST(stream), logits, ld, rows, cols, out);
+  launch_kernel(argmax_rows_kernel, rows, 1024, 0, ST(stream), logits, ld, rows, cols, out);
   OPSG_CHECK_LAUNCH("argmax_rows_kernel");
   return OPSG_OK;
 }
