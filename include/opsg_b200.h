@@ -123,9 +123,12 @@ int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const float* bet
  * for B pair queries whose rows live in the split layout of opsg_qformer_embed_ln.  qkv: bf16 [R, 3*d]
  * (q | k | v, heads of head_dim inside each); text_mask int32 [B, T] (0 = padded key: the reference's
  * -10000 additive bias underflows to weight exactly 0); ctx_out bf16 [R_out, d].  Queries: the n_query
- * query rows of every pair and, if text_queries != 0, the T text rows too. */
-int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_mask, int B, int n_query, int T, int num_heads,
-                         int head_dim, int text_queries, opsg_bf16* ctx_out, void* stream);
+ * query rows of every pair and, if text_queries != 0, the T text rows too.  shared_query_qkv (bf16 [n_query, 3*d] or
+ * NULL): q/k/v of the query rows when they are identical for every pair -- layer 0, where they are the projection of
+ * LN(query tokens) and the reference recomputes them B times; the query rows of qkv are then never read. */
+int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* shared_query_qkv, const int32_t* text_mask, int B,
+                         int n_query, int T, int num_heads, int head_dim, int text_queries, opsg_bf16* ctx_out,
+                         void* stream);
 
 /* ---- a6 / K5: pair-query x image-feature masked cross-attention (the north-star kernel) ------------
  * Replaces the score/softmax/context part of the cross-attention MHA (HF :499-536) as called with

@@ -34,7 +34,7 @@ SIGNATURES = {
     "opsg_init_rows_f32": [P, I, P, I, I, P],
     "opsg_qformer_embed_ln": [P, I, P, I, I, P, I, P, P, P, F, I, P, P],
     "opsg_layernorm_bf16": [P, P, P, F, P, I, I, P],
-    "opsg_self_attn_small": [P, P, I, I, I, I, I, I, P, P],
+    "opsg_self_attn_small": [P, P, P, I, I, I, I, I, I, P, P],
     "opsg_xattn_bias_tiles_bytes": [I, I],
     "opsg_xattn_bias_tiles": [P, I, P, I, I, I, I, P, P],
     "opsg_xattn_pairs": [P, P, I, P, I, P, I, P, I, I, I, I, I, I, P, P, P],

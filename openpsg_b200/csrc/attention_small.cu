@@ -16,6 +16,7 @@ struct SmallAttnParams {
   int mode;                       // 0 = Q-Former split layout, 1 = LLM static KV cache
   // mode 0
   const __nv_bfloat16* qkv;       // [R, 3*d_model]
+  const __nv_bfloat16* qkv_shared;// [n_query, 3*d_model] or NULL: q/k/v of the query rows when they are the same for every pair
   const int32_t* text_mask;       // [B, T]
   int B, n_query, T, text_queries;
   // mode 1
@@ -76,6 +77,10 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
                          : static_cast<size_t>(p.B) * p.n_query + static_cast<size_t>(seq) * p.T + (i - p.n_query);
   };
 
+  auto qformer_qkv_row = [&](int i) -> const __nv_bfloat16* {
+    return (p.qkv_shared && i < p.n_query) ? p.qkv_shared + static_cast<size_t>(i) * (3 * p.d_model)
+                                           : p.qkv + qformer_row(i) * (3 * p.d_model);
+  };
   // ---- stage K, V^T and key validity -------------------------------------------------------------
   constexpr int VEC = HD / 8;
   for (int idx = threadIdx.x; idx < NK * VEC; idx += blockDim.x) {
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
     uint4 ku = make_uint4(0, 0, 0, 0), vu = make_uint4(0, 0, 0, 0);
     if (key < n_keys) {
       if (p.mode == 0) {
-        const __nv_bfloat16* base = p.qkv + qformer_row(key) * (3 * p.d_model) + head * HD + v8 * 8;
+        const __nv_bfloat16* base = qformer_qkv_row(key) + head * HD + v8 * 8;
         ku = __ldg(reinterpret_cast<const uint4*>(base + p.d_model));
         vu = __ldg(reinterpret_cast<const uint4*>(base + 2 * p.d_model));
       } else {
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const SmallAttnParams p
       const int qi = q0 + r;
       uint4 qu = make_uint4(0, 0, 0, 0);
       if (qi < n_q) {
-        if (p.mode == 0) qu = __ldg(reinterpret_cast<const uint4*>(p.qkv + qformer_row(qi) * (3 * p.d_model) + head * HD + v8 * 8));
+        if (p.mode == 0) qu = __ldg(reinterpret_cast<const uint4*>(qformer_qkv_row(qi) + head * HD + v8 * 8));
         else qu = __ldg(reinterpret_cast<const uint4*>(p.q + (static_cast<size_t>(seq) * p.q_len + qi) * p.ld_q + head * HD + v8 * 8));
       }
       *reinterpret_cast<uint4*>(sQ + r * QS + v8 * 8) = qu;
@@ -266,7 +271,10 @@ __global__ void __launch_bounds__(128) qformer_self_attn_kernel(const SmallAttnP
     for (int idx = threadIdx.x; idx < 64 * 8; idx += 128) {
       const int r = idx >> 3, v8 = idx & 7;
       const bool ok = r < n_keys;
-      const __nv_bfloat16* base = p.qkv + row_of(pair, ok ? r : 0) * (3 * p.d_model) + head * kQfHD + v8 * 8;
+      const int rr = ok ? r : 0;
+      const __nv_bfloat16* base = ((p.qkv_shared && rr < p.n_query) ? p.qkv_shared + static_cast<size_t>(rr) * (3 * p.d_model)
+                                                                    : p.qkv + row_of(pair, rr) * (3 * p.d_model)) +
+                                  head * kQfHD + v8 * 8;
       cp_async16(sQ + r * kQfRS + v8 * 8, base, ok && r < n_q);
       cp_async16(sK + r * kQfRS + v8 * 8, base + p.d_model, ok);
       cp_async16(sV + r * kQfRS + v8 * 8, base + 2 * p.d_model, ok);
@@ -558,8 +566,9 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_q
 
 using namespace opsg;
 
-extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_mask, int B, int n_query, int T, int num_heads,
-                                    int head_dim, int text_queries, opsg_bf16* ctx_out, void* stream) {
+extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* shared_query_qkv, const int32_t* text_mask, int B,
+                                    int n_query, int T, int num_heads, int head_dim, int text_queries, opsg_bf16* ctx_out,
+                                    void* stream) {
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(qkv && ctx_out && (T == 0 || text_mask), "self_attn_small: null pointer");
@@ -567,6 +576,8 @@ extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const int32_t* text_ma
   SmallAttnParams p{};
   p.mode = 0;
   p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.qkv_shared = reinterpret_cast<const __nv_bfloat16*>(shared_query_qkv);
+  OPSG_CHECK_ARG(!shared_query_qkv || ((uintptr_t)shared_query_qkv & 15) == 0, "self_attn_small: shared_query_qkv must be 16-byte aligned");
   p.text_mask = text_mask;
   p.B = B; p.n_query = n_query; p.T = T; p.text_queries = text_queries;
   p.out = reinterpret_cast<__nv_bfloat16*>(ctx_out);

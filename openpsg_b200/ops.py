@@ -234,15 +234,19 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def self_attn_small(qkv, text_mask, B, n_query, T, num_heads, head_dim, text_queries: bool, out=None):
+def self_attn_small(qkv, text_mask, B, n_query, T, num_heads, head_dim, text_queries: bool, out=None, shared_query_qkv=None):
+    """shared_query_qkv: bf16 [n_query, 3*d] q/k/v of the query rows when they are the same for every pair (layer 0)."""
     _cuda(qkv, torch.bfloat16, "qkv")
+    if shared_query_qkv is not None:
+        _cuda(shared_query_qkv, torch.bfloat16, "shared_query_qkv")
+        assert shared_query_qkv.is_contiguous() and tuple(shared_query_qkv.shape) == (n_query, 3 * num_heads * head_dim)
     d = num_heads * head_dim
     assert qkv.is_contiguous() and qkv.shape[1] == 3 * d
     rows = B * (n_query + T) if text_queries else B * n_query
     if out is None:
         out = torch.empty((rows, d), dtype=torch.bfloat16, device=qkv.device)
     with _timed("self_attn_small", 4.0 * B * num_heads * (n_query + (T if text_queries else 0)) * (n_query + T) * head_dim, 2.0 * (qkv.numel() + out.numel())):
-        _lib.check(_lib.load().opsg_self_attn_small(_ptr(qkv), _ptr(text_mask), B, n_query, T, num_heads, head_dim,
+        _lib.check(_lib.load().opsg_self_attn_small(_ptr(qkv), _ptr(shared_query_qkv), _ptr(text_mask), B, n_query, T, num_heads, head_dim,
                                                    int(text_queries), _ptr(out), _stream()))
     _count()
     return out

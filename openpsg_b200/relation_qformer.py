@@ -207,6 +207,8 @@ class RelationQueryTransformer:
         # +0.6 % pairs/s only (the epilogue pays for it) and the fp32 atomics behind the row statistics make runs differ
         # in the last bf16 bit, so the default keeps the separate LayerNorm kernel.
         self.fold_ln = (os.environ.get("OPSG_FOLD_LN", "0") == "1") if fold_ln is None else bool(fold_ln)
+        # layer 0 projects the (pair-independent) query rows once instead of B times; OPSG_SHARE_QUERY_ROWS=0 turns it off
+        self.share_query_rows = os.environ.get("OPSG_SHARE_QUERY_ROWS", "1") != "0"
 
     # -- K1 ------------------------------------------------------------------------------------------
     def image_tokens(self, feat: torch.Tensor) -> torch.Tensor:
@@ -256,8 +258,18 @@ class RelationQueryTransformer:
             vt = torch.zeros((d, Lp), dtype=torch.bfloat16, device=dev)
             ops.gemm(lw["w_cv"], X, lw["b_cv"], bias_along_m=True, out=vt[:, :L])  # V^T [d, L]
             # self-attention over the 33 + T rows of every pair
-            qkv = ops.gemm(h, lw["w_qkv"], lw["b_qkv"])                          # [R, 3d]
-            ctx = ops.self_attn_small(qkv, text_mask, B, N_QUERY, T, NUM_HEADS, HEAD_DIM, text_queries=not last)
+            if li == 0 and self.share_query_rows and T > 0:
+                # Layer 0: the 33 query rows of every pair are the same LN(query tokens) (v4:158-159 expands them B times
+                # and HF projects every copy), so their q/k/v are projected once and only the text rows go through the
+                # big GEMM; the attention kernel reads the query rows from the shared table.
+                qkv_q = ops.gemm(h[:N_QUERY], lw["w_qkv"], lw["b_qkv"])          # [33, 3d]
+                qkv = torch.empty((h.shape[0], 3 * d), dtype=torch.bfloat16, device=dev)
+                ops.gemm(h[RQ:], lw["w_qkv"], lw["b_qkv"], out=qkv[RQ:])          # text rows only
+                ctx = ops.self_attn_small(qkv, text_mask, B, N_QUERY, T, NUM_HEADS, HEAD_DIM, text_queries=not last,
+                                          shared_query_qkv=qkv_q)
+            else:
+                qkv = ops.gemm(h, lw["w_qkv"], lw["b_qkv"])                      # [R, 3d]
+                ctx = ops.self_attn_small(qkv, text_mask, B, N_QUERY, T, NUM_HEADS, HEAD_DIM, text_queries=not last)
             rows = ctx.shape[0]                                                  # R, or B*33 on the last layer
             pre = ops.gemm(ctx, lw["w_o"], lw["b_o"], residual=h[:rows])
             h1 = ops.layernorm(pre, lw["ln_self"][0], lw["ln_self"][1], LN_EPS)

@@ -254,6 +254,22 @@ def test_self_attn_small(ops, text_queries):
         assert (got - ref[:nrows]).abs().max() < 2e-2
 
 
+def test_self_attn_small_shared_query_rows(ops):
+    """Layer-0 form: q/k/v of the query rows come from one [n_query, 3d] table shared by all pairs; bit-identical to the
+    full-layout call on a qkv whose query rows are that table repeated (the query rows of qkv itself are never read)."""
+    g = torch.Generator().manual_seed(41)
+    B, nq, T, H, hd = 9, 33, 16, 12, 64
+    d = H * hd
+    shared = _rand_bf16((nq, 3 * d), g)
+    text = _rand_bf16((B * T, 3 * d), g)
+    full = torch.cat([shared.repeat(B, 1), text])
+    tmask = (torch.arange(T)[None, :] < torch.randint(8, T + 1, (B, 1), generator=g)).to(torch.int32)
+    ref = ops.self_attn_small(full.cuda(), tmask.cuda(), B, nq, T, H, hd, True)
+    poisoned = torch.cat([torch.full((B * nq, 3 * d), float("nan"), dtype=torch.bfloat16), text])
+    got = ops.self_attn_small(poisoned.cuda(), tmask.cuda(), B, nq, T, H, hd, True, shared_query_qkv=shared.cuda())
+    assert torch.equal(got, ref)
+
+
 # ----------------------------------------------------------------------------------------------
 # K5: pair x image masked cross-attention (tcgen05).  tol 2e-2 abs (bf16 P, bf16 output)
 # ----------------------------------------------------------------------------------------------
