@@ -539,9 +539,132 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K10b, second version — decode attention with the sequence's K / V head slices staged in shared memory.
+// The register version above keeps 16 loads per lane in flight and needs four dependent round trips per (sequence,
+// head) (two key batches for K, two for V) at 122 registers per thread: 1.35 waves of CTAs, 27 us per launch for ~60 MB.
+// Here a warp issues EVERY 16-byte piece of its item's K and V slices as cp.async at once (one round trip, ~26 KB per
+// warp, no registers held), computes the scores lane-per-key from shared memory while V is still landing, then the
+// context lane-per-dimension-pair.  Rows are padded by 16 bytes so that lane-per-key 16-byte reads are conflict-free.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnParams p, int warps_per_cta) {
+  pdl_wait_then_trigger();
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  constexpr int C = HD / 8;                                 // 16-byte chunks per key row
+  constexpr int RS = HD * 2 + 16;                           // padded row stride (bytes)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * warps_per_cta + warp;      // (sequence, head)
+  if (warp >= warps_per_cta || item >= p.B) return;         // p.B = nseq * num_heads (set by the launcher)
+  const int seq = item / p.num_heads, head = item % p.num_heads;
+  const int ctx = p.q_pos0 + 1;                             // keys 0 .. q_pos0 (causal, the new token included)
+  const int ctx_pad = (ctx + 31) & ~31;
+  const int per_warp = 2 * ctx * RS + HD * 2 + ctx_pad * 4;
+  uint8_t* sK = smem_dyn + static_cast<size_t>(warp) * ((per_warp + 15) & ~15);
+  uint8_t* sV = sK + ctx * RS;
+  uint8_t* sQ = sV + ctx * RS;
+  float* sP = reinterpret_cast<float*>(sQ + HD * 2);
+  const __nv_bfloat16* kbase = p.k_cache + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
+  const __nv_bfloat16* vbase = p.v_cache + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
+  const uint8_t* kmask = p.key_mask + static_cast<size_t>(seq) * p.max_ctx;
+
+  for (int idx = lane; idx < ctx * C; idx += 32) {
+    const int key = idx / C, c = idx - key * C;
+    cp_async16(sK + key * RS + c * 16, kbase + static_cast<size_t>(key) * p.d_model + c * 8, true);
+  }
+  if (lane < C) cp_async16(sQ + lane * 16, p.q + static_cast<size_t>(seq) * p.ld_q + head * HD + lane * 8, true);
+  cp_async_commit();
+  for (int idx = lane; idx < ctx * C; idx += 32) {
+    const int key = idx / C, c = idx - key * C;
+    cp_async16(sV + key * RS + c * 16, vbase + static_cast<size_t>(key) * p.d_model + c * 8, true);
+  }
+  cp_async_commit();
+
+  // ---- scores: lane-per-key ----------------------------------------------------------------------------
+  cp_async_wait<1>();
+  __syncwarp();
+  float sc[4];                                              // ctx <= 128 (host-checked)
+  float mx = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int key = r * 32 + lane;
+    float d = -INFINITY;
+    if (key < ctx && __ldg(kmask + key) != 0) {
+      d = 0.f;
+      const uint8_t* kr = sK + key * RS;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const uint4 k4 = *reinterpret_cast<const uint4*>(kr + c * 16);
+        const uint4 q4 = *reinterpret_cast<const uint4*>(sQ + c * 16);
+        d = fmaf(bf16_lo(k4.x), bf16_lo(q4.x), d); d = fmaf(bf16_hi(k4.x), bf16_hi(q4.x), d);
+        d = fmaf(bf16_lo(k4.y), bf16_lo(q4.y), d); d = fmaf(bf16_hi(k4.y), bf16_hi(q4.y), d);
+        d = fmaf(bf16_lo(k4.z), bf16_lo(q4.z), d); d = fmaf(bf16_hi(k4.z), bf16_hi(q4.z), d);
+        d = fmaf(bf16_lo(k4.w), bf16_lo(q4.w), d); d = fmaf(bf16_hi(k4.w), bf16_hi(q4.w), d);
+      }
+    }
+    sc[r] = d;
+    mx = fmaxf(mx, d);
+  }
+  mx = warp_max(mx);
+  if (mx == -INFINITY) mx = 0.f;
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float e = ex2f((sc[r] - mx) * p.scale_log2e);     // exp2(-inf) = 0 for masked / out-of-range keys
+    // P is rounded to bf16 like the tensor-core path (and HF's bf16 softmax output) before multiplying V
+    if (r * 32 + lane < ctx_pad) sP[r * 32 + lane] = __bfloat162float(__float2bfloat16(e));
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+
+  // ---- context: lane-per-dimension-pair ------------------------------------------------------------------
+  cp_async_wait<0>();
+  __syncwarp();
+#pragma unroll
+  for (int pass = 0; pass < (HD / 2 + 31) / 32; ++pass) {
+    const int dp = pass * 32 + lane;
+    if (dp < HD / 2) {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      int key = 0;
+      for (; key + 1 < ctx; key += 2) {
+        const uint32_t va = *reinterpret_cast<const uint32_t*>(sV + key * RS + dp * 4);
+        const uint32_t vb = *reinterpret_cast<const uint32_t*>(sV + (key + 1) * RS + dp * 4);
+        const float pa = sP[key], pb = sP[key + 1];
+        o0 = fmaf(pa, bf16_lo(va), o0); o1 = fmaf(pa, bf16_hi(va), o1);
+        o2 = fmaf(pb, bf16_lo(vb), o2); o3 = fmaf(pb, bf16_hi(vb), o3);
+      }
+      if (key < ctx) {
+        const uint32_t va = *reinterpret_cast<const uint32_t*>(sV + key * RS + dp * 4);
+        const float pa = sP[key];
+        o0 = fmaf(pa, bf16_lo(va), o0); o1 = fmaf(pa, bf16_hi(va), o1);
+      }
+      *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(seq) * p.ld_out + head * HD + dp * 2) =
+          pack_bf16x2((o0 + o2) * inv, (o1 + o3) * inv);
+    }
+  }
+}
+
 template <int HD>
 static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
   p.B = nseq * p.num_heads;
+  static const int use_smem = [] { const char* e = getenv("OPSG_DECODE_ATTN_SMEM"); return e ? atoi(e) : 1; }();
+  const int ctx = p.q_pos0 + 1;
+  const int per_warp = ((2 * ctx * (HD * 2 + 16) + HD * 2 + ((ctx + 31) & ~31) * 4) + 15) & ~15;
+  if (use_smem && ctx <= 128 && per_warp <= 110 * 1024) {
+    int wpc = (110 * 1024) / per_warp;                     // two or more CTAs per SM
+    if (wpc > 4) wpc = 4;
+    static bool configured = false;
+    if (!configured) {
+      int rc = check_cuda(cudaFuncSetAttribute(decode_attn_smem_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
+                          "cudaFuncSetAttribute(decode_attn_smem)");
+      if (rc) return rc;
+      configured = true;
+    }
+    launch_kernel(decode_attn_smem_kernel<HD>, (p.B + wpc - 1) / wpc, 128, static_cast<size_t>(wpc) * per_warp, st, p, wpc);
+    OPSG_CHECK_LAUNCH("decode_attn_smem_kernel");
+    return OPSG_OK;
+  }
   launch_kernel(decode_attn_kernel<HD>, (p.B + 7) / 8, 256, 0, st, p);
   OPSG_CHECK_LAUNCH("decode_attn_kernel");
   return OPSG_OK;

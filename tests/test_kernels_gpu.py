@@ -254,6 +254,33 @@ def test_self_attn_small(ops, text_queries):
         assert (got - ref[:nrows]).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("hd,heads,q_len,pos0", [(80, 32, 1, 48), (80, 32, 1, 80), (80, 32, 1, 127), (64, 12, 1, 17),
+                                                 (128, 8, 1, 63), (80, 32, 49, 0), (64, 12, 5, 3)])
+def test_llm_attn_static_cache(ops, hd, heads, q_len, pos0):
+    """K10a/b: causal attention of q_len new tokens (positions pos0 ..) over a static KV cache with a key-validity mask
+    (left padding); q_len == 1 takes the shared-memory decode kernel.  tol 2e-2 abs (bf16 P and output)."""
+    g = torch.Generator().manual_seed(hd + q_len + pos0)
+    nseq, max_ctx = 7, 128
+    d = heads * hd
+    qkv = _rand_bf16((nseq * q_len, 3 * d), g)
+    kc = _rand_bf16((nseq, max_ctx, d), g)
+    vc = _rand_bf16((nseq, max_ctx, d), g)
+    pad = torch.randint(0, 6, (nseq,), generator=g)
+    kmask = (torch.arange(max_ctx)[None, :] >= pad[:, None]).to(torch.uint8)
+    kmask[:, pos0:] = 1
+    out = torch.zeros((nseq * q_len, d), dtype=torch.bfloat16, device="cuda")
+    ops.llm_attn(qkv.cuda(), kc.cuda(), vc.cuda(), kmask.cuda(), nseq, q_len, pos0, heads, hd, hd ** -0.5, out)
+    q = qkv[:, :d].float().reshape(nseq, q_len, heads, hd).permute(0, 2, 1, 3)
+    ctx = pos0 + q_len
+    k = kc[:, :ctx].float().reshape(nseq, ctx, heads, hd).permute(0, 2, 1, 3)
+    v = vc[:, :ctx].float().reshape(nseq, ctx, heads, hd).permute(0, 2, 1, 3)
+    sc = q @ k.transpose(-1, -2) * hd ** -0.5
+    causal = torch.arange(ctx)[None, :] <= (pos0 + torch.arange(q_len))[:, None]
+    ok = causal[None, None] & kmask[:, None, None, :ctx].bool()
+    ref = (torch.softmax(sc.masked_fill(~ok, float("-inf")), -1) @ v).permute(0, 2, 1, 3).reshape(nseq * q_len, d)
+    assert (out.float().cpu() - ref).abs().max() < 2e-2
+
+
 def test_self_attn_small_shared_query_rows(ops):
     """Layer-0 form: q/k/v of the query rows come from one [n_query, 3d] table shared by all pairs; bit-identical to the
     full-layout call on a qkv whose query rows are that table repeated (the query rows of qkv itself are never read)."""
