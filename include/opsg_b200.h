@@ -194,6 +194,12 @@ int opsg_llm_build_prefix(const opsg_bf16* proj, int proj_rows_per_seq, int proj
 int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_cache, const opsg_bf16* v_cache, int max_ctx,
                   const uint8_t* key_mask, int nseq, int q_len, int q_pos0, int num_heads, int head_dim, float scale,
                   opsg_bf16* out, int ld_out, void* stream);
+/* Decode step (one new token per sequence at position q_pos0): qkv bf16 [nseq, ld_qkv] holds the fused [q | k | v]
+ * projection of the new tokens; the kernel attends over cache keys < q_pos0 plus the new key and WRITES the new k / v
+ * rows into the caches at position q_pos0 (opsg_kv_append + opsg_llm_attn in one launch).  q_pos0 + 1 <= 128. */
+int opsg_llm_attn_append(const opsg_bf16* qkv, int ld_qkv, opsg_bf16* k_cache, opsg_bf16* v_cache, int max_ctx,
+                         const uint8_t* key_mask, int nseq, int q_pos0, int num_heads, int head_dim, float scale,
+                         opsg_bf16* out, int ld_out, void* stream);
 int opsg_kv_append(const opsg_bf16* qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model, opsg_bf16* k_cache,
                    opsg_bf16* v_cache, int max_ctx, void* stream);
 int opsg_argmax_rows(const float* logits, int ld, int rows, int cols, int32_t* out, void* stream);

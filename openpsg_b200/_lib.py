@@ -44,6 +44,7 @@ SIGNATURES = {
     "opsg_embed_gather": [P, I, P, P, P, I, P, I, P],
     "opsg_llm_build_prefix": [P, I, I, I, P, P, I, P, P, I, I, P, P],
     "opsg_llm_attn": [P, I, P, P, I, P, I, I, I, I, I, F, P, I, P],
+    "opsg_llm_attn_append": [P, I, P, P, I, P, I, I, I, I, F, P, I, P],
     "opsg_kv_append": [P, I, I, I, I, I, P, P, I, P],
     "opsg_argmax_rows": [P, I, I, I, P, P],
 }

@@ -25,6 +25,8 @@ struct SmallAttnParams {
   const __nv_bfloat16* v_cache;
   const uint8_t* key_mask;        // [nseq, max_ctx]
   int ld_q, max_ctx, q_len, q_pos0;
+  int append_kv;                  // decode: q points at fused [q | k | v] rows; the new token's k / v are taken from there
+                                  // (not from the cache) and written to the caches at position q_pos0 by this kernel
   // common
   __nv_bfloat16* out;
   int ld_out, num_heads, d_model;
@@ -568,15 +570,20 @@ __global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnPa
   const __nv_bfloat16* vbase = p.v_cache + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
   const uint8_t* kmask = p.key_mask + static_cast<size_t>(seq) * p.max_ctx;
 
+  const __nv_bfloat16* new_kv = p.q + static_cast<size_t>(seq) * p.ld_q + head * HD;      // + d_model: k, + 2 d_model: v
   for (int idx = lane; idx < ctx * C; idx += 32) {
     const int key = idx / C, c = idx - key * C;
-    cp_async16(sK + key * RS + c * 16, kbase + static_cast<size_t>(key) * p.d_model + c * 8, true);
+    const __nv_bfloat16* src = (p.append_kv && key == ctx - 1) ? new_kv + p.d_model + c * 8
+                                                               : kbase + static_cast<size_t>(key) * p.d_model + c * 8;
+    cp_async16(sK + key * RS + c * 16, src, true);
   }
   if (lane < C) cp_async16(sQ + lane * 16, p.q + static_cast<size_t>(seq) * p.ld_q + head * HD + lane * 8, true);
   cp_async_commit();
   for (int idx = lane; idx < ctx * C; idx += 32) {
     const int key = idx / C, c = idx - key * C;
-    cp_async16(sV + key * RS + c * 16, vbase + static_cast<size_t>(key) * p.d_model + c * 8, true);
+    const __nv_bfloat16* src = (p.append_kv && key == ctx - 1) ? new_kv + 2 * p.d_model + c * 8
+                                                               : vbase + static_cast<size_t>(key) * p.d_model + c * 8;
+    cp_async16(sV + key * RS + c * 16, src, true);
   }
   cp_async_commit();
 
@@ -621,6 +628,11 @@ __global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnPa
   // ---- context: lane-per-dimension-pair ------------------------------------------------------------------
   cp_async_wait<0>();
   __syncwarp();
+  if (p.append_kv && lane < C) {            // the new token's head slice joins the caches (replaces a kv_append launch)
+    const size_t off = static_cast<size_t>(ctx - 1) * p.d_model + lane * 8;
+    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(kbase) + off) = *reinterpret_cast<const uint4*>(sK + (ctx - 1) * RS + lane * 16);
+    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(vbase) + off) = *reinterpret_cast<const uint4*>(sV + (ctx - 1) * RS + lane * 16);
+  }
 #pragma unroll
   for (int pass = 0; pass < (HD / 2 + 31) / 32; ++pass) {
     const int dp = pass * 32 + lane;
@@ -645,6 +657,9 @@ __global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnPa
   }
 }
 
+__global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model,
+                                 __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int max_ctx);
+
 template <int HD>
 static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
   p.B = nseq * p.num_heads;
@@ -664,6 +679,12 @@ static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
     launch_kernel(decode_attn_smem_kernel<HD>, (p.B + wpc - 1) / wpc, 128, static_cast<size_t>(wpc) * per_warp, st, p, wpc);
     OPSG_CHECK_LAUNCH("decode_attn_smem_kernel");
     return OPSG_OK;
+  }
+  if (p.append_kv) {                         // register version reads the cache only: append with the copy kernel first
+    const long long total = static_cast<long long>(nseq) * (p.d_model / 8);
+    launch_kernel(kv_append_kernel, static_cast<int>((total + 255) / 256), 256, 0, st, p.q, p.ld_q, nseq, 1, p.q_pos0,
+                  p.d_model, const_cast<__nv_bfloat16*>(p.k_cache), const_cast<__nv_bfloat16*>(p.v_cache), p.max_ctx);
+    OPSG_CHECK_LAUNCH("kv_append_kernel");
   }
   launch_kernel(decode_attn_kernel<HD>, (p.B + 7) / 8, 256, 0, st, p);
   OPSG_CHECK_LAUNCH("decode_attn_kernel");
@@ -752,6 +773,33 @@ extern "C" int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_ca
     return launch_decode_attn<128>(p, nseq, st);
   }
   return dispatch_hd(p, nseq, q_pos0 + q_len, head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int opsg_llm_attn_append(const opsg_bf16* qkv, int ld_qkv, opsg_bf16* k_cache, opsg_bf16* v_cache, int max_ctx,
+                                    const uint8_t* key_mask, int nseq, int q_pos0, int num_heads, int head_dim, float scale,
+                                    opsg_bf16* out, int ld_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(qkv && k_cache && v_cache && key_mask && out, "llm_attn_append: null pointer");
+  OPSG_CHECK_ARG(nseq > 0 && q_pos0 >= 0 && q_pos0 < max_ctx && q_pos0 + 1 <= 128, "llm_attn_append: bad shape");
+  OPSG_CHECK_ARG(head_dim == 64 || head_dim == 80 || head_dim == 128, "llm_attn_append: head_dim %d unsupported", head_dim);
+  OPSG_CHECK_ARG(ld_qkv >= 3 * num_heads * head_dim && (ld_qkv % 8) == 0 && (ld_out % 8) == 0 &&
+                 (((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)k_cache | (uintptr_t)v_cache) & 15) == 0,
+                 "llm_attn_append: bad layout");
+  SmallAttnParams p{};
+  p.mode = 1;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.k_cache = reinterpret_cast<const __nv_bfloat16*>(k_cache);
+  p.v_cache = reinterpret_cast<const __nv_bfloat16*>(v_cache);
+  p.key_mask = key_mask;
+  p.ld_q = ld_qkv; p.max_ctx = max_ctx; p.q_len = 1; p.q_pos0 = q_pos0; p.append_kv = 1;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out; p.num_heads = num_heads; p.d_model = num_heads * head_dim;
+  p.scale_log2e = 1.4426950408889634f * scale;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (head_dim == 64) return launch_decode_attn<64>(p, nseq, st);
+  if (head_dim == 80) return launch_decode_attn<80>(p, nseq, st);
+  return launch_decode_attn<128>(p, nseq, st);
 }
 
 extern "C" int opsg_kv_append(const opsg_bf16* qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model, opsg_bf16* k_cache,

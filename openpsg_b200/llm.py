@@ -107,9 +107,13 @@ class OPTDecodeEngine:
         gemm = ops.gemm_small_m if (self.small_m and h.shape[0] <= 128) else ops.gemm
         x = ops.layernorm(h, lw["ln1"][0], lw["ln1"][1], self.LN_EPS)
         qkv = gemm(x, lw["w_qkv"], lw["b_qkv"])                                        # [rows, 3d]
-        ops.kv_append(qkv, nseq, q_len, pos0, d, k_cache, v_cache)
         ctx = torch.empty((nseq * q_len, d), dtype=torch.bfloat16, device=h.device)
-        ops.llm_attn(qkv, k_cache, v_cache, key_mask, nseq, q_len, pos0, w.heads, w.head_dim, w.head_dim ** -0.5, ctx)
+        if q_len == 1 and pos0 + 1 <= 128:
+            # decode step: the attention kernel takes the new k / v from qkv and writes them into the caches itself
+            ops.llm_attn_append(qkv, k_cache, v_cache, key_mask, nseq, pos0, w.heads, w.head_dim, w.head_dim ** -0.5, ctx)
+        else:
+            ops.kv_append(qkv, nseq, q_len, pos0, d, k_cache, v_cache)
+            ops.llm_attn(qkv, k_cache, v_cache, key_mask, nseq, q_len, pos0, w.heads, w.head_dim, w.head_dim ** -0.5, ctx)
         gemm(ctx, lw["w_o"], lw["b_o"], residual=h, out=h)                             # h += out_proj(ctx)
         x = ops.layernorm(h, lw["ln2"][0], lw["ln2"][1], self.LN_EPS)
         f = gemm(x, lw["w_fc1"], lw["b_fc1"], act=ops.ACT_RELU)

@@ -357,6 +357,18 @@ def llm_attn(q, k_cache, v_cache, key_mask, nseq, q_len, q_pos0, num_heads, head
     return out
 
 
+def llm_attn_append(qkv, k_cache, v_cache, key_mask, nseq, q_pos0, num_heads, head_dim, scale, out):
+    """Decode step: append the new tokens' k / v (from the fused qkv rows) to the caches at q_pos0 and attend, one launch."""
+    max_ctx = k_cache.shape[1]
+    ctx = q_pos0 + 1
+    with _timed("llm_attn", 4.0 * nseq * ctx * num_heads * head_dim, 4.0 * nseq * ctx * num_heads * head_dim):
+        _lib.check(_lib.load().opsg_llm_attn_append(_ptr(qkv), qkv.stride(0), _ptr(k_cache), _ptr(v_cache), max_ctx, _ptr(key_mask),
+                                                   nseq, q_pos0, num_heads, head_dim, float(scale), _ptr(out), out.stride(0),
+                                                   _stream()))
+    _count()
+    return out
+
+
 def kv_append(qkv, nseq, q_len, pos0, d_model, k_cache, v_cache):
     with _timed("kv_append", 0.0, 8.0 * nseq * q_len * d_model):
         _lib.check(_lib.load().opsg_kv_append(_ptr(qkv), qkv.stride(0), nseq, q_len, pos0, d_model, _ptr(k_cache), _ptr(v_cache),

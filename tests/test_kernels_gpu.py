@@ -281,6 +281,27 @@ def test_llm_attn_static_cache(ops, hd, heads, q_len, pos0):
     assert (out.float().cpu() - ref).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("hd,heads,pos0", [(80, 32, 60), (64, 12, 0), (128, 8, 127)])
+def test_llm_attn_append_equals_append_then_attend(ops, hd, heads, pos0):
+    """The fused decode entry (new k / v taken from the qkv row and written to the caches by the attention kernel) gives
+    the same output and the same caches as opsg_kv_append followed by opsg_llm_attn."""
+    g = torch.Generator().manual_seed(hd + pos0)
+    nseq, max_ctx = 5, 128
+    d = heads * hd
+    qkv = _rand_bf16((nseq, 3 * d), g).cuda()
+    kc = _rand_bf16((nseq, max_ctx, d), g).cuda()
+    vc = _rand_bf16((nseq, max_ctx, d), g).cuda()
+    kmask = torch.ones((nseq, max_ctx), dtype=torch.uint8).cuda()
+    kmask[1, :min(3, pos0)] = 0
+    kc2, vc2 = kc.clone(), vc.clone()
+    ref = torch.zeros((nseq, d), dtype=torch.bfloat16, device="cuda")
+    ops.kv_append(qkv, nseq, 1, pos0, d, kc, vc)
+    ops.llm_attn(qkv, kc, vc, kmask, nseq, 1, pos0, heads, hd, hd ** -0.5, ref)
+    got = torch.zeros_like(ref)
+    ops.llm_attn_append(qkv, kc2, vc2, kmask, nseq, pos0, heads, hd, hd ** -0.5, got)
+    assert torch.equal(got, ref) and torch.equal(kc2, kc) and torch.equal(vc2, vc)
+
+
 def test_self_attn_small_shared_query_rows(ops):
     """Layer-0 form: q/k/v of the query rows come from one [n_query, 3d] table shared by all pairs; bit-identical to the
     full-layout call on a qkv whose query rows are that table repeated (the query rows of qkv itself are never read)."""
