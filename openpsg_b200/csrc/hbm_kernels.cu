@@ -174,10 +174,13 @@ __global__ void __launch_bounds__(256) qformer_embed_ln_kernel(const float* __re
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                float eps, int d, __nv_bfloat16* __restrict__ out) {
   pdl_wait_then_trigger();
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // work item w: 0 .. nq-1 = the query rows of pair 0 (every other pair gets a copy, qformer_broadcast_rows_kernel),
+  // nq .. nq + B*T - 1 = the text rows
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int n_query_rows = B * nq;
-  if (row >= n_query_rows + B * T) return;
+  if (w >= nq + B * T) return;
+  const int row = w < nq ? w : n_query_rows + (w - nq);
   const float* src;
   const float* pos = nullptr;
   if (row < n_query_rows) {
@@ -238,26 +241,28 @@ __global__ void __launch_bounds__(256) exist_logits_kernel(const __nv_bfloat16* 
 }
 
 // rank(i) = #{j : z_j > z_i or (z_j == z_i and j < i)};  rank < k  ->  topk[rank] = i.
+// Exact top-k by rank counting (ties -> lower index, as torch.topk / sort of the reference, v4:236-237): candidate i's
+// rank = #{j : z_j > z_i or (z_j == z_i and j < i)}.  A CTA ranks 32 candidates; each of its 8 warps counts over one
+// eighth of the list (lane = candidate), so a thread walks B / 8 values instead of B (25 us -> ~4 us at B = 1600).
 __global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict__ logits, int B, int k,
                                                         int32_t* __restrict__ topk) {
   pdl_wait_then_trigger();
-  __shared__ float tile[2048];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float zi = i < B ? logits[i] : 0.f;
+  __shared__ int s_rank[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 32 + lane;
+  if (threadIdx.x < 32) s_rank[threadIdx.x] = 0;
+  __syncthreads();
+  const float zi = i < B ? __ldg(logits + i) : 0.f;
+  const int per = (B + 7) / 8;
+  const int j0 = warp * per, j1 = min(B, j0 + per);
   int rank = 0;
-  for (int j0 = 0; j0 < B; j0 += 2048) {
-    const int n = min(2048, B - j0);
-    __syncthreads();
-    for (int t = threadIdx.x; t < n; t += blockDim.x) tile[t] = logits[j0 + t];
-    __syncthreads();
-    if (i < B) {
-      for (int t = 0; t < n; ++t) {
-        const float zj = tile[t];
-        rank += (zj > zi || (zj == zi && (j0 + t) < i)) ? 1 : 0;
-      }
-    }
+  for (int j = j0; j < j1; ++j) {
+    const float zj = __ldg(logits + j);                  // same address across the warp: one broadcast load
+    rank += (zj > zi || (zj == zi && j < i)) ? 1 : 0;
   }
-  if (i < B && rank < k) topk[rank] = i;
+  if (i < B) atomicAdd(&s_rank[lane], rank);
+  __syncthreads();
+  if (warp == 0 && i < B && s_rank[lane] < k) topk[s_rank[lane]] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,6 +483,19 @@ extern "C" int opsg_init_rows_f32(float* out, int ld_out, const float* row, int 
   return OPSG_OK;
 }
 
+// rows [nq, B*nq) of h = copies of rows [0, nq): LN(query tokens) is the same for every pair (v4:158-159 expands it)
+__global__ void __launch_bounds__(256) qformer_broadcast_rows_kernel(__nv_bfloat16* __restrict__ h, int nq, int B, int d) {
+  pdl_wait_then_trigger();
+  const int vec = d / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B - 1) * nq * vec;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % vec);
+  const long long r = idx / vec + nq;                    // destination row
+  const int q = static_cast<int>(r % nq);
+  reinterpret_cast<uint4*>(h + r * d)[c] = __ldg(reinterpret_cast<const uint4*>(h + static_cast<size_t>(q) * d) + c);
+}
+
 extern "C" int opsg_qformer_embed_ln(const float* query, int n_query, const int32_t* input_ids, int B, int T,
                                      const float* word_emb, int vocab, const float* pos_emb, const float* gamma,
                                      const float* beta, float eps, int d, opsg_bf16* h_out, void* stream) {
@@ -486,11 +504,17 @@ extern "C" int opsg_qformer_embed_ln(const float* query, int n_query, const int3
   OPSG_CHECK_ARG(query && word_emb && pos_emb && gamma && beta && h_out, "qformer_embed_ln: null pointer");
   OPSG_CHECK_ARG(T == 0 || input_ids, "qformer_embed_ln: null input_ids");
   OPSG_CHECK_ARG(d % 8 == 0 && d <= 1024 && B > 0 && n_query > 0 && T >= 0, "qformer_embed_ln: bad shape (d=%d)", d);
-  const long long rows = static_cast<long long>(B) * (n_query + T);
-  launch_kernel(qformer_embed_ln_kernel, ceil_div(rows * 32, 256), 256, 0, ST(stream), query, n_query, input_ids, B, T, word_emb, vocab,
+  const long long items = n_query + static_cast<long long>(B) * T;
+  launch_kernel(qformer_embed_ln_kernel, ceil_div(items * 32, 256), 256, 0, ST(stream), query, n_query, input_ids, B, T, word_emb, vocab,
                                                                            pos_emb, gamma, beta, eps, d,
                                                                            reinterpret_cast<__nv_bfloat16*>(h_out));
   OPSG_CHECK_LAUNCH("qformer_embed_ln_kernel");
+  if (B > 1) {
+    const long long total = static_cast<long long>(B - 1) * n_query * (d / 8);
+    launch_kernel(qformer_broadcast_rows_kernel, ceil_div(total, 256), 256, 0, ST(stream),
+                  reinterpret_cast<__nv_bfloat16*>(h_out), n_query, B, d);
+    OPSG_CHECK_LAUNCH("qformer_broadcast_rows_kernel");
+  }
   return OPSG_OK;
 }
 
@@ -590,7 +614,7 @@ extern "C" int opsg_exist_filter_topk(const opsg_bf16* x, int ld_x, int B, int d
       reinterpret_cast<const __nv_bfloat16*>(x), ld_x, B, d, w, b, logit_thr, logits_out, probs_out, mask_out);
   OPSG_CHECK_LAUNCH("exist_logits_kernel");
   if (k > 0) {
-    launch_kernel(topk_rank_kernel, ceil_div(B, 256), 256, 0, ST(stream), logits_out, B, k, topk_out);
+    launch_kernel(topk_rank_kernel, ceil_div(B, 32), 256, 0, ST(stream), logits_out, B, k, topk_out);
     OPSG_CHECK_LAUNCH("topk_rank_kernel");
   }
   return OPSG_OK;

@@ -218,7 +218,7 @@ def qformer_embed_ln(query, input_ids, word_emb, pos_emb, gamma, beta, eps, out=
     with _timed("qformer_embed_ln", 0.0, 2.0 * out.numel() + 4.0 * B * T * d):
         _lib.check(_lib.load().opsg_qformer_embed_ln(_ptr(query), nq, _ptr(input_ids), B, T, _ptr(word_emb), word_emb.shape[0],
                                                     _ptr(pos_emb), _ptr(gamma), _ptr(beta), float(eps), d, _ptr(out), _stream()))
-    _count()
+    _count(2 if B > 1 else 1)          # LN kernel + broadcast of the pair-independent query rows
     return out
 
 

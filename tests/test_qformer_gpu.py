@@ -140,7 +140,9 @@ def test_subset_of_pairs_equals_full_run(head):
 def test_graph_replay_and_forward_batch_equal_eager():
     """CUDA-graph replay (default) and the pipelined host-input batch entry give the same results as eager launches.
     (PatchEmbed's split-K uses fp32 atomics, so two runs agree to rounding, not bit-for-bit: a one-ulp flip of a bf16
-    activation in [2, 4) is already 0.016, hence max 6e-2 / mean 2e-3 on the output rows.)"""
+    activation in [2, 4) is already 0.016, hence max 6e-2 / mean 2e-3 on the output rows; a flipped CLS activation moves
+    a pair's existence logit by up to ~0.015 (seen in 2 of 4 repeated runs), hence 2e-2 there -- still inside the 3e-2
+    parity budget against the reference.)"""
     eager = build_product_head(device="cuda:0")
     eager.use_cuda_graphs = False
     graphed = build_product_head(device="cuda:0")
@@ -160,16 +162,16 @@ def test_graph_replay_and_forward_batch_equal_eager():
         o = graphed.last_output
         dh = (o.hidden.float().cpu() - h).abs()
         assert dh.max() < 6e-2 and dh.mean() < 2e-3, (dh.max(), dh.mean())
-        assert (o.logits.cpu() - z).abs().max() < 5e-3
-        assert torch.equal(o.exist_mask.cpu()[z.abs() > 1e-2], m[z.abs() > 1e-2])
+        assert (o.logits.cpu() - z).abs().max() < 2e-2
+        assert torch.equal(o.exist_mask.cpu()[z.abs() > 4e-2], m[z.abs() > 4e-2])
     assert len(graphed._graphs.entries) == 1
     # host-resident (pinned) inputs through the pipelined batch entry
     got = []
     res = graphed.forward_batch(host, on_result=lambda hd: got.append((hd.last_output.logits.cpu(), hd.last_output.topk.cpu().tolist())))
     assert len(res) == 3 and all(set(r) == {"rel_pred", "rel_score"} for r in res)
     for (z, top), (h, zr, topr, m) in zip(got, ref):
-        assert (z - zr).abs().max() < 5e-3
-        ok, diff = margin_set_equal(top, zr, 20, 5e-3)
+        assert (z - zr).abs().max() < 2e-2
+        ok, diff = margin_set_equal(top, zr, 20, 2e-2)
         assert ok, diff
 
 
