@@ -265,10 +265,14 @@ __global__ void __launch_bounds__(256) skinny_finalize_kernel(const FinalizePara
   const int row = static_cast<int>(idx / n4), col = static_cast<int>(idx % n4) * 4;
   const size_t slice_stride = static_cast<size_t>(p.M) * p.N;
   const float* src = p.ws + static_cast<size_t>(row) * p.N + col;
-  float4 a = *reinterpret_cast<const float4*>(src);
-  for (int s = 1; s < p.S; ++s) {
-    const float4 v = *reinterpret_cast<const float4*>(src + s * slice_stride);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < p.S; s0 += 8) {                    // eight slices in flight, added in slice order
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = (s0 + u < p.S) ? *reinterpret_cast<const float4*>(src + (s0 + u) * slice_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
   }
   float f[4] = {a.x, a.y, a.z, a.w};
   if (p.bias) {
@@ -295,11 +299,15 @@ __global__ void __launch_bounds__(256) skinny_finalize_kernel(const FinalizePara
   }
 }
 
-// K slicing for a problem: S slices of KS <= kMaxKS K-blocks, every slice non-empty
-static void slicing(int K, int* S, int* KS) {
+// K slicing for a problem: S slices of KS <= kMaxKS K-blocks, every slice non-empty.  When K is so long that the
+// slices alone outnumber half the SMs (PatchEmbed: K = 65536 -> 1024 K-blocks) every SM gets one slice.
+static void slicing(int K, int sms, int* S, int* KS) {
   const int kb_total = (K + kBK - 1) / kBK;
-  int s = (kb_total + kMaxKS - 1) / kMaxKS;
-  const int ks = (kb_total + s - 1) / s;
+  int ks = kMaxKS;
+  if ((kb_total + kMaxKS - 1) / kMaxKS > sms / 2) ks = (kb_total + sms - 1) / sms;
+  if (ks > kMaxKS) ks = kMaxKS;                            // more slices than SMs: several waves of CTAs would be needed
+  int s = (kb_total + ks - 1) / ks;
+  ks = (kb_total + s - 1) / s;
   s = (kb_total + ks - 1) / ks;
   *S = s;
   *KS = ks;
@@ -309,7 +317,9 @@ static void slicing(int K, int* S, int* KS) {
 
 size_t gemm_skinny_workspace_bytes(int N, int K) {      // for any M <= 128
   int S, KS;
-  sk::slicing(K, &S, &KS);
+  int sms = opsg_num_sms();
+  if (sms <= 0) sms = 148;
+  sk::slicing(K, sms, &S, &KS);
   return static_cast<size_t>(S) * 128 * ((N + 3) / 4 * 4) * sizeof(float);
 }
 
@@ -323,9 +333,9 @@ int launch_gemm_skinny(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw,
       (residual && (reinterpret_cast<uintptr_t>(residual) & 7) != 0))
     return OPSG_E_UNSUPPORTED;
   Params p;
-  slicing(K, &p.S, &p.KS);
-  p.MR = (M + 7) / 8 * 8;
   const int sms = opsg_num_sms();
+  slicing(K, sms, &p.S, &p.KS);
+  p.MR = (M + 7) / 8 * 8;
   if (p.S > sms) return OPSG_E_UNSUPPORTED;
   p.M = M; p.N = N; p.K = K;
   p.n_tiles = (N + kBN - 1) / kBN;

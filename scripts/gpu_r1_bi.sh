@@ -1,0 +1,4 @@
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for v in 1 0; do OPSG_PATCH_ATOMICS=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-llm --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('atomics',$v,'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'], {k:round(v,3) for k,v in d['kernel_ms_per_step'].items()})"; done

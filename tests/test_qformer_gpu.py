@@ -175,6 +175,27 @@ def test_graph_replay_and_forward_batch_equal_eager():
         assert ok, diff
 
 
+def test_deterministic_patch_embed_is_bit_reproducible(monkeypatch):
+    """OPSG_PATCH_DETERMINISTIC=1 routes PatchEmbed through the K-sliced GEMM (no atomics): two runs of the whole
+    relation-query path are bit-identical, and they agree with the default (split-K atomics) path to rounding."""
+    monkeypatch.setenv("OPSG_PATCH_DETERMINISTIC", "1")
+    det = build_product_head(device="cuda:0")
+    det.use_cuda_graphs = False
+    inputs = synth.inputs_to(_inputs("cfg1"), "cuda:0")
+    det(inputs)
+    a = det.last_output
+    tok_a, hid_a, z_a = a.image_tokens.clone(), a.hidden.clone(), a.logits.clone()
+    det(inputs)
+    b = det.last_output
+    assert torch.equal(b.image_tokens, tok_a) and torch.equal(b.hidden, hid_a) and torch.equal(b.logits, z_a)
+    monkeypatch.setenv("OPSG_PATCH_DETERMINISTIC", "0")
+    ref = build_product_head(device="cuda:0")
+    ref.use_cuda_graphs = False
+    ref(inputs)
+    assert (ref.last_output.image_tokens.float() - tok_a.float()).abs().max() < 2e-2
+    assert (ref.last_output.logits - z_a).abs().max() < 2e-2
+
+
 def test_relation_queries_80_objects_subset_vs_oracle(head):
     """cfg5's image shape (80 objects, 6400 pair queries): the full run must agree with the fp32 oracle on a sample of
     pairs (the oracle evaluates only the sampled pairs through its pair_index argument)."""
