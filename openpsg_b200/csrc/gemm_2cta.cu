@@ -45,6 +45,7 @@ struct Params {
   int res_tma;                // residual rows are 16-byte aligned: the slab warp loads them with TMA
   int bias_along_m;
   int bias_mma;               // the per-column bias is added by the tensor core (one extra K = 16 step per tile)
+  int gelu_tanh;              // GELU through tanh.approx (gelu_tanh_fast) instead of the ex2 form (gelu_erf_fast)
   int act;
   int m2_tiles, n_tiles;
   // ---- LayerNorm folding (all optional; see opsg_gemm_bf16_ln in include/opsg_b200.h) ----
@@ -501,8 +502,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (col_ok) {
           if (p.act == OPSG_ACT_GELU) {
+            if (p.gelu_tanh) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) f[j] = gelu_erf_fast(f[j]);
+              for (int j = 0; j < CW; ++j) f[j] = gelu_tanh_fast(f[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) f[j] = gelu_erf_fast(f[j]);
+            }
           } else if (p.act == OPSG_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -604,6 +610,8 @@ int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, o
   p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.M = M; p.N = N; p.K = K; p.ldr = ldr; p.bias_along_m = bias_along_m; p.act = act; p.res_tma = res_tma ? 1 : 0;
   static const int bias_mma_on = [] { const char* e = getenv("OPSG_GEMM2_BIAS_MMA"); return e ? atoi(e) : 1; }();
+  static const int gelu_tanh_on = [] { const char* e = getenv("OPSG_GELU_TANH"); return e ? atoi(e) : 0; }();
+  p.gelu_tanh = gelu_tanh_on;
   p.bias_mma = (bias && !bias_along_m && !(ln && ln->a_stats) && bias_mma_on) ? 1 : 0;
   p.m2_tiles = m2_tiles; p.n_tiles = n_tiles;
   p.a_stats = nullptr; p.a_colsum = nullptr; p.r_stats = nullptr; p.r_gamma = nullptr; p.r_beta = nullptr;
