@@ -347,7 +347,12 @@ class RelationQueryTransformer:
             vt = torch.zeros((d, Lp), dtype=torch.bfloat16, device=dev)
             ops.gemm(lw["w_cv"], X, lw["b_cv"], bias_along_m=True, out=vt[:, :L])
             # ---- self-attention block ----
-            if h_st is None:
+            qkv_q = None
+            if h_st is None and self.share_query_rows and T > 0:
+                qkv_q = ops.gemm(h[:N_QUERY], lw["w_qkv"], lw["b_qkv"])          # layer 0: query rows projected once
+                qkv = torch.empty((h.shape[0], 3 * d), dtype=torch.bfloat16, device=dev)
+                ops.gemm(h[RQ:], lw["w_qkv"], lw["b_qkv"], out=qkv[RQ:])
+            elif h_st is None:
                 qkv = ops.gemm(h, lw["w_qkv"], lw["b_qkv"])
             else:
                 qkv = torch.empty((h.shape[0], 3 * d), dtype=torch.bfloat16, device=dev)
@@ -356,7 +361,8 @@ class RelationQueryTransformer:
                 if h.shape[0] > RQ:
                     Wt, ct_, bt_ = lw["f_qkv_t"]
                     ops.gemm_ln(h[RQ:], Wt, bt_, a_stats=h_st[RQ:], a_colsum=ct_, out=qkv[RQ:], eps=LN_EPS)
-            ctx = ops.self_attn_small(qkv, text_mask, B, N_QUERY, T, NUM_HEADS, HEAD_DIM, text_queries=not last)
+            ctx = ops.self_attn_small(qkv, text_mask, B, N_QUERY, T, NUM_HEADS, HEAD_DIM, text_queries=not last,
+                                      shared_query_qkv=qkv_q)
             rows = ctx.shape[0]
             pre1 = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
             st1 = zeros_stats(rows)
