@@ -10,9 +10,10 @@ PER RANK (weak scaling; 4 per rank = BASELINE cfg4's 32 images over 8 GPUs), eve
 (1024x1024, 40 objects, 1600 queries = 1560 ordered pairs, 256 image tokens).  Images are independent, so ranks
 share nothing on the data path; NCCL is used for the barrier and the max-over-ranks time only.
 
-value  : whole-job ordered pairs / s with inputs resident in HBM (device-timed, CUDA events, max over ranks).
-e2e    : same through the head's public forward(inputs) with HOST (pinned) inputs: H2D of features, panoptic map
-         and ids, D2H of the selected pair list inside the timed region.
+value  : whole-job ordered pairs / s with inputs resident in HBM: the K steps' images through one head.forward_batch
+         call (device-timed, CUDA events, max over ranks); ms_per_step_separate_calls = one head(inputs) call per image.
+e2e    : same call with HOST (pinned) inputs: H2D of every image's features, panoptic map and ids and D2H of the selected
+         pair lists inside the timed region (timed twice, both passes reported; coarser call patterns beside it).
 roofline / roofline_xattn: dominant kernel (tcgen05 GEMM) and the north-star cross-attention kernel, CUDA-event
          timed per launch during the timed steps.
 cpu_baseline / --impl reference: oracle/ref_port.py (the reference's call pattern on HF modules) on host cores.
@@ -143,10 +144,10 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
-# DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_ncu_gemm_c.md: mean of the eight
-# layer-0 GEMM launches of one cfg2 image; profiles/r1_ncu_xattn_k.md is the N=80 launch, the N=40 launch of
-# profiles/r1_ncu_xattn_h.md moved 129 MB) — per launch, like `achieved`.
-NCU_TRAFFIC_BYTES = {"gemm_bf16": 287e6, "xattn_pairs": 129e6}
+# DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_ncu_gemm_final2.md: mean of
+# dram read + write over the eight layer-0 GEMM launches of one cfg2 image = 290 MB; profiles/r1_ncu_xattn_final2.md:
+# the N=40 cross-attention launch, 94 MB read + 42 MB written) — per launch, like `achieved`.
+NCU_TRAFFIC_BYTES = {"gemm_bf16": 290e6, "xattn_pairs": 136e6}
 
 
 def _llm_leg(dev, head, hidden, steps):
