@@ -173,6 +173,13 @@ def test_graph_replay_and_forward_batch_equal_eager():
         assert (z - zr).abs().max() < 2e-2
         ok, diff = margin_set_equal(top, zr, 20, 2e-2)
         assert ok, diff
+    # device-resident inputs through the same entry (object ids are read back on the copy stream)
+    got_dev = []
+    graphed.forward_batch([synth.inputs_to(inp, "cuda:0") for inp in host],
+                          on_result=lambda hd: got_dev.append(hd.last_output.logits.cpu()))
+    assert len(got_dev) == 3
+    for z, (h, zr, topr, m) in zip(got_dev, ref):
+        assert (z - zr).abs().max() < 2e-2
 
 
 def test_deterministic_patch_embed_is_bit_reproducible(monkeypatch):
