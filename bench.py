@@ -145,7 +145,7 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
 # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_ncu_gemm_final2.md: mean of
-# dram read + write over the eight layer-0 GEMM launches of one cfg2 image = 290 MB; profiles/r1_ncu_xattn_final2.md:
+# dram read + write over the eight layer-0 GEMM launches of one cfg2 image = 290 MB; profiles/r1_ncu_xattn_final3.md:
 # the N=40 cross-attention launch, 94 MB read + 42 MB written) — per launch, like `achieved`.
 NCU_TRAFFIC_BYTES = {"gemm_bf16": 290e6, "xattn_pairs": 136e6}
 

@@ -265,14 +265,18 @@ __global__ void __launch_bounds__(256) skinny_finalize_kernel(const FinalizePara
   const int row = static_cast<int>(idx / n4), col = static_cast<int>(idx % n4) * 4;
   const size_t slice_stride = static_cast<size_t>(p.M) * p.N;
   const float* src = p.ws + static_cast<size_t>(row) * p.N + col;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s0 = 0; s0 < p.S; s0 += 8) {                    // eight slices in flight, added in slice order
+  float4 a = *reinterpret_cast<const float4*>(src);
+  int s0 = 1;
+  for (; s0 + 8 <= p.S; s0 += 8) {                         // many slices (long K): eight in flight, added in slice order
     float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      v[u] = (s0 + u < p.S) ? *reinterpret_cast<const float4*>(src + (s0 + u) * slice_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(src + (s0 + u) * slice_stride);
 #pragma unroll
     for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
+  for (; s0 < p.S; ++s0) {
+    const float4 v = *reinterpret_cast<const float4*>(src + s0 * slice_stride);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
   }
   float f[4] = {a.x, a.y, a.z, a.w};
   if (p.bias) {
