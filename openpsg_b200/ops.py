@@ -123,7 +123,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if residual is not None:
         _cuda(residual, torch.bfloat16, "residual")
         assert residual.shape == (M, N) and residual.stride(1) == 1
-    with _timed("gemm_bf16", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)):
+    # profiling key: the large GEMMs (CTA-pair kernel, the dominant kernel of the step) apart from the small per-image ones
+    # (K3 projections of 256 image tokens, the 33 shared query rows, PatchEmbed's split-K)
+    key = "gemm_bf16" if 2.0 * M * N * K >= 2e9 and k_splits == 1 else "gemm_bf16_small"
+    with _timed(key, 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)):
         _lib.check(_lib.load().opsg_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
                                              _ptr(bias), int(bias_along_m), _ptr(residual),
                                              residual.stride(0) if residual is not None else 0, act, mode, k_splits, _stream()))
