@@ -6,12 +6,14 @@
 // (scripts/ubench/mma_cost.cu, profiles/r1_ubench.md) — a 75 % ceiling for every cta_group::1 GEMM.  In a pair each CTA
 // supplies its own 128 rows of A and only HALF of the W^T tile (128 of the 256 N rows): 8 KB per 128-cycle step.
 //
-// Roles per CTA (384 threads), same as gemm.cu:
+// Roles per CTA (128 + 32 x EPIW threads; EPIW = 8 epilogue warps by default):
 //   warp 0  TMA producer : own A tile [128 x 64] + own half of W^T [128 x 64] per stage (32 KB), completion bytes of BOTH
 //                          CTAs are signalled on the LEADER's full barrier (cta rank 0; peer bit of the address cleared)
 //   warp 1  MMA issuer   : leader only — tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16), accumulator rows 0-127 in
 //                          the leader's TMEM, rows 128-255 in the peer's; tcgen05.commit multicasts to both CTAs' barriers
-//   warp 2  TMEM allocator (tcgen05.alloc.cta_group::2, both CTAs)
+//   warp 2  TMEM allocator (tcgen05.alloc.cta_group::2, both CTAs), then builder of the bias operand: per tile it writes
+//                          (bias_hi, bias_lo) of its CTA's 128 columns into a [128 x 16] no-swizzle tile; the leader's MMA warp
+//                          adds the bias with one more K = 16 step against a ones operand
 //   warp 3  slab warp    : ring of [128 x 64] staging slabs: TMA-loads the residual slab, TMA-stores the packed result
 //   warps 4-11 epilogue  : own 128 rows: tcgen05.ld -> LayerNorm fold / bias / residual / activation -> bf16 -> swizzled
 //                          smem; column vectors of the next tile are prefetched into shared memory; the accumulator stage
