@@ -149,9 +149,11 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16
                                                              const float* __restrict__ beta, float eps,
                                                              __nv_bfloat16* __restrict__ y, int rows, int cols) {
   pdl_wait_then_trigger();
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // Rows are walked from the END of the tensor: the producer (a GEMM epilogue) wrote them in ascending order, so the last
+  // ~100 MB are still in L2 when this kernel starts; reading those first saves their HBM round trip.
+  const int row = rows - 1 - static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  if (row < 0) return;
   const __nv_bfloat16* xr = x + static_cast<size_t>(row) * cols;
   float v[CHUNKS][8];
 #pragma unroll
