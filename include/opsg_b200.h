@@ -114,7 +114,7 @@ int opsg_qformer_embed_ln(const float* query, int n_query, const int32_t* input_
                           const float* word_emb, int vocab, const float* pos_emb, const float* gamma,
                           const float* beta, float eps, int d, opsg_bf16* h_out, void* stream);
 
-/* y = LayerNorm(x) * gamma + beta over the last dim; x,y bf16 [rows, cols] (same ld = cols). */
+/* y = LayerNorm(x) * gamma + beta over the last dim; x,y bf16 [rows, cols] (same ld = cols); cols % 8 == 0, <= 8192. */
 int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const float* beta, float eps, opsg_bf16* y,
                         int rows, int cols, void* stream);
 
@@ -176,7 +176,8 @@ int opsg_mask_pool_pairs(const float* feat, int channels, int h, int w, const in
  * opsg_embed_gather: out[r] = table[ids[r]] (+ pos_table[pos[r]] if given), bf16 out (v4:296; OPT :64-70).
  * opsg_llm_attn: causal multi-head attention over a static KV cache; q bf16 [nseq*q_len, H*hd],
  *   k/v cache bf16 [nseq, max_ctx, H*hd]; key_mask uint8 [nseq, max_ctx] (0 = padded key); query t of a
- *   sequence sits at absolute position q_pos0 + t and sees keys <= its position (HF OPT :75-101).
+ *   sequence sits at absolute position q_pos0 + t and sees keys <= its position (HF OPT :75-101); q_pos0 + q_len <= 256,
+ *   head_dim 64, 80 or 128.
  * opsg_argmax_rows: greedy token = argmax over fp32 logits rows (ties -> lower index). */
 int opsg_gather_rows_bf16(const opsg_bf16* src, int row_elems, const int32_t* idx, int n_rows, opsg_bf16* out,
                           void* stream);
@@ -196,13 +197,45 @@ int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_cache, const 
                   opsg_bf16* out, int ld_out, void* stream);
 /* Decode step (one new token per sequence at position q_pos0): qkv bf16 [nseq, ld_qkv] holds the fused [q | k | v]
  * projection of the new tokens; the kernel attends over cache keys < q_pos0 plus the new key and WRITES the new k / v
- * rows into the caches at position q_pos0 (opsg_kv_append + opsg_llm_attn in one launch).  q_pos0 + 1 <= 128. */
+ * rows into the caches at position q_pos0 (opsg_kv_append + opsg_llm_attn in one launch).  q_pos0 + 1 <= 256. */
 int opsg_llm_attn_append(const opsg_bf16* qkv, int ld_qkv, opsg_bf16* k_cache, opsg_bf16* v_cache, int max_ctx,
                          const uint8_t* key_mask, int nseq, int q_pos0, int num_heads, int head_dim, float scale,
                          opsg_bf16* out, int ld_out, void* stream);
 int opsg_kv_append(const opsg_bf16* qkv, int ld_qkv, int nseq, int q_len, int pos0, int d_model, opsg_bf16* k_cache,
                    opsg_bf16* v_cache, int max_ctx, void* stream);
 int opsg_argmax_rows(const float* logits, int ld, int rows, int cols, int32_t* out, void* stream);
+
+/* ---- a10 / K10 for Llama-family decoders (the LLM configs/psg/baseline_v4_ov.py:60-61 names; v4:99-105) ------------
+ * opsg_rmsnorm_bf16: y = weight * (x * rsqrt(mean(x^2) + eps)) over the last dim (HF modeling_llama.py:52-69, statistics
+ *   in fp32); x, y bf16 [rows, cols] with leading dims ld_x / ld_y; cols % 8 == 0, cols <= 8192.
+ * opsg_rope_bf16: rotary position embedding, HF rotate_half convention (modeling_llama.py:137-166), applied IN PLACE to
+ *   the first n_parts column blocks of num_heads * head_dim elements of every row of x (bf16 [rows, ld]; n_parts = 2 for
+ *   the q | k part of a fused q | k | v projection).  Row r uses position pos[r] (HF generate: cumsum(attention_mask) - 1);
+ *   cos_table / sin_table fp32 [table_rows, head_dim / 2] hold cos / sin(pos * theta^(-2e / head_dim)) as
+ *   LlamaRotaryEmbedding computes them (:120-135).  head_dim % 16 == 0.
+ * opsg_swiglu_bf16: out[r, c] = silu(gate_up[r, c]) * gate_up[r, ffn + c] (modeling_llama.py:181-183 with gate_proj and
+ *   up_proj fused into one [2 * ffn, d] projection); gate_up bf16 [rows, ld_gu >= 2 * ffn], out bf16 [rows, ld_out]. */
+int opsg_rmsnorm_bf16(const opsg_bf16* x, int ld_x, const float* weight, float eps, opsg_bf16* y, int ld_y, int rows,
+                      int cols, void* stream);
+int opsg_rope_bf16(opsg_bf16* x, int ld, int rows, int n_parts, int num_heads, int head_dim, const int32_t* pos,
+                   const float* cos_table, const float* sin_table, int table_rows, void* stream);
+int opsg_swiglu_bf16(const opsg_bf16* gate_up, int ld_gu, int rows, int ffn, opsg_bf16* out, int ld_out, void* stream);
+
+/* ---- a9 / a10 bookkeeping that the reference leaves to torch / HF generate ------------------------------------------
+ * opsg_llm_prompt_layout: positions and key mask of the batched prompt [n_prefix projected rows ; left-padded text]
+ *   (v4:294-301): with m = [1 x n_prefix ; text_mask] and c = cumsum(m), pos_out int32 [nseq, n_prefix + T] =
+ *   m ? c - 1 + pos_offset : max(pos_offset - 1, 0)  (pos_offset 2 = OPT learned positions, HF opt :64-70; 0 = rotary
+ *   positions as HF generate derives them, generation/utils.py:707-729); key_mask_out uint8 [nseq, n_prefix + T +
+ *   max_new_tokens] (generated positions 1); last_rows_out int32 [nseq] = row of the last prompt token in the
+ *   [nseq * (n_prefix + T)] row stack; dec_pos_out int32 [max_new_tokens - 1, nseq] = position of the token fed at
+ *   decode step j + 1.
+ * opsg_copy_bytes: dst = src, device to device, as a kernel (CUDA-graph input staging off the copy engines).
+ * opsg_transpose_i32: dst[c, r] = src[r, c]. */
+int opsg_llm_prompt_layout(const int32_t* text_mask, int nseq, int T, int n_prefix, int max_new_tokens, int pos_offset,
+                           int32_t* pos_out, uint8_t* key_mask_out, int32_t* last_rows_out, int32_t* dec_pos_out,
+                           void* stream);
+int opsg_copy_bytes(void* dst, const void* src, size_t nbytes, void* stream);
+int opsg_transpose_i32(const int32_t* src, int rows, int cols, int32_t* dst, void* stream);
 
 #ifdef __cplusplus
 }

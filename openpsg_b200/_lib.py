@@ -47,6 +47,12 @@ SIGNATURES = {
     "opsg_llm_attn_append": [P, I, P, P, I, P, I, I, I, I, F, P, I, P],
     "opsg_kv_append": [P, I, I, I, I, I, P, P, I, P],
     "opsg_argmax_rows": [P, I, I, I, P, P],
+    "opsg_rmsnorm_bf16": [P, I, P, F, P, I, I, I, P],
+    "opsg_rope_bf16": [P, I, I, I, I, I, P, P, P, I, P],
+    "opsg_swiglu_bf16": [P, I, I, I, P, I, P],
+    "opsg_llm_prompt_layout": [P, I, I, I, I, I, P, P, P, P, P],
+    "opsg_copy_bytes": [P, P, ctypes.c_size_t, P],
+    "opsg_transpose_i32": [P, I, I, P, P],
 }
 
 

@@ -1,5 +1,5 @@
 // K4 / K10a / K10b — small-sequence multi-head attention (Q-Former self-attention over S = 33 + T <= 64 rows per
-// pair; OPT prefill / decode attention over a static KV cache, context <= 128).
+// pair; OPT / Llama prefill / decode attention over a static KV cache, context <= 256).
 //
 // These problems are tiny and independent (B * heads of them, <= 64 x 128 scores each): one CTA per
 // (sequence, head), whole K / V / Q tile in shared memory (row-major, 16-byte copies; the PV B fragments come
@@ -416,7 +416,8 @@ template <int HD>
 static int dispatch_nk(const SmallAttnParams& p, int nseq, int n_keys, cudaStream_t st) {
   if (n_keys <= 64) return launch_small_attn<HD, 64>(p, nseq, st);
   if (n_keys <= 128) return launch_small_attn<HD, 128>(p, nseq, st);
-  return set_error(OPSG_E_UNSUPPORTED, "small attention: %d keys > 128 unsupported", n_keys);
+  if (n_keys <= 256) return launch_small_attn<HD, 256>(p, nseq, st);
+  return set_error(OPSG_E_UNSUPPORTED, "small attention: %d keys > 256 unsupported", n_keys);
 }
 
 static int dispatch_hd(const SmallAttnParams& p, int nseq, int n_keys, int head_dim, cudaStream_t st) {
@@ -439,7 +440,7 @@ template <int HD>
 __global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams p) {
   pdl_wait_then_trigger();
   constexpr int kWarps = 8;
-  constexpr int kMaxCtx = 128;
+  constexpr int kMaxCtx = 256;
   constexpr int LPK = (HD / 8 <= 8) ? 8 : 16;              // lanes per key (power of two >= HD / 8)
   constexpr int KPW = 32 / LPK;                             // keys per warp iteration
   constexpr int CH = 16;                                    // iterations whose loads are issued back to back
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams 
 // warp, no registers held), computes the scores lane-per-key from shared memory while V is still landing, then the
 // context lane-per-dimension-pair.  Rows are padded by 16 bytes so that lane-per-key 16-byte reads are conflict-free.
 // ------------------------------------------------------------------------------------------------
-template <int HD>
+template <int HD, int R>
 __global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnParams p, int warps_per_cta) {
   pdl_wait_then_trigger();
   extern __shared__ __align__(16) uint8_t smem_dyn[];
@@ -590,10 +591,10 @@ __global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnPa
   // ---- scores: lane-per-key ----------------------------------------------------------------------------
   cp_async_wait<1>();
   __syncwarp();
-  float sc[4];                                              // ctx <= 128 (host-checked)
+  float sc[R];                                              // ctx <= 32 * R (host-checked)
   float mx = -INFINITY;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < R; ++r) {
     const int key = r * 32 + lane;
     float d = -INFINITY;
     if (key < ctx && __ldg(kmask + key) != 0) {
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnPa
   if (mx == -INFINITY) mx = 0.f;
   float sum = 0.f;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < R; ++r) {
     const float e = ex2f((sc[r] - mx) * p.scale_log2e);     // exp2(-inf) = 0 for masked / out-of-range keys
     // P is rounded to bf16 like the tensor-core path (and HF's bf16 softmax output) before multiplying V
     if (r * 32 + lane < ctx_pad) sP[r * 32 + lane] = __bfloat162float(__float2bfloat16(e));
@@ -666,17 +667,25 @@ static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
   static const int use_smem = [] { const char* e = getenv("OPSG_DECODE_ATTN_SMEM"); return e ? atoi(e) : 1; }();
   const int ctx = p.q_pos0 + 1;
   const int per_warp = ((2 * ctx * (HD * 2 + 16) + HD * 2 + ((ctx + 31) & ~31) * 4) + 15) & ~15;
-  if (use_smem && ctx <= 128 && per_warp <= 110 * 1024) {
-    int wpc = (110 * 1024) / per_warp;                     // two or more CTAs per SM
+  // contexts <= 128 keys: 110 KB of shared memory per CTA (two CTAs per SM); up to 256 keys: one CTA per SM
+  const int budget = ctx <= 128 ? 110 * 1024 : 220 * 1024;
+  if (use_smem && ctx <= 256 && per_warp <= budget) {
+    int wpc = budget / per_warp;
     if (wpc > 4) wpc = 4;
     static bool configured = false;
     if (!configured) {
-      int rc = check_cuda(cudaFuncSetAttribute(decode_attn_smem_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
+      int rc = check_cuda(cudaFuncSetAttribute(decode_attn_smem_kernel<HD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
                           "cudaFuncSetAttribute(decode_attn_smem)");
+      if (rc) return rc;
+      rc = check_cuda(cudaFuncSetAttribute(decode_attn_smem_kernel<HD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+                      "cudaFuncSetAttribute(decode_attn_smem)");
       if (rc) return rc;
       configured = true;
     }
-    launch_kernel(decode_attn_smem_kernel<HD>, (p.B + wpc - 1) / wpc, 128, static_cast<size_t>(wpc) * per_warp, st, p, wpc);
+    if (ctx <= 128)
+      launch_kernel(decode_attn_smem_kernel<HD, 4>, (p.B + wpc - 1) / wpc, 128, static_cast<size_t>(wpc) * per_warp, st, p, wpc);
+    else
+      launch_kernel(decode_attn_smem_kernel<HD, 8>, (p.B + wpc - 1) / wpc, 128, static_cast<size_t>(wpc) * per_warp, st, p, wpc);
     OPSG_CHECK_LAUNCH("decode_attn_smem_kernel");
     return OPSG_OK;
   }
@@ -765,7 +774,7 @@ extern "C" int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_ca
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ld_out = ld_out; p.num_heads = num_heads; p.d_model = num_heads * head_dim;
   p.scale_log2e = 1.4426950408889634f * scale;
-  if (q_len == 1 && q_pos0 + 1 <= 128 && (head_dim == 64 || head_dim == 80 || head_dim == 128) && (ld_q % 8) == 0 &&
+  if (q_len == 1 && q_pos0 + 1 <= 256 && (head_dim == 64 || head_dim == 80 || head_dim == 128) && (ld_q % 8) == 0 &&
       (ld_out % 8) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)q & 15) == 0) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);     // decode step: GEMV-style kernel, one warp per (seq, head)
     if (head_dim == 64) return launch_decode_attn<64>(p, nseq, st);
@@ -781,7 +790,7 @@ extern "C" int opsg_llm_attn_append(const opsg_bf16* qkv, int ld_qkv, opsg_bf16*
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(qkv && k_cache && v_cache && key_mask && out, "llm_attn_append: null pointer");
-  OPSG_CHECK_ARG(nseq > 0 && q_pos0 >= 0 && q_pos0 < max_ctx && q_pos0 + 1 <= 128, "llm_attn_append: bad shape");
+  OPSG_CHECK_ARG(nseq > 0 && q_pos0 >= 0 && q_pos0 < max_ctx && q_pos0 + 1 <= 256, "llm_attn_append: bad shape");
   OPSG_CHECK_ARG(head_dim == 64 || head_dim == 80 || head_dim == 128, "llm_attn_append: head_dim %d unsupported", head_dim);
   OPSG_CHECK_ARG(ld_qkv >= 3 * num_heads * head_dim && (ld_qkv % 8) == 0 && (ld_out % 8) == 0 &&
                  (((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)k_cache | (uintptr_t)v_cache) & 15) == 0,

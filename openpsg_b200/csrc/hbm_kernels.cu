@@ -522,6 +522,7 @@ extern "C" int opsg_qformer_embed_ln(const float* query, int n_query, const int3
 
 // Few rows (LLM decode: 100 rows of 2560): one CTA per row instead of one warp per row -- 256 threads issue the row's
 // loads (x, gamma, beta) at once, so the kernel is one memory round trip deep instead of ten chunks per lane.
+template <int CH>                                         // CH x 256 x 8 columns max
 __global__ void __launch_bounds__(256) layernorm_row_cta_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float eps,
                                                                 __nv_bfloat16* __restrict__ y, int cols) {
@@ -529,7 +530,6 @@ __global__ void __launch_bounds__(256) layernorm_row_cta_kernel(const __nv_bfloa
   __shared__ float red[2][8];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const __nv_bfloat16* xr = x + static_cast<size_t>(blockIdx.x) * cols;
-  constexpr int CH = 2;                                   // 2 x 256 x 8 = 4096 columns max
   float v[CH][8], g[CH][8], b[CH][8];
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
@@ -590,12 +590,14 @@ extern "C" int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(x && gamma && beta && y, "layernorm: null pointer");
-  OPSG_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 256 * kMaxChunks, "layernorm: cols=%d unsupported", cols);
+  OPSG_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 8192, "layernorm: cols=%d unsupported (multiple of 8, <= 8192)", cols);
   const int grid = ceil_div(static_cast<long long>(rows) * 32, 256);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
-  if (rows <= 512 && cols >= 1024)
-    launch_kernel(layernorm_row_cta_kernel, rows, 256, 0, ST(stream), xp, gamma, beta, eps, yp, cols);
+  if (cols > 4096)
+    launch_kernel(layernorm_row_cta_kernel<4>, rows, 256, 0, ST(stream), xp, gamma, beta, eps, yp, cols);
+  else if ((rows <= 512 && cols >= 1024) || cols > 256 * kMaxChunks)
+    launch_kernel(layernorm_row_cta_kernel<2>, rows, 256, 0, ST(stream), xp, gamma, beta, eps, yp, cols);
   else if (cols <= 1024) launch_kernel(layernorm_bf16_kernel<4>, grid, 256, 0, ST(stream), xp, gamma, beta, eps, yp, rows, cols);
   else launch_kernel(layernorm_bf16_kernel<kMaxChunks>, grid, 256, 0, ST(stream), xp, gamma, beta, eps, yp, rows, cols);
   OPSG_CHECK_LAUNCH("layernorm_bf16_kernel");

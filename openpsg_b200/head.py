@@ -167,9 +167,13 @@ class RelationTransformerHeadV4(BaseModule):
             language_model = AutoModelForCausalLM.from_pretrained(
                 llm_model_name, low_cpu_mem_usage=True, trust_remote_code=True)
         if language_model is not False:
+            from .llm import check_llm_supported
+            check_llm_supported(language_model.config)        # fail at construction, not at the first forward
             self.language_model = language_model
-            if self.llm_truncate_num > 0:
-                self.language_model.model.layers = self.language_model.model.layers[:self.llm_truncate_num]
+            if self.llm_truncate_num > 0:                     # v4:101-103 (Llama layout); OPT keeps its layers one level down
+                inner = self.language_model.model
+                holder = inner if hasattr(inner, "layers") else inner.decoder
+                holder.layers = holder.layers[:self.llm_truncate_num]
         else:
             self.language_model = None                       # opt-out: relation queries + filter only
         if llm_tokenizer is None and self.language_model is not None:
@@ -182,6 +186,7 @@ class RelationTransformerHeadV4(BaseModule):
         self._packed: Optional[PackedQFormer] = None
         self._engine: Optional[RelationQueryTransformer] = None
         self._llm_engine = None
+        self._graphs = None
         self._qformer_cache = PairInstructionCache(self.relation_qformer_tokenizer, qformer_instruction,
                                                    object_categories, "right")
         self._llm_cache = (PairInstructionCache(self.llm_tokenizer, llm_instruction, object_categories, "left")
@@ -195,6 +200,10 @@ class RelationTransformerHeadV4(BaseModule):
         if torch.device(device).type != "cuda":
             raise RuntimeError("RelationTransformerHeadV4 (openpsg_b200) runs on CUDA (sm_100a) only; "
                                "there is no CPU fallback — move the head to a B200 with .cuda()")
+        if 'binary' not in self.rel_cls_type:
+            raise NotImplementedError(
+                f"rel_cls_type={self.rel_cls_type!r}: inference needs the binary existence classifier (the reference's "
+                "multiclass-only test branch reads an undefined selected_idxes, v4:261)")
         sd = {k: v for k, v in self.state_dict().items() if not k.startswith("language_model.")}
         self._packed = PackedQFormer(sd, device, num_layers=self.qformer_layer_num, patch=self.patch_size)
         self._engine = RelationQueryTransformer(self._packed)
@@ -206,9 +215,21 @@ class RelationTransformerHeadV4(BaseModule):
                                                 use_cuda_graphs=self.use_cuda_graphs)
         return self
 
-    def _load_from_state_dict(self, *a, **k):   # weights changed -> drop the packed copy
+    def _drop_packed(self):
         self._packed = self._engine = self._llm_engine = self._graphs = None
+
+    def _load_from_state_dict(self, *a, **k):   # weights changed -> drop the packed copy
+        self._drop_packed()
         return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):              # .to() / .cuda() / .half(): the packed copy lives on the old device
+        self._drop_packed()
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode: bool = True):         # weights may be updated while training -> repack at the next eval forward
+        if mode:
+            self._drop_packed()
+        return super().train(mode)
 
     # ------------------------------------------------------------------------------------------------
     def forward(self, inputs, is_generation=None):
@@ -284,6 +305,8 @@ class RelationTransformerHeadV4(BaseModule):
         meta_info, object_info = inputs['img_metas'][0], inputs['object_info'][0]
         object_id_list = object_info['object_id_list'][:self.max_object_num]          # v4:136
         n = len(object_id_list)
+        if n == 0:                                                                      # nothing to pair (reference: torch.cat([]) raises)
+            return dict(n=0)
         ids_any = torch.stack([torch.as_tensor(x).reshape(()) for x in object_id_list])
         ids_host = ids_any.cpu().numpy().astype(np.int32)                               # one D2H (ref: N .item() calls)
         cats = (ids_host % INSTANCE_OFFSET).astype(np.int64)                            # v4:138
@@ -301,6 +324,9 @@ class RelationTransformerHeadV4(BaseModule):
 
     # -- stage 2: every input on the device (on the CURRENT stream) --------------------------------------------------
     def _to_device(self, prep, dev):
+        if prep["n"] == 0:
+            prep["device"] = {}
+            return prep
         want = dict(feat=torch.float32, pan=torch.int32, obj_ids=torch.int32, q_ids=torch.int32, q_mask=torch.int32)
         out = {}
         for name, t in prep["host"].items():
@@ -313,6 +339,9 @@ class RelationTransformerHeadV4(BaseModule):
     # -- stage 3: kernels ---------------------------------------------------------------------------------------------
     def _run(self, prep, is_generation):
         from . import ops as _ops
+        if prep["n"] == 0:
+            self.last_output = None
+            return {'rel_pred': [], 'rel_score': []}
         d = prep["device"]
         n, cats = prep["n"], prep["cats"]
         dev = self._packed.device

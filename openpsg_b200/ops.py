@@ -388,3 +388,95 @@ def argmax_rows(logits: torch.Tensor, out=None):
         _lib.check(_lib.load().opsg_argmax_rows(_ptr(logits), logits.stride(0), rows, cols, _ptr(out), _stream()))
     _count()
     return out
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out=None) -> torch.Tensor:
+    """Llama RMSNorm over the last dim; x bf16 [rows, cols] (row stride may exceed cols), weight fp32 [cols]."""
+    _cuda(x, torch.bfloat16, "x"); _cuda(weight, torch.float32, "weight")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    with _timed("rmsnorm_bf16", 0.0, 4.0 * rows * cols):
+        _lib.check(_lib.load().opsg_rmsnorm_bf16(_ptr(x), x.stride(0), _ptr(weight), float(eps), _ptr(out), out.stride(0),
+                                                rows, cols, _stream()))
+    _count()
+    return out
+
+
+def rope(x: torch.Tensor, n_parts: int, num_heads: int, head_dim: int, pos: torch.Tensor, cos_table: torch.Tensor,
+         sin_table: torch.Tensor) -> torch.Tensor:
+    """In-place rotary embedding of the first n_parts (q, k) column blocks of x bf16 [rows, ld]; pos int32 [rows]."""
+    _cuda(x, torch.bfloat16, "x"); _cuda(pos, torch.int32, "pos")
+    _cuda(cos_table, torch.float32, "cos_table"); _cuda(sin_table, torch.float32, "sin_table")
+    assert x.dim() == 2 and x.stride(1) == 1 and pos.numel() == x.shape[0] and pos.is_contiguous()
+    assert cos_table.is_contiguous() and sin_table.is_contiguous() and cos_table.shape == sin_table.shape == (cos_table.shape[0], head_dim // 2)
+    rows = x.shape[0]
+    with _timed("rope_bf16", 0.0, 4.0 * rows * n_parts * num_heads * head_dim):
+        _lib.check(_lib.load().opsg_rope_bf16(_ptr(x), x.stride(0), rows, n_parts, num_heads, head_dim, _ptr(pos), _ptr(cos_table),
+                                             _ptr(sin_table), cos_table.shape[0], _stream()))
+    _count()
+    return x
+
+
+def swiglu(gate_up: torch.Tensor, ffn: int, out=None) -> torch.Tensor:
+    """out = silu(gate_up[:, :ffn]) * gate_up[:, ffn:2*ffn]; bf16."""
+    _cuda(gate_up, torch.bfloat16, "gate_up")
+    assert gate_up.dim() == 2 and gate_up.stride(1) == 1 and gate_up.shape[1] >= 2 * ffn
+    rows = gate_up.shape[0]
+    if out is None:
+        out = torch.empty((rows, ffn), dtype=torch.bfloat16, device=gate_up.device)
+    with _timed("swiglu_bf16", 0.0, 6.0 * rows * ffn):
+        _lib.check(_lib.load().opsg_swiglu_bf16(_ptr(gate_up), gate_up.stride(0), rows, ffn, _ptr(out), out.stride(0), _stream()))
+    _count()
+    return out
+
+
+class PromptLayout:
+    __slots__ = ("pos", "key_mask", "last_rows", "dec_pos")
+
+
+def llm_prompt_layout(text_mask: torch.Tensor, n_prefix: int, max_new_tokens: int, pos_offset: int) -> PromptLayout:
+    """Positions / key mask / last-row indices / decode-step positions of the batched prompt (one kernel; see
+    include/opsg_b200.h).  text_mask int32 [k, T] (left-padded)."""
+    _cuda(text_mask, torch.int32, "text_mask")
+    assert text_mask.is_contiguous()
+    k, T = text_mask.shape
+    dev = text_mask.device
+    Tp = n_prefix + T
+    lay = PromptLayout()
+    lay.pos = torch.empty((k, Tp), dtype=torch.int32, device=dev)
+    lay.key_mask = torch.empty((k, Tp + max_new_tokens), dtype=torch.uint8, device=dev)
+    lay.last_rows = torch.empty((k,), dtype=torch.int32, device=dev)
+    lay.dec_pos = torch.empty((max(max_new_tokens - 1, 1), k), dtype=torch.int32, device=dev)
+    with _timed("llm_prompt_layout", 0.0, 4.0 * k * T + 5.0 * k * (Tp + max_new_tokens)):
+        _lib.check(_lib.load().opsg_llm_prompt_layout(_ptr(text_mask), k, T, n_prefix, max_new_tokens, pos_offset, _ptr(lay.pos),
+                                                     _ptr(lay.key_mask), _ptr(lay.last_rows), _ptr(lay.dec_pos), _stream()))
+    _count()
+    return lay
+
+
+def copy_into(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst <- src.  Device-resident sources of the same dtype / shape go through the library's copy KERNEL (a copy-engine
+    D2D copy would queue behind an in-flight host->device prefetch); anything else (host source, dtype conversion) is a
+    plain asynchronous ``copy_``."""
+    if src.is_cuda and src.device == dst.device and src.dtype == dst.dtype and src.shape == dst.shape \
+            and src.is_contiguous() and dst.is_contiguous():
+        if src.data_ptr() != dst.data_ptr():
+            nbytes = src.numel() * src.element_size()
+            with _timed("copy_bytes", 0.0, 2.0 * nbytes):
+                _lib.check(_lib.load().opsg_copy_bytes(_ptr(dst), _ptr(src), nbytes, _stream()))
+            _count()
+    else:
+        dst.copy_(src, non_blocking=True)
+    return dst
+
+
+def transpose_i32(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    _cuda(src, torch.int32, "src"); _cuda(dst, torch.int32, "dst")
+    rows, cols = src.shape
+    assert src.is_contiguous() and dst.is_contiguous() and dst.shape == (cols, rows)
+    with _timed("transpose_i32", 0.0, 8.0 * rows * cols):
+        _lib.check(_lib.load().opsg_transpose_i32(_ptr(src), rows, cols, _ptr(dst), _stream()))
+    _count()
+    return dst

@@ -21,6 +21,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
+from .graphs import GraphCache
 
 NUM_HEADS = 12
 HEAD_DIM = 64
@@ -125,6 +126,11 @@ class RelationQueryOutput:
     image_tokens: torch.Tensor      # bf16 [L, 256]
     intermediates: Optional[dict] = None
 
+    def clone(self) -> "RelationQueryOutput":
+        """Private copy of a result that lives in a CUDA graph's static buffers (overwritten by the next replay)."""
+        return RelationQueryOutput(**{f: (getattr(self, f).clone() if torch.is_tensor(getattr(self, f)) else getattr(self, f))
+                                      for f in self.__dataclass_fields__})
+
 
 class GraphedRelationQuery:
     """CUDA-graph replay of ``RelationQueryTransformer.forward`` per input-shape signature.
@@ -133,41 +139,39 @@ class GraphedRelationQuery:
     (measured 11 % of the step on cfg2) without touching the arithmetic.  Inputs are copied into static buffers
     (``copy_`` also performs the host->device transfer / dtype conversion when the caller's tensors live on the
     host), outputs are the static tensors of the captured run: they are overwritten by the next call with the same
-    signature, so callers that keep results across calls must clone them."""
+    signature, so callers that keep results across calls must clone them (``RelationQueryOutput.clone()``)."""
 
-    def __init__(self, engine: "RelationQueryTransformer", max_entries: int = 4):
+    def __init__(self, engine: "RelationQueryTransformer", max_entries: int = 4, capture_after: int = 2):
         self.engine = engine
-        self.max_entries = max_entries
-        self.entries: Dict[tuple, dict] = {}
+        self.cache = GraphCache(max_entries=max_entries, capture_after=capture_after)
+
+    @property
+    def entries(self):
+        return self.cache.entries
 
     def run(self, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, *, topk: int, threshold: float):
+        """A signature is replayed from its graph once it has been seen ``capture_after`` times; before that (and for
+        signatures that never repeat, the common case on real PSG images) it runs eagerly through the same kernels."""
         dev = self.engine.w.device
         key = (tuple(feat.shape), tuple(pan.shape), tuple(int(x) for x in img_hw), tuple(int(x) for x in pad_hw),
                int(obj_ids.numel()), tuple(input_ids.shape), int(topk), float(threshold))
-        e = self.entries.get(key)
+        e = self.cache.lookup(key)
         if e is None:
-            if len(self.entries) >= self.max_entries:          # drop the oldest signature (frees its private pool)
-                self.entries.pop(next(iter(self.entries)))
+            if not self.cache.should_capture(key):
+                return self.engine.forward(self._dev(feat, torch.float32, dev), self._dev(pan, torch.int32, dev), img_hw, pad_hw,
+                                           self._dev(obj_ids, torch.int32, dev), self._dev(input_ids, torch.int32, dev),
+                                           self._dev(text_mask, torch.int32, dev), topk=topk, threshold=threshold)
             e = self._capture(key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev)
-            self.entries[key] = e
+            self.cache.insert(key, e)
         for name, src in (("feat", feat), ("pan", pan), ("obj_ids", obj_ids), ("input_ids", input_ids), ("text_mask", text_mask)):
-            self._stage(e[name], src)
+            ops.copy_into(e[name], src)
         e["graph"].replay()
         ops._count(e["launches"])
         return e["out"]
 
     @staticmethod
-    def _stage(dst, src):
-        """Copy into a static graph input.  Device-resident sources of the same dtype go through an elementwise KERNEL
-        instead of cudaMemcpyAsync: a copy-engine D2D copy would queue behind an in-flight host->device prefetch of the
-        next image and serialise the pipeline of ``forward_batch``."""
-        if src.is_cuda and src.dtype == dst.dtype and src.shape == dst.shape:
-            if dst.is_floating_point():
-                torch.mul(src, 1.0, out=dst)
-            else:
-                torch.add(src, 0, out=dst)
-        else:
-            dst.copy_(src, non_blocking=True)
+    def _dev(t, dtype, dev):
+        return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
 
     def _capture(self, key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev):
         st = dict(
@@ -234,6 +238,13 @@ class RelationQueryTransformer:
         ops.gemm(a, w.patch_w, out=acc, atomic=True, k_splits=splits)
         return ops.cast_f32_bf16(acc)
 
+    @staticmethod
+    def _vt_buffer(d, L, Lp, dev):
+        # V^T rows are padded to a multiple of 8 tokens for the TMA box; the pad columns must read as zero
+        if Lp == L:
+            return torch.empty((d, Lp), dtype=torch.bfloat16, device=dev)
+        return torch.zeros((d, Lp), dtype=torch.bfloat16, device=dev)
+
     # -- a3..a8 --------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, feat: torch.Tensor, pan: torch.Tensor, img_hw, pad_hw, obj_ids: torch.Tensor,
@@ -265,7 +276,7 @@ class RelationQueryTransformer:
             last = li == len(w.layers) - 1
             # K3: per-image K and V^T for this layer's cross-attention (shared by all pairs)
             kc = ops.gemm(X, lw["w_ck"], lw["b_ck"])                             # [L, d]
-            vt = torch.zeros((d, Lp), dtype=torch.bfloat16, device=dev)
+            vt = self._vt_buffer(d, L, Lp, dev)
             ops.gemm(lw["w_cv"], X, lw["b_cv"], bias_along_m=True, out=vt[:, :L])  # V^T [d, L]
             # self-attention over the 33 + T rows of every pair
             if li == 0 and self.share_query_rows and T > 0:
@@ -344,7 +355,7 @@ class RelationQueryTransformer:
         for li, lw in enumerate(w.layers):
             last = li == len(w.layers) - 1
             kc = ops.gemm(X, lw["w_ck"], lw["b_ck"])
-            vt = torch.zeros((d, Lp), dtype=torch.bfloat16, device=dev)
+            vt = self._vt_buffer(d, L, Lp, dev)
             ops.gemm(lw["w_cv"], X, lw["b_cv"], bias_along_m=True, out=vt[:, :L])
             # ---- self-attention block ----
             qkv_q = None

@@ -254,6 +254,22 @@ OPT_2P7B = dict(vocab_size=50272, hidden_size=2560, num_hidden_layers=32, ffn_di
 OPT_TINY = dict(vocab_size=1024, hidden_size=320, num_hidden_layers=2, ffn_dim=1280,
                 num_attention_heads=4, max_position_embeddings=256, word_embed_proj_dim=320,
                 do_layer_norm_before=True, activation_function="relu")
+# Llama family (the LLM configs/psg/baseline_v4_ov.py:60-61 names).  "model_type" selects the HF class in the builders.
+LLAMA2_7B = dict(model_type="llama", vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                 num_attention_heads=32, num_key_value_heads=32, max_position_embeddings=4096, rms_norm_eps=1e-5)
+LLAMA_TINY = dict(model_type="llama", vocab_size=1024, hidden_size=256, intermediate_size=704, num_hidden_layers=2,
+                  num_attention_heads=2, num_key_value_heads=2, max_position_embeddings=512, rms_norm_eps=1e-5)
+LLAMA_TINY_GQA = dict(LLAMA_TINY, hidden_size=512, num_attention_heads=4, num_key_value_heads=2, intermediate_size=1408)
+
+
+def build_causal_lm(llm_config: dict):
+    """Random-init HF causal LM from one of the config dicts above (OPT unless ``model_type == 'llama'``)."""
+    cfg = dict(llm_config)
+    if cfg.pop("model_type", "opt") == "llama":
+        from transformers import LlamaConfig, LlamaForCausalLM
+        return LlamaForCausalLM(LlamaConfig(**cfg))
+    from transformers import OPTConfig, OPTForCausalLM
+    return OPTForCausalLM(OPTConfig(**cfg))
 
 
 def make_stress_inputs() -> dict:

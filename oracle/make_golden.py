@@ -17,12 +17,12 @@ from oracle import ref_shims
 
 GOLDEN_DIR = Path(__file__).resolve().parent.parent / "tests" / "golden"
 WEIGHT_SEED = 0
-LLM_FEATURE_SIZE = synth.OPT_TINY["hidden_size"]
 
 
-def build_reference_head(max_object_num=80):
-    cls = ref_shims.load_reference_head_class(synth.OPT_TINY)
-    head = cls(llm_feature_size=LLM_FEATURE_SIZE, max_object_num=max_object_num)
+def build_reference_head(max_object_num=80, llm_config=None, **kwargs):
+    llm_config = llm_config or synth.OPT_TINY
+    cls = ref_shims.load_reference_head_class(llm_config)
+    head = cls(llm_feature_size=llm_config["hidden_size"], max_object_num=max_object_num, **kwargs)
     synth.init_parameters(head, WEIGHT_SEED)
     return head
 
@@ -76,7 +76,23 @@ def main(argv=None):
             g["image_tokens"] = g["image_tokens"][::16].clone()
         torch.save(g, GOLDEN_DIR / f"{name}.pt")
         print(f"{name}: {time.time() - t:.1f}s  ->  {(GOLDEN_DIR / (name + '.pt')).stat().st_size / 1e6:.2f} MB")
+    make_llama_golden()
     return 0
+
+
+def make_llama_golden():
+    """The shipped config's LLM family (configs/psg/baseline_v4_ov.py:60-61): the unmodified reference head with a tiny
+    random LlamaForCausalLM behind the ``AutoModelForCausalLM.from_pretrained`` shim, cfg1 image.  Only the LLM leg is
+    stored (the relation-query leg is the one cfg1.pt already pins)."""
+    t = time.time()
+    head = build_reference_head(llm_config=synth.LLAMA_TINY)
+    rec = ref_shims.run_reference(head, synth.make_image_inputs(synth.WORKLOADS["cfg1"], 0))
+    g = _summarise(rec, list(range(0, 64, 4)))
+    keep = {k: g[k] for k in ("exist_logits", "selected", "selected_embeds0", "llm_masks", "sequences", "scores_first2",
+                              "lang_proj_first2", "terminal_error")}
+    keep["qformer_out_selected"] = rec["qformer"][:, :33][g["selected"][:4]].clone()     # rows the LLM leg consumed
+    torch.save(keep, GOLDEN_DIR / "cfg1_llama.pt")
+    print(f"cfg1_llama: {time.time() - t:.1f}s  ->  {(GOLDEN_DIR / 'cfg1_llama.pt').stat().st_size / 1e6:.2f} MB")
 
 
 if __name__ == "__main__":

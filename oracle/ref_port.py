@@ -54,8 +54,8 @@ class ReferencePortHead(nn.Module):
         self.llm_tokenizer = SyntheticTokenizer("llm")
         self.language_model = None
         if llm_config is not None:
-            from transformers import OPTConfig, OPTForCausalLM
-            self.language_model = OPTForCausalLM(OPTConfig(**llm_config))
+            from openpsg_b200.synth import build_causal_lm
+            self.language_model = build_causal_lm(llm_config)      # OPT or Llama (config "model_type")
             self.llm_tokenizer.set_vocab_size(llm_config["vocab_size"])
 
     # -- v4:408-435 -----------------------------------------------------------------------------

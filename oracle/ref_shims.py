@@ -13,7 +13,7 @@ Shimmed, and why:
   * ``timm.layers.PatchEmbed`` -> Conv2d(k=s=patch) + flatten(2).transpose(1,2) (v4:15,75; restated from
     the public timm >= 0.9 source: norm_layer=None -> Identity, no size check when img_size=None)
   * ``AutoTokenizer.from_pretrained`` -> ``openpsg_b200.synth.SyntheticTokenizer`` (no vocab offline)
-  * ``AutoModelForCausalLM.from_pretrained`` -> random-init ``OPTForCausalLM`` of the requested dims
+  * ``AutoModelForCausalLM.from_pretrained`` -> random-init ``OPTForCausalLM`` / ``LlamaForCausalLM`` of the requested dims
   * ``torch.Tensor.cuda`` -> identity (the reference hard-codes ``.cuda()`` on 9 lines)
 """
 from __future__ import annotations
@@ -138,7 +138,8 @@ def load_reference_head_class(llm_config: dict):
         return tok
 
     def _lm_from_pretrained(name, *a, **k):
-        return OPTForCausalLM(OPTConfig(**llm_config))
+        from openpsg_b200.synth import build_causal_lm
+        return build_causal_lm(llm_config)                 # OPTForCausalLM or LlamaForCausalLM, random init
 
     AutoTokenizer.from_pretrained = staticmethod(_tok_from_pretrained)
     AutoModelForCausalLM.from_pretrained = staticmethod(_lm_from_pretrained)

@@ -281,11 +281,112 @@ def opt_greedy_decode(sd, cfg, prefix_embeds: torch.Tensor, prefix_mask: torch.T
 
 
 def build_llm_prefix(sd, pair_feature: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,
-                     prefix: str = "language_model."):
+                     prefix: str = "language_model.", embed_key: str | None = None):
     """a9 (v4:294-301): U = pair_feature @ W_L^T + b_L  [k,32,d_llm]; cat with embed_tokens(ids);
     mask = cat(ones[k,32], left-padded text mask)."""
     U = _lin(pair_feature, sd, "language_projection")
-    E = sd[prefix + "model.decoder.embed_tokens.weight"][llm_ids]
+    E = sd[embed_key or (prefix + "model.decoder.embed_tokens.weight")][llm_ids]
     embeds = torch.cat([U, E], dim=1)
     mask = torch.cat([torch.ones(U.shape[0], U.shape[1], dtype=torch.long), llm_mask.long()], dim=1)
     return embeds, mask
+
+# ----------------------------------------------------------------------------------------------
+# a9-a10 for the LLM the shipped config names: Llama greedy decode (HF models/llama/modeling_llama.py)
+# ----------------------------------------------------------------------------------------------
+
+
+def _lin_opt_bias(x, sd, prefix):
+    y = x @ sd[prefix + ".weight"].t()
+    b = sd.get(prefix + ".bias")
+    return y if b is None else y + b
+
+
+def _rmsnorm(x, w, eps):
+    """LlamaRMSNorm (:52-69): weight * (x * rsqrt(mean(x^2) + eps))."""
+    return w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+
+
+def llama_positions(mask: torch.Tensor) -> torch.Tensor:
+    """position_ids as HF ``generate`` derives them from the attention mask (generation/utils.py:707-729):
+    cumsum(mask) - 1, pad slots set to a dummy in-range value (their rows are never attended to)."""
+    m = mask.long()
+    return (torch.cumsum(m, dim=1) - 1).clamp_min(0)
+
+
+def llama_forward(sd: Dict[str, torch.Tensor], cfg: dict, embeds: torch.Tensor, mask: torch.Tensor,
+                  prefix: str = "language_model.") -> torch.Tensor:
+    """Full (non-cached) Llama decoder forward: RMSNorm -> q/k/v (no bias) -> rotate_half RoPE on q, k (:137-166) ->
+    causal + key-padding softmax(qk^T / sqrt(hd)) v with repeat_kv (:187-196) -> o_proj + residual -> RMSNorm ->
+    down(silu(gate) * up) + residual (:170-184) -> final RMSNorm -> untied lm_head.  embeds [B,S,d], mask [B,S]."""
+    B, S, d = embeds.shape
+    H = cfg["num_attention_heads"]
+    KV = cfg.get("num_key_value_heads") or H
+    hd = cfg.get("head_dim") or d // H
+    eps = cfg.get("rms_norm_eps", 1e-6)
+    theta = cfg.get("rope_theta", 10000.0)
+    mp = prefix + "model."
+    pos = llama_positions(mask).float()                                           # [B,S]
+    inv_freq = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    freqs = pos[:, :, None] * inv_freq[None, None, :]                             # [B,S,hd/2]
+    emb = torch.cat([freqs, freqs], dim=-1)
+    cos, sin = emb.cos()[:, None], emb.sin()[:, None]                             # [B,1,S,hd]
+
+    def rot(x):
+        x1, x2 = x[..., : hd // 2], x[..., hd // 2:]
+        return torch.cat([-x2, x1], dim=-1)
+
+    h = embeds
+    causal = torch.tril(torch.ones(S, S, dtype=torch.bool))
+    allow = causal[None, :, :] & mask.bool()[:, None, :]
+    bias = torch.zeros(B, 1, S, S).masked_fill(~allow[:, None], torch.finfo(torch.float32).min)
+    n_layers = cfg["num_hidden_layers"]
+    for l in range(n_layers):
+        lp = f"{mp}layers.{l}."
+        x = _rmsnorm(h, sd[lp + "input_layernorm.weight"], eps)
+        q = _lin_opt_bias(x, sd, lp + "self_attn.q_proj").reshape(B, S, H, hd).transpose(1, 2)
+        k = _lin_opt_bias(x, sd, lp + "self_attn.k_proj").reshape(B, S, KV, hd).transpose(1, 2)
+        v = _lin_opt_bias(x, sd, lp + "self_attn.v_proj").reshape(B, S, KV, hd).transpose(1, 2)
+        q = q * cos + rot(q) * sin
+        k = k * cos + rot(k) * sin
+        if KV != H:
+            k = k.repeat_interleave(H // KV, dim=1)
+            v = v.repeat_interleave(H // KV, dim=1)
+        a = torch.softmax(q @ k.transpose(-1, -2) * (hd ** -0.5) + bias, dim=-1) @ v
+        a = a.transpose(1, 2).reshape(B, S, H * hd)
+        h = h + _lin_opt_bias(a, sd, lp + "self_attn.o_proj")
+        x = _rmsnorm(h, sd[lp + "post_attention_layernorm.weight"], eps)
+        g = _lin_opt_bias(x, sd, lp + "mlp.gate_proj")
+        u = _lin_opt_bias(x, sd, lp + "mlp.up_proj")
+        h = h + _lin_opt_bias(F.silu(g) * u, sd, lp + "mlp.down_proj")
+    h = _rmsnorm(h, sd[mp + "norm.weight"], eps)
+    lm = sd.get(prefix + "lm_head.weight")
+    if lm is None:
+        lm = sd[mp + "embed_tokens.weight"]
+    return h @ lm.t()
+
+
+def llama_greedy_decode(sd, cfg, prefix_embeds: torch.Tensor, prefix_mask: torch.Tensor, max_new_tokens: int,
+                        prefix: str = "language_model.", forced_tokens: torch.Tensor | None = None):
+    """Greedy decode as ``opt_greedy_decode`` (v4:305-312), Llama arithmetic."""
+    emb = sd[prefix + "model.embed_tokens.weight"]
+    embeds, mask = prefix_embeds, prefix_mask.long()
+    toks, scores = [], []
+    for t in range(max_new_tokens):
+        logits = llama_forward(sd, cfg, embeds, mask, prefix)[:, -1]
+        nxt = logits.argmax(dim=-1)
+        scores.append(logits)
+        toks.append(nxt)
+        feed = nxt if forced_tokens is None else forced_tokens[:, t]
+        embeds = torch.cat([embeds, emb[feed][:, None, :]], dim=1)
+        mask = torch.cat([mask, torch.ones(mask.shape[0], 1, dtype=mask.dtype)], dim=1)
+    return torch.stack(toks, dim=1), torch.stack(scores, dim=1)
+
+
+def greedy_decode(sd, cfg, prefix_embeds, prefix_mask, max_new_tokens, prefix: str = "language_model.", forced_tokens=None):
+    """Dispatch on the config's ``model_type`` (OPT when absent)."""
+    fn = llama_greedy_decode if cfg.get("model_type", "opt") == "llama" else opt_greedy_decode
+    return fn(sd, cfg, prefix_embeds, prefix_mask, max_new_tokens, prefix, forced_tokens)
+
+
+def embed_tokens_key(cfg, prefix: str = "language_model.") -> str:
+    return prefix + ("model.embed_tokens.weight" if cfg.get("model_type", "opt") == "llama" else "model.decoder.embed_tokens.weight")

@@ -11,8 +11,7 @@ def build_product_head(llm=None, max_object_num=80, topk_pairs=20, max_new_token
     from openpsg_b200.head import RelationTransformerHeadV4
     lm, ltok, d_llm = False, None, 4096
     if llm is not None:
-        from transformers import OPTConfig, OPTForCausalLM
-        lm = OPTForCausalLM(OPTConfig(**llm))
+        lm = synth.build_causal_lm(llm)
         ltok = synth.SyntheticTokenizer("llm")
         ltok.set_vocab_size(llm["vocab_size"])
         d_llm = llm["hidden_size"]

@@ -154,3 +154,59 @@ def test_mask_pool_matches_reference_formula():
     assert (obj - ref).abs().max() < 1e-5
     assert torch.equal(pair[7], torch.cat([obj[1], obj[2]]))
     assert obj[4].abs().max() == 0
+
+
+# ---- Llama family (the LLM the shipped config names) -----------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def llama_port_head():
+    head = ReferencePortHead(synth.LLAMA_TINY, llm_feature_size=synth.LLAMA_TINY["hidden_size"], max_object_num=80)
+    synth.init_parameters(head, 0)
+    return head.eval()
+
+
+def test_llama_restatement_matches_reference(golden, llama_port_head):
+    """restated.llama_greedy_decode against what the UNMODIFIED reference head produced with a tiny LlamaForCausalLM behind
+    its from_pretrained call (tests/golden/cfg1_llama.pt): ids and per-step scores of the first two generate calls."""
+    g = golden("cfg1_llama")
+    sd = {k: v.detach() for k, v in llama_port_head.state_dict().items()}
+    embeds0 = g["selected_embeds0"][None]
+    n_new = g["scores_first2"][0].shape[0]
+    toks, scores = restated.llama_greedy_decode(sd, synth.LLAMA_TINY, embeds0, g["llm_masks"][:1], n_new)
+    assert torch.equal(toks[0], g["sequences"][0][:n_new])
+    assert (scores[0] - g["scores_first2"][0]).abs().max() < 1e-3
+    # a9 on the Llama width: projection of the first selected pair's 32 relation rows
+    feat = g["qformer_out_selected"][0][1:]
+    u = feat @ sd["language_projection.weight"].t() + sd["language_projection.bias"]
+    assert (u - g["lang_proj_first2"][0]).abs().max() < TOL
+    emb, mask = restated.build_llm_prefix(sd, g["qformer_out_selected"][:1, 1:], torch.zeros((1, 0), dtype=torch.long),
+                                          torch.zeros((1, 0), dtype=torch.long), embed_key=restated.embed_tokens_key(synth.LLAMA_TINY))
+    assert (emb[0] - g["selected_embeds0"][:32]).abs().max() < TOL
+
+
+def test_llama_port_matches_reference(golden, llama_port_head):
+    g = golden("cfg1_llama")
+    q = llama_port_head.relation_queries(_inputs("cfg1"))
+    assert (q["exist_logits"] - g["exist_logits"]).abs().max() < TOL
+    assert q["selected"] == g["selected"]
+    d = llama_port_head.decode_relations(q, max_pairs=3)
+    for got, ref in zip(d["sequences"], g["sequences"][:3]):
+        n = min(len(got), len(ref))
+        assert torch.equal(got[:n], ref[:n])
+
+
+def test_llama_gqa_restatement_matches_hf():
+    """Grouped-query attention + left-padded batch: the restatement against the live HF LlamaForCausalLM forward."""
+    cfg = synth.LLAMA_TINY_GQA
+    lm = synth.build_causal_lm(cfg).eval()
+    synth.init_parameters(lm, 3)
+    sd = {"language_model." + k: v.detach() for k, v in lm.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    embeds = torch.randn((2, 9, cfg["hidden_size"]), generator=g) * 0.1
+    mask = torch.ones((2, 9), dtype=torch.long)
+    mask[1, 3:5] = 0                                      # pads mid-sequence like [prefix ; left-padded text] (v4:298-299)
+    with torch.no_grad():
+        ref = lm(inputs_embeds=embeds, attention_mask=mask, position_ids=restated.llama_positions(mask)).logits
+    got = restated.llama_forward(sd, cfg, embeds, mask)
+    valid = mask.bool()
+    assert (got - ref)[valid].abs().max() < 1e-4
