@@ -53,6 +53,7 @@ SIGNATURES = {
     "opsg_llm_prompt_layout": [P, I, I, I, I, I, P, P, P, P, P],
     "opsg_copy_bytes": [P, P, ctypes.c_size_t, P],
     "opsg_transpose_i32": [P, I, I, P, P],
+    "opsg_splitk_reduce_bf16": [P, I, I, I, P, P, I, P],
 }
 
 

@@ -91,7 +91,7 @@ struct GemmSegIter {
     const int split = rest / p.m_tiles;
     s.kb0 = min(kb_total, split * kb_per_split);
     s.kb1 = min(kb_total, s.kb0 + kb_per_split);
-    s.slot = 0;
+    s.slot = split;      // k_splits > 1 with OUT_F32: index of this split's partial slice
     tile += gridDim.x;
     return true;
   }
@@ -352,7 +352,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_commit();
           }
           buf ^= 1;
-        } else if (row_ok && col_ok && has_k) {
+        } else if (row_ok && col_ok && (has_k || (p.out_mode == OPSG_OUT_F32 && p.k_splits > 1))) {
           if (p.out_mode == OPSG_OUT_BF16) {
             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
             if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
@@ -371,7 +371,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (col0 + j < p.N) d[j] = __float2bfloat16(f[j]);
             }
           } else if (p.out_mode == OPSG_OUT_F32) {
-            float* d = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+            // k_splits > 1: split s writes its fp32 partial to slice s of D ([k_splits][M][ldd]; opsg_splitk_reduce sums
+            // the slices in split order -- deterministic, unlike OPSG_OUT_F32_ATOMIC)
+            float* d = reinterpret_cast<float*>(p.D) + (static_cast<size_t>(p.k_splits > 1 ? sg.slot : 0) * p.M + row) * p.ldd + col0;
             if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -590,7 +592,9 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
   OPSG_CHECK_ARG(out_mode >= OPSG_OUT_BF16 && out_mode <= OPSG_OUT_F32_ATOMIC, "gemm: bad out_mode");
   OPSG_CHECK_ARG(act >= OPSG_ACT_NONE && act <= OPSG_ACT_RELU, "gemm: bad activation");
   OPSG_CHECK_ARG(k_splits >= 1, "gemm: k_splits must be >= 1");
-  if (k_splits > 1)
+  if (k_splits > 1 && out_mode == OPSG_OUT_F32) {
+    OPSG_CHECK_ARG(!bias && !residual && act == OPSG_ACT_NONE, "gemm: split-K partial slices take no bias / residual / activation");
+  } else if (k_splits > 1)
     OPSG_CHECK_ARG(out_mode == OPSG_OUT_F32_ATOMIC && !bias && !residual && act == OPSG_ACT_NONE,
                    "gemm: split-K needs OPSG_OUT_F32_ATOMIC and no bias/residual/act");
   OPSG_CHECK_ARG(!residual || ldr >= N, "gemm: ldr too small");

@@ -173,6 +173,39 @@ __global__ void transpose_i32_kernel(const int32_t* __restrict__ src, int rows, 
   dst[i] = src[static_cast<size_t>(r) * cols + c];
 }
 
+
+// out[r, c] = bf16(bias[c] + sum_s partials[s][r][c]), slices summed in split order (fixed order -> bit-reproducible);
+// thread = 4 consecutive columns, 16-byte loads, `splits` independent loads in flight per thread in groups of 8.
+__global__ void __launch_bounds__(256) splitk_reduce_bf16_kernel(const float* __restrict__ partials, int splits, int rows, int cols,
+                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                                 int ld_out) {
+  pdl_wait_then_trigger();
+  const int vec = cols / 4;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * vec) return;
+  const int c = static_cast<int>(idx % vec);
+  const long long r = idx / vec;
+  const size_t slice = static_cast<size_t>(rows) * cols;
+  const float4* src = reinterpret_cast<const float4*>(partials + r * cols) + c;
+  float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(src + (static_cast<size_t>(s + u) * slice) / 4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+  for (; s < splits; ++s) {
+    const float4 v = __ldcs(src + (static_cast<size_t>(s) * slice) / 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  uint2 o;
+  o.x = pack_bf16x2(acc.x, acc.y);
+  o.y = pack_bf16x2(acc.z, acc.w);
+  *reinterpret_cast<uint2*>(out + r * ld_out + c * 4) = o;
+}
+
 }  // namespace opsg
 
 using namespace opsg;
@@ -257,5 +290,18 @@ extern "C" int opsg_transpose_i32(const int32_t* src, int rows, int cols, int32_
   OPSG_CHECK_ARG(src && dst && rows > 0 && cols > 0, "transpose_i32: bad arguments");
   launch_kernel(transpose_i32_kernel, (rows * cols + 255) / 256, 256, 0, ST(stream), src, rows, cols, dst);
   OPSG_CHECK_LAUNCH("transpose_i32_kernel");
+  return OPSG_OK;
+}
+
+extern "C" int opsg_splitk_reduce_bf16(const float* partials, int splits, int rows, int cols, const float* bias, opsg_bf16* out,
+                                       int ld_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(partials && out, "splitk_reduce: null pointer");
+  OPSG_CHECK_ARG(splits > 0 && rows > 0 && cols > 0 && cols % 4 == 0 && ld_out % 4 == 0 && ld_out >= cols, "splitk_reduce: bad shape");
+  OPSG_CHECK_ARG((((uintptr_t)partials | (uintptr_t)bias) & 15) == 0 && ((uintptr_t)out & 7) == 0, "splitk_reduce: bad alignment");
+  launch_kernel(splitk_reduce_bf16_kernel, ceil_div_ll(static_cast<long long>(rows) * (cols / 4), 256), 256, 0, ST(stream),
+                partials, splits, rows, cols, bias, reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  OPSG_CHECK_LAUNCH("splitk_reduce_bf16_kernel");
   return OPSG_OK;
 }

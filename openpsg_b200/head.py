@@ -238,9 +238,9 @@ class RelationTransformerHeadV4(BaseModule):
         meta_info = inputs['img_metas'][0]
         assert batch_size == 1, 'only support batch size 1 for now.'
         if self.training:
-            raise NotImplementedError(
-                "training branch (v4:114-133,187-204,267-285,327-341) is outside the accelerated hot path; "
-                "see DESIGN.md §scope")
+            # plain PyTorch on the head's own HF modules (autograd), API completeness only: openpsg_b200/train_branch.py
+            from .train_branch import forward_train
+            return forward_train(self, inputs, is_generation)
         if is_generation is None:
             is_generation = True
         with torch.no_grad():

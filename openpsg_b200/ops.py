@@ -480,3 +480,18 @@ def transpose_i32(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.load().opsg_transpose_i32(_ptr(src), rows, cols, _ptr(dst), _stream()))
     _count()
     return dst
+
+
+def gemm_splitk(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k_splits: int, out: Optional[torch.Tensor] = None):
+    """Deterministic split-K GEMM for skinny-M / huge-K problems (PatchEmbed: K = 65536): every split writes its fp32
+    partial to its own slice, a second kernel sums the slices in split order and applies the bias -> bf16 [M, N]."""
+    M, K = a.shape
+    N = w.shape[0]
+    part = torch.empty((k_splits, M, N), dtype=torch.float32, device=a.device)
+    gemm(a, w, out=part.view(k_splits * M, N)[:M], k_splits=k_splits)          # the kernel strides the slices by M rows
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    with _timed("splitk_reduce", 0.0, 4.0 * part.numel() + 2.0 * M * N):
+        _lib.check(_lib.load().opsg_splitk_reduce_bf16(_ptr(part), k_splits, M, N, _ptr(bias), _ptr(out), out.stride(0), _stream()))
+    _count()
+    return out

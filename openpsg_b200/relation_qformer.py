@@ -213,9 +213,9 @@ class RelationQueryTransformer:
         self.fold_ln = (os.environ.get("OPSG_FOLD_LN", "0") == "1") if fold_ln is None else bool(fold_ln)
         # layer 0 projects the (pair-independent) query rows once instead of B times; OPSG_SHARE_QUERY_ROWS=0 turns it off
         self.share_query_rows = os.environ.get("OPSG_SHARE_QUERY_ROWS", "1") != "0"
-        # OPSG_PATCH_DETERMINISTIC=1: PatchEmbed through the K-sliced GEMM (bit-reproducible runs; 136 us per cfg2 image
-        # instead of ~85 us for split-K with fp32 atomics, -7 % pairs/s, so it is opt-in)
-        self.deterministic_patch_embed = os.environ.get("OPSG_PATCH_DETERMINISTIC", "0") == "1"
+        # PatchEmbed's split-K is deterministic by default (per-split partial slices + fixed-order reduction);
+        # OPSG_PATCH_DETERMINISTIC=0 selects the round-1 fp32-atomics accumulation (run-to-run differences in the last bit)
+        self.deterministic_patch_embed = os.environ.get("OPSG_PATCH_DETERMINISTIC", "1") != "0"
 
     # -- K1 ------------------------------------------------------------------------------------------
     def image_tokens(self, feat: torch.Tensor) -> torch.Tensor:
@@ -223,18 +223,15 @@ class RelationQueryTransformer:
         w = self.w
         a = ops.patch_im2col(feat, w.patch)                                  # bf16 [L, C*p*p]
         L, K = a.shape
-        if self.deterministic_patch_embed:
-            # K = 65536 against 16..256 rows: the K-sliced small-M GEMM (one slice per SM, fp32 partials summed in slice
-            # order by its second kernel, bias and bf16 rounding there too) -- bit-reproducible, unlike split-K atomics
-            out = torch.empty((L, w.patch_w.shape[0]), dtype=torch.bfloat16, device=feat.device)
-            for r0 in range(0, L, 128):
-                ops.gemm_small_m(a[r0:r0 + 128], w.patch_w, w.patch_b, out=out[r0:r0 + 128])
-            return out
-        acc = torch.empty((L, w.patch_w.shape[0]), dtype=torch.float32, device=feat.device)
-        ops.init_rows_f32(acc, w.patch_b)
         kb = K // 64
         m_tiles = (L + 127) // 128
         splits = max(1, min(kb, 148 // max(1, m_tiles)))
+        if self.deterministic_patch_embed:
+            # default: every K split writes its own fp32 partial slice, summed in split order with the bias by a second
+            # kernel (ops.gemm_splitk) -- two runs of the product return the same bits, hence the same top-k set
+            return ops.gemm_splitk(a, w.patch_w, w.patch_b, splits)
+        acc = torch.empty((L, w.patch_w.shape[0]), dtype=torch.float32, device=feat.device)
+        ops.init_rows_f32(acc, w.patch_b)
         ops.gemm(a, w.patch_w, out=acc, atomic=True, k_splits=splits)
         return ops.cast_f32_bf16(acc)
 

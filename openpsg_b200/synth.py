@@ -128,6 +128,45 @@ def make_image_inputs(workload: Workload, image_index: int = 0, *, ensure_token_
     }
 
 
+class BitmapMasksStandIn:
+    """The one method of mmdet's ``BitmapMasks`` the head uses at train time (``to_tensor(dtype, device)``, v4:371)."""
+
+    def __init__(self, masks: np.ndarray):
+        self.masks = np.asarray(masks, dtype=np.uint8)          # [n_thing, H, W]
+
+    def to_tensor(self, dtype, device):
+        return torch.tensor(self.masks, dtype=dtype, device=device)
+
+
+def make_train_inputs(workload: Workload, image_index: int = 0, num_rels: int = 6) -> dict:
+    """One image worth of TRAIN-mode head inputs (``detectors/openseed_relation_v2.py:159-165``):
+    ``mask_features``, ``img_metas`` with ``masks_info`` / ``gt_rels`` (``datasets/pipelines/loading.py:23-28``),
+    ``gt_masks`` (thing bitmaps), ``gt_labels``, ``gt_semantic_seg``.  Objects alternate thing / stuff."""
+    base = make_image_inputs(workload, image_index)
+    gen = torch.Generator().manual_seed(4321 + image_index)
+    N = workload.num_objects
+    pan = base["object_info"][0]["pan_results"]
+    ids = object_ids(N)
+    infos = [dict(category=i % INSTANCE_OFFSET, is_thing=(k % 2 == 0)) for k, i in enumerate(ids)]
+    thing = np.stack([(pan == i).numpy() for k, i in enumerate(ids) if infos[k]["is_thing"]]).astype(np.uint8)
+    sem = (pan % INSTANCE_OFFSET).to(torch.int64)[None]            # [1, H, W] category map
+    rels, seen = [], set()
+    while len(rels) < num_rels:
+        i, j = (int(x) for x in torch.randint(0, N, (2,), generator=gen))
+        r = int(torch.randint(0, len(relation_categories), (1,), generator=gen))
+        if i != j and (i, j, r) not in seen:
+            seen.add((i, j, r))
+            rels.append([i, j, r])
+    meta = dict(base["img_metas"][0], masks_info=infos, gt_rels=[rels])
+    return {
+        "mask_features": base["mask_features"],
+        "img_metas": [meta],
+        "gt_labels": [torch.tensor([x["category"] for x in infos if x["is_thing"]])],
+        "gt_masks": [BitmapMasksStandIn(thing)],
+        "gt_semantic_seg": [sem],
+    }
+
+
 def inputs_to(inputs: dict, device) -> dict:
     out = dict(inputs)
     out["mask_features"] = inputs["mask_features"].to(device)

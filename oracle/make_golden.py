@@ -77,7 +77,39 @@ def main(argv=None):
         torch.save(g, GOLDEN_DIR / f"{name}.pt")
         print(f"{name}: {time.time() - t:.1f}s  ->  {(GOLDEN_DIR / (name + '.pt')).stat().st_size / 1e6:.2f} MB")
     make_llama_golden()
+    make_train_golden()
     return 0
+
+
+def run_reference_train(head, inputs, seed, dropout):
+    """The reference's TRAIN branch (v4:114-133,187-204,267-285,327-341) with seeded samplers.  ``dropout=False`` puts the
+    two HF sub-modules in eval mode (the head itself stays in training mode) so the losses do not depend on dropout draws."""
+    import random
+    head.train()
+    if not dropout:
+        head.relation_qformer.eval()
+        head.language_model.eval()
+    torch.manual_seed(seed)
+    random.seed(seed)
+    out = head(inputs)
+    return {k: v.detach().clone() for k, v in out.items()}
+
+
+def make_train_golden():
+    """Loss values of the unmodified reference head in training mode on a synthetic train-mode image (cfg1 geometry)."""
+    t = time.time()
+    g = {}
+    for llm_name, llm_cfg in (("opt", synth.OPT_TINY), ("llama", synth.LLAMA_TINY)):
+        for rel_cls_type in ("binary", "binary+multiclass"):
+            head = build_reference_head(llm_config=llm_cfg, rel_cls_type=rel_cls_type)
+            for dropout in (False, True):
+                for image in (0, 1):
+                    inputs = synth.make_train_inputs(synth.WORKLOADS["cfg1"], image)
+                    key = (llm_name, rel_cls_type, dropout, image)
+                    g[key] = run_reference_train(head, inputs, 100 + image, dropout)
+                    print(key, {k: round(float(v), 6) for k, v in g[key].items()})
+    torch.save(g, GOLDEN_DIR / "train_losses.pt")
+    print(f"train_losses: {time.time() - t:.1f}s")
 
 
 def make_llama_golden():

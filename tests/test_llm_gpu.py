@@ -166,4 +166,4 @@ def test_llm_rejects_long_context(head):
     ids = torch.full((1, 17), 5, dtype=torch.int32, device="cuda")
     with pytest.raises(OpsgError):
         (head._llm_engine or head.repack("cuda:0")._llm_engine).generate(out_hidden, torch.zeros(1, dtype=torch.int32, device="cuda"), ids,
-                                                   torch.ones_like(ids), max_new_tokens=100)
+                                                   torch.ones_like(ids), max_new_tokens=250)
