@@ -1,26 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — object-pairs/sec of the relation-head hot path (BASELINE.json metric) on N B200s.
+"""bench.py — object-pairs/sec (+ relation-tokens/sec) of the relation-head hot path (BASELINE.json metric) on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--images-per-step I]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling strong|weak]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
 
-A step = one pass of the path a2-a8 (feature map + panoptic map -> Q-Former over all N^2 pair queries ->
-existence probabilities, existence mask, top-k pair list) over a batch of `images_per_step` synthetic images
-PER RANK (weak scaling; 4 per rank = BASELINE cfg4's 32 images over 8 GPUs), every image of the cfg2 shape
-(1024x1024, 40 objects, 1600 queries = 1560 ordered pairs, 256 image tokens).  Images are independent, so ranks
-share nothing on the data path; NCCL is used for the barrier and the max-over-ranks time only.
+A step = one pass of the path a2-a8 (feature map + panoptic map -> Q-Former over all N^2 pair queries -> existence
+probabilities, existence mask, top-k pair list) over BASELINE cfg4's batch: 32 synthetic images of the cfg2 shape
+(1024x1024, 40 objects, 1600 queries = 1560 ordered pairs, 256 image tokens), image i on rank i % N
+(openpsg_b200/sharding.py) — STRONG scaling, the total work is fixed (``--scaling weak`` keeps 4 images per rank).
+Images are independent, so ranks share nothing on the data path; NCCL carries the barrier, the max-over-ranks time and,
+after the timed region, one gather of the per-image result records (whose SHA-1 must not depend on N).
 
 value  : whole-job ordered pairs / s with inputs resident in HBM: the K steps' images through one head.forward_batch
          call (device-timed, CUDA events, max over ranks); ms_per_step_separate_calls = one head(inputs) call per image.
 e2e    : same call with HOST (pinned) inputs: H2D of every image's features, panoptic map and ids and D2H of the selected
          pair lists inside the timed region (timed twice, both passes reported; coarser call patterns beside it).
 roofline / roofline_xattn: dominant kernel (tcgen05 GEMM) and the north-star cross-attention kernel, CUDA-event
-         timed per launch during the timed steps.
-cpu_baseline / --impl reference: oracle/ref_port.py (the reference's call pattern on HF modules) on host cores.
+         timed per launch during the timed steps; `traffic` = DRAM bytes per launch from the committed ncu capture
+         named in `traffic_source` (profiles/r2_traffic.json, written by scripts/ncu_summary.py).
+relation_tokens_per_sec / e2e_cfg3 / e2e_cfg5: BASELINE configs 3 and 5 end to end through head.forward_batch (feature map
+         -> relation queries -> top-100 filter -> batched OPT-2.7B prefill + 32-token greedy decode -> triples), images
+         sharded over the ranks, plus the decode-only leg [a9..a10] with its HBM roofline.
+cpu_baseline / --impl reference: oracle/ref_port.py (the reference's call pattern on HF modules, fp32) on the host cores:
+         one FULL 1600-query image timed once (`full_image`), then K bounded-sample steps (`extrapolated`).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,10 +41,14 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-from openpsg_b200 import synth  # noqa: E402
+from openpsg_b200 import sharding, synth  # noqa: E402
 
 WORKLOAD = "cfg2"
+TOTAL_IMAGES = 32          # BASELINE cfg4
+LLM_IMAGES = 8             # BASELINE cfg5's batch; the cfg3 leg uses the same count
 METRIC, UNIT = "object_pairs_per_sec", "pairs/s"
+WORKLOAD_DESC = ("cfg4: batch of 32 synthetic 1024x1024 images, 40 objects each (1600 pair queries = 1560 ordered pairs, "
+                 "256 image tokens), relation-query Q-Former + existence filter (a2-a8)")
 
 
 def _peaks():
@@ -46,6 +57,12 @@ def _peaks():
         d = json.loads(p.read_text())
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def _traffic():
+    """DRAM bytes per launch of the profiled kernels, parsed from the committed ncu summaries."""
+    p = ROOT / "profiles" / "r2_traffic.json"
+    return json.loads(p.read_text()) if p.exists() else {}
 
 
 class ClockSampler:
@@ -83,128 +100,226 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port) — also the cpu_baseline leg of the GPU arm
+# CPU reference arm (oracle port) — also the cpu_baseline leg of the GPU arm.  The ONLY code in this file that touches oracle/.
 # ---------------------------------------------------------------------------------------------------
-def _cpu_reference_pass(head, inputs, n_sample):
+def _build_port(llm=None, topk_pairs=20, max_new_tokens=16):
+    from oracle.ref_port import ReferencePortHead
+    d_llm = llm["hidden_size"] if llm is not None else 4096
+    head = ReferencePortHead(llm, llm_feature_size=d_llm, max_object_num=80, topk_pairs=topk_pairs, max_new_tokens=max_new_tokens)
+    synth.init_parameters(head, synth.WEIGHT_SEED, skip_prefixes=("language_model",))
+    return head.eval()
+
+
+def _cpu_pairs_pass(head, inputs, n_sample):
+    """-> (ordered pairs covered, seconds) of the reference call pattern on the first n_sample pair queries of one image."""
     wl = synth.WORKLOADS[WORKLOAD]
     t0 = time.perf_counter()
-    head.relation_queries(inputs, pair_subset=list(range(n_sample)))
+    head.relation_queries(inputs, pair_subset=None if n_sample >= wl.queries else list(range(n_sample)))
     dt = time.perf_counter() - t0
-    pairs = n_sample * wl.ordered_pairs / wl.queries
-    return pairs, dt
+    return min(n_sample, wl.queries) * wl.ordered_pairs / wl.queries, dt
 
 
-def cpu_baseline(n_sample=96, repeats=1):
-    from tests.helpers import build_port_head
+def _cpu_tokens_pass(budget_s=25.0, max_pairs=4, new_tokens=32):
+    """relation-tokens/s of the reference's per-pair batch-1 ``generate`` (v4:305-312) with a random-init OPT-2.7B in fp32 on
+    the host cores: pairs are decoded one after the other until the budget is spent (cost is linear in pairs)."""
+    t0 = time.perf_counter()
+    head = _build_port(llm=synth.OPT_2P7B, topk_pairs=max_pairs, max_new_tokens=new_tokens)
+    init_s = time.perf_counter() - t0
+    n = 40
+    g = torch.Generator().manual_seed(3)
+    q = dict(object_num=n, names=[synth.object_categories[i % 133] for i in synth.object_ids(n)],
+             selected=[int(x) for x in torch.randperm(n * n, generator=g)[:max_pairs]],
+             qformer_out=torch.randn((n * n, 33, 768), generator=g))
+    done, t1 = 0, time.perf_counter()
+    for p in range(max_pairs):
+        head.decode_relations(dict(q, selected=q["selected"][p:p + 1]))
+        done += 1
+        if time.perf_counter() - t1 > budget_s:
+            break
+    dt = time.perf_counter() - t1
+    return {"value": done * new_tokens / dt, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "extrapolated": True,
+            "model_init_s": round(init_s, 1),
+            "sample": f"{done} of the 100 selected pairs of a cfg3 image x {new_tokens} new tokens, one batch-1 HF generate per pair "
+                      f"(v4:305-312) through a random-init OPT-2.7B in fp32 ({dt:.1f} s); cost is linear in pairs"}
+
+
+def cpu_baseline(n_sample=96, with_tokens=True):
     torch.set_num_threads(os.cpu_count())
-    head = build_port_head(max_object_num=80)
+    head = _build_port()
     inputs = synth.make_image_inputs(synth.WORKLOADS[WORKLOAD], 0)
-    _cpu_reference_pass(head, inputs, 8)        # warm-up
-    best = None
-    for _ in range(repeats):
-        pairs, dt = _cpu_reference_pass(head, inputs, n_sample)
-        best = dt if best is None else min(best, dt)
-    return {"value": pairs / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"first {n_sample} of 1600 pair queries of one cfg2 image through oracle/ref_port.py "
-                      f"(HF InstructBlipQFormerModel fp32, the reference's per-pair K/V call pattern; cost is linear in pairs)"}
+    _cpu_pairs_pass(head, inputs, 8)        # warm-up
+    pairs, dt = _cpu_pairs_pass(head, inputs, n_sample)
+    out = {"value": pairs / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "extrapolated": True,
+           "sample": f"first {n_sample} of 1600 pair queries of one cfg2 image through oracle/ref_port.py "
+                     f"(HF InstructBlipQFormerModel fp32, the reference's per-pair K/V call pattern; cost is linear in pairs; "
+                     f"`bench.py --impl reference` times a full image)"}
+    del head
+    if with_tokens:
+        out["relation_tokens_per_sec"] = _cpu_tokens_pass()
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from tests.helpers import build_port_head
     torch.set_num_threads(os.cpu_count())
     wl = synth.WORKLOADS[WORKLOAD]
-    head = build_port_head(max_object_num=80)
+    head = _build_port()
     inputs = synth.make_image_inputs(wl, 0)
-    n_sample = args.ref_sample
-    for _ in range(args.warmup):
-        _cpu_reference_pass(head, inputs, min(n_sample, 16))
+    t_start = time.perf_counter()
+    for _ in range(max(1, args.warmup)):
+        _cpu_pairs_pass(head, inputs, 16)
+    # one FULL image (all 1600 pair queries, what the reference executes per image) — measured, not extrapolated
+    full_pairs, full_dt = _cpu_pairs_pass(head, inputs, wl.queries)
+    # K timed steps sized to the remaining budget: each a leading subset of the same image's pair queries
+    budget = max(20.0, args.ref_budget_s - (time.perf_counter() - t_start))
+    n_sample = args.ref_sample or int(wl.queries * budget / (args.steps * full_dt))
+    n_sample = max(16, min(wl.queries, n_sample))
     t0 = time.perf_counter()
     pairs = 0.0
     for _ in range(args.steps):
-        p, _dt = _cpu_reference_pass(head, inputs, n_sample)
+        p, _dt = _cpu_pairs_pass(head, inputs, n_sample)
         pairs += p
     dt = time.perf_counter() - t0
     v = pairs / dt
-    sample = (f"each step = first {n_sample} of the 1600 pair queries of one cfg2 image through oracle/ref_port.py "
-              f"(reference call pattern on HF modules, fp32, {os.cpu_count()} threads)")
-    print(json.dumps({
+    sample = (f"each of the {args.steps} timed steps = first {n_sample} of the 1600 pair queries of one image of the workload through "
+              f"oracle/ref_port.py (reference call pattern on HF modules, fp32, {os.cpu_count()} threads); one full image "
+              f"(1600 queries) took {full_dt:.1f} s = {full_pairs / full_dt:.1f} pairs/s")
+    line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 1024x1024, 40 objects, relation-query Q-Former + existence filter (bounded sample)"},
+        "config": {"workload": WORKLOAD_DESC},
+        "extrapolated": n_sample < wl.queries,
+        "full_image": {"value": full_pairs / full_dt, "unit": UNIT, "seconds": full_dt, "queries": wl.queries, "extrapolated": False},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if not args.no_llm:
+        del head
+        line["relation_tokens_per_sec"] = _cpu_tokens_pass(budget_s=20.0, max_pairs=3)
+    print(json.dumps(line))
     return 0
 
 
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
-# DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_ncu_gemm_final2.md: mean of
-# dram read + write over the eight layer-0 GEMM launches of one cfg2 image = 290 MB; profiles/r1_ncu_xattn_final3.md:
-# the N=40 cross-attention launch, 94 MB read + 42 MB written) — per launch, like `achieved`.
-NCU_TRAFFIC_BYTES = {"gemm_bf16": 290e6, "xattn_pairs": 136e6}
+def _pin(inp):
+    inp["mask_features"] = inp["mask_features"].pin_memory()
+    inp["object_info"][0]["pan_results"] = inp["object_info"][0]["pan_results"].to(torch.int32).pin_memory()
+    return inp
 
 
-def _llm_leg(dev, head, hidden, steps):
-    """cfg3's LLM leg (a9-a10): top-100 pairs x 32 new tokens through a random-init OPT-2.7B, batched prefill + decode."""
-    from transformers import OPTConfig, OPTForCausalLM
-    from openpsg_b200.llm import build_llm_engine
-    wl = synth.WORKLOADS["cfg3"]
+class Runner:
+    """Barrier / device-timer plumbing shared by the legs (time = max over ranks of the CUDA-event time)."""
+
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, repeats=1):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+
+def _llm_legs(run: Runner, rank, world, steps, peaks):
+    """BASELINE configs 3 and 5 end to end through the head (a2-a10) with a random-init OPT-2.7B on every rank, and the
+    decode-only leg [a9..a10] of one cfg3 image (rank 0 profile)."""
+    from openpsg_b200 import ops
+    dev = run.dev
     t0 = time.perf_counter()
-    with torch.device(dev):
-        lm = OPTForCausalLM(OPTConfig(**synth.OPT_2P7B)).eval()
-        proj = torch.nn.Linear(768, synth.OPT_2P7B["hidden_size"])
-    eng = build_llm_engine(lm, proj, dev)
-    weight_bytes = 2.0 * sum(p.numel() for n, p in lm.named_parameters() if "embed_positions" not in n)
-    del lm
-    torch.cuda.empty_cache()
+    head = synth.build_synthetic_head(llm=synth.OPT_2P7B, max_object_num=80, topk_pairs=100, max_new_tokens=32, device=dev,
+                                      llm_on_device=True)
+    head.repack(dev)
+    weight_bytes = 2.0 * sum(p.numel() for n, p in head.language_model.named_parameters() if "embed_positions" not in n)
     init_s = time.perf_counter() - t0
-    k, T, T_new = wl.topk_pairs, 17, wl.max_new_tokens
+    out = {}
+    for name in ("cfg3", "cfg5"):
+        wl = synth.WORKLOADS[name]
+        mine = sharding.shard_indices(LLM_IMAGES, rank, world)
+        host = [_pin(synth.make_image_inputs(wl, i)) for i in mine]
+        toks = []
+
+        def grab(h):
+            toks.append(h.last_generation.tokens.to("cpu", non_blocking=True))
+
+        def step():
+            toks.clear()
+            res = head.forward_batch(host, on_result=grab)
+            assert len(res) == len(host) and all(set(r) == {"rel_pred", "rel_score"} for r in res)
+        for _ in range(3):                     # first sighting eager, second captures the graphs, third replays
+            step()
+        ms = run.timed(step, steps) / steps
+        torch.cuda.synchronize()
+        k, t_new = wl.topk_pairs, wl.max_new_tokens
+        h2d = sum(i["mask_features"].numel() * 4 + i["object_info"][0]["pan_results"].numel() * 4 for i in host)
+        out["e2e_" + name] = {
+            "workload": f"{name}: {LLM_IMAGES} images ({wl.num_objects} objects, {wl.queries} pair queries each) sharded over {world} "
+                        f"rank(s); host feature map -> relation queries -> top-{k} filter -> batched OPT-2.7B prefill + {t_new}-token "
+                        "greedy decode -> [sub, obj, rel] triples, through head.forward_batch",
+            "ms_per_step": ms, "images_per_sec": LLM_IMAGES / (ms * 1e-3),
+            "object_pairs_per_sec": LLM_IMAGES * wl.ordered_pairs / (ms * 1e-3),
+            "relation_tokens_per_sec": LLM_IMAGES * k * t_new / (ms * 1e-3),
+            "h2d_bytes_per_step_per_rank": h2d, "d2h_bytes_per_step_per_rank": len(host) * k * t_new * 4,
+            "tokens_checksum_rank0": int(sum(int(t.long().sum()) for t in toks))}
+    # decode-only leg (a9-a10) of one cfg3 image on this rank: device time of engine.generate on resident Q-Former rows
+    wl = synth.WORKLOADS["cfg3"]
+    head(synth.inputs_to(synth.make_image_inputs(wl, 0), dev), is_generation=False)
+    hidden = head.last_output.hidden.clone()
+    k, T, t_new = wl.topk_pairs, 17, wl.max_new_tokens
     g = torch.Generator().manual_seed(5)
     sel = torch.randperm(hidden.shape[0] // 33, generator=g)[:k].to(torch.int32).to(dev)
     ids = torch.randint(4, synth.OPT_2P7B["vocab_size"], (k, T), generator=g).to(torch.int32).to(dev)
     lens = torch.randint(14, T + 1, (k, 1), generator=g)
     mask = (torch.arange(T)[None, :] >= (T - lens)).to(torch.int32).to(dev)            # left padded
-    for _ in range(2):
-        out = eng.generate(hidden, sel, ids, mask, max_new_tokens=T_new)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        out = eng.generate(hidden, sel, ids, mask, max_new_tokens=T_new)
-        toks = out.tokens.cpu()                                                         # D2H of the generated ids
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    peaks = _peaks()
-    # per-kernel device time of one image (eager launches, an event pair around every C-ABI call)
-    from openpsg_b200 import ops
+    eng = head._llm_engine
+    for _ in range(3):
+        gen = eng.generate(hidden, sel, ids, mask, max_new_tokens=t_new)
+    ms = run.timed(lambda: eng.generate(hidden, sel, ids, mask, max_new_tokens=t_new).tokens.cpu(), steps) / steps
+    toks = gen.tokens.cpu()
     ops.profile_begin()
-    eng.generate(hidden, sel, ids, mask, max_new_tokens=T_new)
+    eng.generate(hidden, sel, ids, mask, max_new_tokens=t_new)
     prof = ops.profile_end()
-    # HBM floor of the decode: every step streams the weights once for the whole batch (+ the KV cache, ignored here)
-    decode_bytes = (T_new - 1) * weight_bytes
-    return {"value": k * T_new / (ms * 1e-3), "unit": "tokens/s", "ms_per_image": ms,
-            "config": {"workload": "cfg3 LLM leg: top-100 pairs x 32 new tokens, 49-token embedded prompt, random-init OPT-2.7B "
-                                   "(32 layers, d 2560), batched prefill + greedy decode as one CUDA graph", "pairs": k,
-                       "new_tokens": T_new},
-            "tokens_checksum": int(toks.long().sum()), "model_init_s": init_s,
-            "kernel_ms_per_image": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-            "kernel_launches_per_image": {k: v["n"] for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-            "roofline": {"bound": "hbm", "achieved": decode_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": decode_bytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
-                         "note": "weight bytes of the 31 decode steps / whole prefill+decode time (lower bound on achieved)"}}
+    # HBM floor of the decode: every step streams the weights once for the whole batch, plus the KV cache it has so far
+    kv_bytes = sum(2.0 * 2 * eng.w.n_layers * k * (32 + T + s) * eng.w.d for s in range(1, t_new))
+    decode_bytes = (t_new - 1) * weight_bytes + kv_bytes
+    out["relation_tokens_per_sec"] = {
+        "value": world * k * t_new / (ms * 1e-3), "unit": "tokens/s", "ms_per_image": ms, "n_gpus": world,
+        "config": {"workload": "cfg3 LLM leg (a9-a10): top-100 pairs x 32 new tokens, 49-token embedded prompt, random-init OPT-2.7B "
+                               "(32 layers, d 2560), batched prefill + greedy decode as one CUDA graph; one image per rank",
+                   "pairs": k, "new_tokens": t_new},
+        "tokens_checksum": int(toks.long().sum()), "model_init_s": init_s,
+        "kernel_ms_per_image": {n: round(v["ms"], 3) for n, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        "kernel_launches_per_image": {n: v["n"] for n, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        "roofline": {"bound": "hbm", "achieved": decode_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": decode_bytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                     "note": "(weights + KV cache bytes of the 31 decode steps) / whole prefill+decode time of one image "
+                             "(a lower bound on the achieved rate: the prefill is inside the time, not inside the bytes)"}}
+    del head
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
     import torch.distributed as dist
     from openpsg_b200 import ops
-    from tests.helpers import build_product_head
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,16 +331,20 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    run = Runner(dev, world)
     wl = synth.WORKLOADS[WORKLOAD]
-    ips = args.images_per_step
-    head = build_product_head(max_object_num=wl.num_objects, topk_pairs=20, device=dev)
+    head = synth.build_synthetic_head(max_object_num=wl.num_objects, topk_pairs=20, device=dev)
     head.repack(dev)
-    # this rank's images: global image index = rank * ips + i  (image sharding)
-    host_inputs = [synth.make_image_inputs(wl, rank * ips + i) for i in range(ips)]
-    for inp in host_inputs:   # pinned host copies for the e2e leg
-        inp["mask_features"] = inp["mask_features"].pin_memory()
-        inp["object_info"][0]["pan_results"] = inp["object_info"][0]["pan_results"].to(torch.int32).pin_memory()
+    # this rank's images (image sharding)
+    if args.scaling == "strong":
+        total_images = args.total_images
+        mine = sharding.shard_indices(total_images, rank, world)
+    else:
+        total_images = args.images_per_rank * world
+        mine = [rank * args.images_per_rank + i for i in range(args.images_per_rank)]
+    host_inputs = [_pin(synth.make_image_inputs(wl, i)) for i in mine]
     dev_inputs = [synth.inputs_to(inp, dev) for inp in host_inputs]
+    ips = len(mine)
 
     def step_resident():
         for inp in dev_inputs:
@@ -252,38 +371,8 @@ def run_ours(args):
         outs = head.forward_batch(host_inputs * steps, on_result=grab)
         assert len(outs) == ips * steps and k[0] == ips * steps
 
-    def timed_call(fn):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
     def step_e2e_single():   # the reference-facing batch-1 call with host tensors, no prefetch
         return [(head(inp), head.last_output.topk.cpu())[1] for inp in host_inputs]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -291,6 +380,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+
     # value: the images of K steps, resident in HBM, through ONE forward_batch call (host-side parsing of image i+1
     # overlaps the kernels of image i; separate head(inputs) calls read the object ids back with a stream-wide sync
     # per image, as the reference does, and are reported as ms_per_step_separate_calls)
@@ -299,10 +389,10 @@ def run_ours(args):
         assert len(outs) == ips * steps
     run_resident(2)
     l0 = ops.launch_count
-    ms = timed_call(lambda: run_resident(args.steps))
+    ms = run.timed(lambda: run_resident(args.steps))
     launches = ops.launch_count - l0
-    ms_separate = timed(step_resident, args.steps) / args.steps
-    pairs_per_step = wl.ordered_pairs * ips * world
+    ms_separate = run.timed(step_resident, args.steps) / args.steps
+    pairs_per_step = wl.ordered_pairs * total_images
     value = pairs_per_step * args.steps / (ms * 1e-3)
 
     for _ in range(2):
@@ -310,52 +400,80 @@ def run_ours(args):
     run_e2e_stream(2)
     # K steps timed twice; the host->device copies ride a PCIe link whose rate is not ours alone (observed: the same
     # command 284 k and 585 k pairs/s minutes apart on one box), so both passes are reported and `value` is the better one
-    e2e_runs = [timed_call(lambda: run_e2e_stream(args.steps)) for _ in range(2)]
+    e2e_runs = [run.timed(lambda: run_e2e_stream(args.steps)) for _ in range(2)]
     ms_e2e = min(e2e_runs)
     e2e_value = pairs_per_step * args.steps / (ms_e2e * 1e-3)
-    ms_e2e_calls = timed(step_e2e, args.steps) / args.steps
-    ms_e2e_single = timed(step_e2e_single, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    ms_e2e_calls = run.timed(step_e2e, args.steps) / args.steps
+    ms_e2e_single = run.timed(step_e2e_single, max(2, args.steps // 2)) / max(2, args.steps // 2)
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(inp["mask_features"].numel() * 4 + inp["object_info"][0]["pan_results"].numel() *
               inp["object_info"][0]["pan_results"].element_size() + wl.num_objects * 4 +
               2 * wl.queries * 16 * 4 for inp in host_inputs)
     d2h = ips * 20 * 4          # the selected pair indices of every image
 
+    # per-image result records gathered over the ranks (after the timed region): selected pairs + existence mask of every
+    # image; the digest must be the same for every N (PatchEmbed's split-K reduction is deterministic)
+    def record(j):
+        head(dev_inputs[j])
+        o = head.last_output
+        return (o.topk.cpu().tolist(), hashlib.sha1(o.exist_mask.cpu().numpy().tobytes()).hexdigest())
+    local_records = {i: record(j) for j, i in enumerate(mine)}
+    records = sharding.gather_by_index(local_records, total_images)
+    results_sha1 = hashlib.sha1(json.dumps(records).encode()).hexdigest()
+
     # per-kernel device times: same step, eager launches (CUDA graphs off while profiling) with an event pair around
     # every C-ABI call on the launching stream
-    prof_steps = max(2, min(args.steps, 5))
+    prof_steps = max(1, min(args.steps, 3))
     step_resident()
     ops.profile_begin()
-    timed(step_resident, prof_steps)
+    run.timed(step_resident, prof_steps)
     prof = ops.profile_end()
+    del dev_inputs, res_slots
+    torch.cuda.empty_cache()
 
-    llm = None
-    if rank == 0 and world == 1 and not args.no_llm:
-        llm = _llm_leg(dev, head, head.last_output.hidden.clone(), max(2, args.steps // 4))
+    peaks = _peaks()
+    llm = None if args.no_llm else _llm_legs(run, rank, world, max(2, args.steps // 5), peaks)
 
     if rank == 0:
-        peaks = _peaks()
-        g = prof.get("gemm_bf16", {"ms": 0.0, "flops": 0.0, "n": 1})
-        x = prof.get("xattn_pairs", {"ms": 0.0, "flops": 0.0, "n": 1})
+        traffic = _traffic()
+        g = prof.get("gemm_bf16", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 1})
+        x = prof.get("xattn_pairs", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 1})
         total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
 
         def roof(name, rec, peak_tf):
             ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12 if rec["ms"] > 0 else 0.0
+            t = traffic.get(name, {})
             return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": NCU_TRAFFIC_BYTES.get(name), "launches": rec["n"], "avg_launch_ms": rec["ms"] / max(1, rec["n"]),
+                    "traffic": t.get("dram_bytes_per_launch"), "traffic_source": t.get("source"),
+                    "launches": rec["n"], "avg_launch_ms": rec["ms"] / max(1, rec["n"]),
                     "algorithmic_flops_per_launch": rec["flops"] / max(1, rec["n"]),
                     "share_of_kernel_time": rec["ms"] / total_kernel_ms, "peak_source": peaks["src"] + " (sustained bf16 cuBLAS)"}
+
+        def roof_hbm(name):
+            rec = prof.get(name)
+            if not rec or rec["ms"] <= 0:
+                return None
+            ach = rec["bytes"] / (rec["ms"] * 1e-3) / 1e9
+            t = traffic.get(name, {})
+            return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                    "traffic": t.get("dram_bytes_per_launch"), "traffic_source": t.get("source"), "launches": rec["n"],
+                    "avg_launch_ms": rec["ms"] / max(1, rec["n"]), "algorithmic_bytes_per_launch": rec["bytes"] / max(1, rec["n"])}
+        scaling_note = (f"strong: {total_images} images per step over {world} rank(s), image i on rank i % N" if args.scaling == "strong"
+                        else f"weak: {args.images_per_rank} images per rank per step")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"cfg2 x {ips} images per rank per step (cfg4 sharding): 1024x1024, 40 objects, "
-                                   "1600 pair queries, 256 image tokens, relation-query Q-Former + existence filter (a2-a8)",
-                       "images_per_step_per_rank": ips, "parallelism": f"image-shard x{world}",
-                       "l2": "inputs larger than L2 (4 x 67 MB feature maps + >100 MB activations per image)",
+            "config": {"workload": WORKLOAD_DESC if args.scaling == "strong" and total_images == TOTAL_IMAGES else
+                       f"cfg2 x {total_images} images per step: 1024x1024, 40 objects, 1600 pair queries, 256 image tokens, "
+                       "relation-query Q-Former + existence filter (a2-a8)",
+                       "images_per_step": total_images, "images_per_step_this_rank": ips, "parallelism": f"image-shard x{world}",
+                       "scaling": scaling_note,
+                       "l2": "inputs larger than L2 (67 MB feature map + >100 MB of activations per image)",
                        "launch": "one CUDA-graph replay per image (per-kernel times below come from an eager pass of the same step)"},
             "ms_per_step_separate_calls": ms_separate,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world if args.scaling == "weak" else
+                    h2d * total_images // max(1, ips), "d2h_bytes_per_step": d2h * total_images // max(1, ips),
                     "ms_per_step": ms_e2e / args.steps,
                     "ms_per_step_both_passes": [m / args.steps for m in e2e_runs],
                     "api": "one head.forward_batch(stream of host input dicts) call over the K steps' images: pinned-host H2D "
@@ -366,14 +484,18 @@ def run_ours(args):
                     "value_single_calls": pairs_per_step / (ms_e2e_single * 1e-3)},
             "gpu_launches": launches,
             "clocks": clocks,
+            "results": {"images": total_images, "sha1": results_sha1,
+                        "note": "digest of every image's selected pairs + existence mask, gathered over the ranks; independent of N"},
             "roofline": roof("gemm_bf16", g, peaks["tf_sustained"]),
             "roofline_xattn": roof("xattn_pairs", x, peaks["tf_sustained"]),
+            "roofline_hbm_kernels": {n: r for n in ("layernorm_bf16", "pair_mask_bits", "exist_filter_topk", "patch_im2col",
+                                                    "qformer_embed_ln") if (r := roof_hbm(n))},
             "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
         }
         if llm is not None:
-            line["relation_tokens_per_sec"] = llm
+            line.update(llm)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(with_tokens=not args.no_llm)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -383,13 +505,17 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images-per-step", type=int, default=4)
-    ap.add_argument("--ref-sample", type=int, default=64)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): cfg4's 32 images per step split over the ranks; weak: --images-per-rank per rank")
+    ap.add_argument("--total-images", type=int, default=TOTAL_IMAGES)
+    ap.add_argument("--images-per-rank", "--images-per-step", type=int, default=4, dest="images_per_rank")
+    ap.add_argument("--ref-sample", type=int, default=0, help="pair queries per timed reference step (0 = fit --ref-budget-s)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-llm", action="store_true", help="skip the cfg3 LLM leg (relation_tokens_per_sec)")
+    ap.add_argument("--no-llm", action="store_true", help="skip the cfg3 / cfg5 LLM legs (relation_tokens_per_sec)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

@@ -145,6 +145,13 @@ int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* shared_query_qkv
  * They depend only on (bits, pair_index, N, B, n_query, L) — one build per image serves every head of both
  * Q-Former layers — and let the kernel apply the mask as an additive bias inside the QK^T MMA.  With
  * bias_tiles == NULL the self-contained (slower) kernel that ORs the bit rows per score row is used. */
+/* Key order for opsg_xattn_pairs: perm_out int32 [L] lists the image tokens sorted by owning object (the first object of
+ * `bits` whose mask holds the token; unowned tokens last; stable), bits_sorted_out [num_objects, words] are the same masks
+ * in that order.  Softmax attention does not depend on the order of the keys (HF:ib:499-536 as called at v4:183-184); with
+ * an object's keys contiguous, most 16-key chunks are invisible to a 32-row group of pair queries and K5 skips their
+ * exponentials.  Project K / V from the token rows gathered by perm_out and pass bits_sorted_out to the two calls below. */
+int opsg_token_order(const uint32_t* bits, int words, int num_objects, int L, int32_t* perm_out, uint32_t* bits_sorted_out,
+                     void* stream);
 size_t opsg_xattn_bias_tiles_bytes(int B, int n_query);
 int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                           int n_query, int L, void* tiles_out, void* stream);
@@ -163,13 +170,27 @@ int opsg_exist_filter_topk(const opsg_bf16* x, int ld_x, int B, int d, const flo
                            float threshold, int k, float* logits_out, float* probs_out, uint8_t* mask_out,
                            int32_t* topk_out, void* stream);
 
-/* ---- a11 / K11: mask mean-pool + pair gather ------------------------------------------------------
- * Replaces detectors/openseed_relation.py:454-468 (obj = sum(feat*mask)/(sum(mask)+1e-8)) and :502-527
- * (pair = cat(obj[i], obj[j])).  feat fp32 [C, h, w]; label int32 [h, w] = object slot (0..N-1) owning
- * the pixel or -1; count_scratch fp32 [N] (caller-provided workspace); obj_out fp32 [N, C];
- * pair_out fp32 [N*N, 2C] (may be NULL). */
-int opsg_mask_pool_pairs(const float* feat, int channels, int h, int w, const int32_t* label, int num_objects,
-                         float* count_scratch, float* obj_out, float* pair_out, void* stream);
+/* ---- a11 / K11: per-mask feature pooling + pair gather ---------------------------------------------
+ * Replaces detectors/openseed_relation.py:441-527 (same code in mask2former_relation.py:275-295 and
+ * mask2former_relation_v2.py:392-465).
+ * opsg_mask_pool_labels: the reference's mask chain (:441-462: mask = pan == id -> nearest to img_shape -> zero pad to
+ *   pad_shape -> nearest to the feature size) for ALL objects at once: label_out int32 [feat_h, feat_w] = index of the
+ *   first listed object whose id equals the source pixel, num_objects where nobody does (padding, unlisted ids);
+ *   rep_out int32 [num_objects] = first object with the same id (objects repeating an id share its mask).
+ * opsg_mask_pool_pairs: obj = sum(feat * mask) / (sum(mask) + 1e-8) (:466-468), optional class embedding
+ *   cls_table[cls_ids[o]] added (cls_mode 1) or concatenated (2) (:469-474), optional background feature
+ *   sum(feat * (1 - mask)) / (sum(1 - mask) + 1e-8) added (:487-493); pair = cat(obj[i], obj[j]) (:502-527).
+ *   feat fp32 [C, h, w] is read once; no atomics, fixed summation order (bit-reproducible).  obj_out fp32 [N, C'] with
+ *   C' = C (+ cls_dim when concatenating), pair_out fp32 [N*N, 2C'] or NULL; workspace of
+ *   opsg_mask_pool_workspace_bytes bytes.  num_objects <= 255. */
+int opsg_mask_pool_labels(const int32_t* pan, int pan_h, int pan_w, int img_h, int img_w, int pad_h, int pad_w, int feat_h,
+                          int feat_w, const int32_t* obj_ids, int num_objects, int32_t* label_out, int32_t* rep_out,
+                          void* stream);
+size_t opsg_mask_pool_workspace_bytes(int channels, int h, int w, int num_objects);
+int opsg_mask_pool_pairs(const float* feat, int channels, int h, int w, const int32_t* label, const int32_t* rep,
+                         int num_objects, const float* cls_table, const int32_t* cls_ids, int cls_dim, int cls_mode,
+                         int use_background, float* workspace, size_t workspace_bytes, float* obj_out, float* pair_out,
+                         void* stream);
 
 /* ---- a9-a10 / K9-K10: LLM prefix assembly, attention, greedy step ---------------------------------
  * opsg_gather_rows_bf16: out[r] = src[idx[r]] for contiguous row blocks (pair_feature[si], v4:294).

@@ -35,11 +35,14 @@ SIGNATURES = {
     "opsg_qformer_embed_ln": [P, I, P, I, I, P, I, P, P, P, F, I, P, P],
     "opsg_layernorm_bf16": [P, P, P, F, P, I, I, P],
     "opsg_self_attn_small": [P, P, P, I, I, I, I, I, I, P, P],
+    "opsg_token_order": [P, I, I, I, P, P, P],
     "opsg_xattn_bias_tiles_bytes": [I, I],
     "opsg_xattn_bias_tiles": [P, I, P, I, I, I, I, P, P],
     "opsg_xattn_pairs": [P, P, I, P, I, P, I, P, I, I, I, I, I, I, P, P, P],
     "opsg_exist_filter_topk": [P, I, I, I, P, P, F, I, P, P, P, P, P],
-    "opsg_mask_pool_pairs": [P, I, I, I, P, I, P, P, P, P],
+    "opsg_mask_pool_labels": [P, I, I, I, I, I, I, I, I, P, I, P, P, P],
+    "opsg_mask_pool_workspace_bytes": [I, I, I, I],
+    "opsg_mask_pool_pairs": [P, I, I, I, P, P, I, P, P, I, I, I, P, ctypes.c_size_t, P, P, P],
     "opsg_gather_rows_bf16": [P, I, P, I, P, P],
     "opsg_embed_gather": [P, I, P, P, P, I, P, I, P],
     "opsg_llm_build_prefix": [P, I, I, I, P, P, I, P, P, I, I, P, P],
@@ -82,7 +85,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = (c_char_p if name == "opsg_last_error_string"
-                      else ctypes.c_size_t if name in ("opsg_xattn_bias_tiles_bytes", "opsg_gemm_streamk_workspace_bytes")
+                      else ctypes.c_size_t if name in ("opsg_xattn_bias_tiles_bytes", "opsg_gemm_streamk_workspace_bytes",
+                                                       "opsg_mask_pool_workspace_bytes")
                       else c_int)
     _lib = lib
     return lib

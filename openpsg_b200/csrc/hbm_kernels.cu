@@ -1,6 +1,6 @@
 // HBM-bound integer / byte / elementwise kernels of the relation-head path: pair-mask bits (K2), PatchEmbed
 // operand re-layout (K1 input side), Q-Former embeddings + LayerNorm (K7), LayerNorm, existence filter +
-// exact top-k (K8), mask mean-pool + pair gather (K11), row/embedding gathers, argmax.
+// exact top-k (K8), row/embedding gathers, argmax.  (K11, mask mean-pool + pair gather: mask_pool.cu.)
 // Coalesced 16-byte accesses, warp-shuffle reductions, no tensor cores (none of this is GEMM-shaped).
 #include "common.cuh"
 #include "host_util.h"
@@ -265,58 +265,6 @@ __global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict_
   if (i < B) atomicAdd(&s_rank[lane], rank);
   __syncthreads();
   if (warp == 0 && i < B && s_rank[lane] < k) topk[s_rank[lane]] = i;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K11: mask mean-pool (single pass over the feature map) + pair gather.
-// Warp = 32 consecutive pixels x all channels; lanes sharing a label are reduced with shuffles and the
-// leader adds into obj_sum[label, c].
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mask_pool_accum_kernel(const float* __restrict__ feat, int C, int hw,
-                                                              const int32_t* __restrict__ label, int N,
-                                                              float* __restrict__ obj_sum, float* __restrict__ count) {
-  pdl_wait_then_trigger();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int c_per_block_y = (C + gridDim.y - 1) / gridDim.y;
-  const int c_begin = blockIdx.y * c_per_block_y;
-  const int c_end = min(C, c_begin + c_per_block_y);
-  const int pix = warp * 32 + lane;
-  if (warp * 32 >= hw) return;
-  int lbl = (pix < hw) ? label[pix] : -1;
-  if (lbl >= N) lbl = -1;
-  // distinct labels inside the warp (typically 1-3 for panoptic regions)
-  uint32_t remaining = __ballot_sync(0xffffffffu, lbl >= 0);
-  while (remaining) {
-    const int leader = __ffs(remaining) - 1;
-    const int cur = __shfl_sync(0xffffffffu, lbl, leader);
-    const uint32_t group = __ballot_sync(0xffffffffu, lbl == cur);
-    remaining &= ~group;
-    if (blockIdx.y == 0 && lane == leader) atomicAdd(count + cur, static_cast<float>(__popc(group)));
-    const bool mine = (lbl == cur);
-    for (int c = c_begin; c < c_end; ++c) {
-      float v = (mine && pix < hw) ? __ldg(feat + static_cast<size_t>(c) * hw + pix) : 0.f;
-      v = warp_sum(v);
-      if (lane == leader) atomicAdd(obj_sum + static_cast<size_t>(cur) * C + c, v);
-    }
-  }
-}
-
-__global__ void mask_pool_normalize_kernel(float* __restrict__ obj, const float* __restrict__ count, int N, int C) {
-  pdl_wait_then_trigger();
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(N) * C) return;
-  obj[idx] = obj[idx] / (count[idx / C] + 1e-8f);
-}
-
-__global__ void pair_concat_kernel(const float* __restrict__ obj, int N, int C, float* __restrict__ pair_out) {
-  pdl_wait_then_trigger();
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(N) * N * 2 * C) return;
-  const int col = static_cast<int>(idx % (2 * C));
-  const long long p = idx / (2 * C);
-  const int i = static_cast<int>(p / N), j = static_cast<int>(p % N);
-  pair_out[idx] = col < C ? obj[static_cast<size_t>(i) * C + col] : obj[static_cast<size_t>(j) * C + (col - C)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -620,34 +568,6 @@ extern "C" int opsg_exist_filter_topk(const opsg_bf16* x, int ld_x, int B, int d
   if (k > 0) {
     launch_kernel(topk_rank_kernel, ceil_div(B, 32), 256, 0, ST(stream), logits_out, B, k, topk_out);
     OPSG_CHECK_LAUNCH("topk_rank_kernel");
-  }
-  return OPSG_OK;
-}
-
-extern "C" int opsg_mask_pool_pairs(const float* feat, int channels, int h, int w, const int32_t* label, int num_objects,
-                                    float* count_scratch, float* obj_out, float* pair_out, void* stream) {
-  int rc = opsg_device_check();
-  if (rc) return rc;
-  OPSG_CHECK_ARG(feat && label && obj_out && count_scratch, "mask_pool_pairs: null pointer");
-  OPSG_CHECK_ARG(channels > 0 && h > 0 && w > 0 && num_objects > 0, "mask_pool_pairs: bad shape");
-  rc = check_cuda(cudaMemsetAsync(obj_out, 0, static_cast<size_t>(num_objects) * channels * sizeof(float), ST(stream)),
-                  "cudaMemsetAsync(obj_out)");
-  if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(count_scratch, 0, static_cast<size_t>(num_objects) * sizeof(float), ST(stream)),
-                  "cudaMemsetAsync(count)");
-  if (rc) return rc;
-  const int hw = h * w;
-  const int warps = ceil_div(hw, 32);
-  dim3 grid(ceil_div(static_cast<long long>(warps) * 32, 256), channels >= 64 ? 8 : 1);
-  launch_kernel(mask_pool_accum_kernel, grid, 256, 0, ST(stream), feat, channels, hw, label, num_objects, obj_out, count_scratch);
-  OPSG_CHECK_LAUNCH("mask_pool_accum_kernel");
-  launch_kernel(mask_pool_normalize_kernel, ceil_div(static_cast<long long>(num_objects) * channels, 256), 256, 0, ST(stream), 
-      obj_out, count_scratch, num_objects, channels);
-  OPSG_CHECK_LAUNCH("mask_pool_normalize_kernel");
-  if (pair_out) {
-    const long long total = static_cast<long long>(num_objects) * num_objects * 2 * channels;
-    launch_kernel(pair_concat_kernel, ceil_div(total, 256), 256, 0, ST(stream), obj_out, num_objects, channels, pair_out);
-    OPSG_CHECK_LAUNCH("pair_concat_kernel");
   }
   return OPSG_OK;
 }

@@ -43,7 +43,7 @@ extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int l
 
 namespace opsg {
 
-constexpr int kXaThreads = 640;
+constexpr int kXaThreads = 512;
 constexpr int kXaKeys = 256;       // max keys (one N=256 MMA)
 constexpr int kXaHd = 64;
 constexpr int kXaPvN = 80;         // PV MMA N: 64 value dims + 1 ones row (row sum) + 15 zero rows
@@ -52,7 +52,7 @@ constexpr int kXaSlots = 8;        // tile-local pair slots carried by the mask 
 struct XattnParams {
   const uint8_t* tiles;      // [m_tiles][kXaTileBytes] A_aug | B_aug in core-matrix order (xattn_bias_tiles_kernel)
   const uint8_t* row_flags;  // [m_tiles * 128] 1 = the row's pair has an empty union mask (uniform attention)
-  const uint8_t* chunk_vis;  // [m_tiles * 4] per 32-row quarter: bit c = some row of the quarter sees a key of chunk c
+  const uint16_t* chunk_vis; // [m_tiles * 4] per 32-row quarter: bit c = some row of the quarter sees a key of 16-key chunk c
   int L, num_heads, d_model;
   int rows;          // B * n_query
   int m_tiles;
@@ -135,6 +135,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   uint32_t v;
@@ -152,7 +166,7 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
 __global__ void __launch_bounds__(256)
 xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int32_t* __restrict__ pair_index,
                         int num_objects, int num_pairs, int n_query, int L, int rows, uint8_t* __restrict__ tiles,
-                        uint8_t* __restrict__ row_flags, uint8_t* __restrict__ chunk_vis) {
+                        uint8_t* __restrict__ row_flags, uint16_t* __restrict__ chunk_vis) {
   pdl_wait_then_trigger();
   const int mt = blockIdx.x;
   const int t = threadIdx.x;
@@ -181,16 +195,17 @@ xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int3
     s_any[t] = any;
   }
   __syncthreads();
-  if (t < 4) {   // key chunks (32 keys) in which any row of 32-row quarter t sees at least one key
+  if (t < 4) {   // 16-key chunks in which any row of 32-row quarter t sees at least one key
     uint32_t vis = 0;
     for (int r = t * 32; r < t * 32 + 32; ++r) {
       const int row = mt * 128 + r;
       if (row >= rows) break;
       const int slot = row / n_query - first_pair;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) vis |= (s_union[slot][w] != 0u) ? (1u << w) : 0u;
+      for (int w = 0; w < 8; ++w)
+        vis |= ((s_union[slot][w] & 0xFFFFu) ? (1u << (2 * w)) : 0u) | ((s_union[slot][w] >> 16) ? (2u << (2 * w)) : 0u);
     }
-    chunk_vis[mt * 4 + t] = static_cast<uint8_t>(vis);
+    chunk_vis[mt * 4 + t] = static_cast<uint16_t>(vis);
   }
   uint8_t* tile = tiles + static_cast<size_t>(mt) * kXaTileBytes;
   {  // B_aug: thread = key
@@ -223,9 +238,62 @@ xattn_bias_tiles_kernel(const uint32_t* __restrict__ bits, int words, const int3
   }
 }
 
-// POLY_MOD: 0 = every exponential on the MUFU; m > 0 = elements with (index % m == 1) use ex2_poly.
-// PREFETCH : tcgen05.ld of the next 32-column chunk in flight while the current one is processed.
-template <int POLY_MOD, bool PREFETCH>
+
+// ------------------------------------------------------------------------------------------------
+// Key order for K5: image tokens sorted by owning object (owner = first listed object whose mask holds the token; tokens
+// nobody owns go last), stable in the token index.  Attention is invariant under a permutation of the keys, and with the
+// keys of an object contiguous a pair's visible keys are two short runs, so most 16-key chunks of a 32-row quarter are
+// invisible and skip the softmax work entirely (the panoptic map partitions the image: an object owns ~L/N tokens).
+// One CTA of 256 threads (L <= 256): perm[new] = old token index; bits_sorted = the object masks in the new order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+token_order_kernel(const uint32_t* __restrict__ bits, int words, int num_objects, int L, int32_t* __restrict__ perm,
+                   uint32_t* __restrict__ bits_sorted) {
+  pdl_wait_then_trigger();
+  __shared__ int s_owner[kXaKeys];
+  __shared__ int s_perm[kXaKeys];
+  const int t = threadIdx.x;
+  int owner = 0x7fffffff;
+  if (t < L) {
+    owner = num_objects;
+    for (int o = 0; o < num_objects; ++o)
+      if ((bits[static_cast<size_t>(o) * words + (t >> 5)] >> (t & 31)) & 1u) { owner = o; break; }
+  }
+  s_owner[t] = owner;
+  __syncthreads();
+  if (t < L) {
+    int rank = 0;
+    for (int u = 0; u < L; ++u) {
+      const int ou = s_owner[u];
+      rank += (ou < owner || (ou == owner && u < t)) ? 1 : 0;
+    }
+    s_perm[rank] = t;
+    perm[rank] = t;
+  }
+  __syncthreads();
+  const int src = t < L ? s_perm[t] : 0;
+  const int lane = t & 31, w = t >> 5;
+  for (int o = 0; o < num_objects; ++o) {
+    const bool on = t < L && ((bits[static_cast<size_t>(o) * words + (src >> 5)] >> (src & 31)) & 1u);
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if (lane == 0 && w < words) bits_sorted[static_cast<size_t>(o) * words + w] = word;
+  }
+}
+
+// POLY_MOD: 0 = every exponential on the MUFU; m > 0 = elements with (index % m == 1) use ex2_poly (FMA / ALU pipes).
+//
+// v4 warp roles (512 threads, <= 128 registers each):
+//   warp 0      TMA producer
+//   warp 1      QK^T issuer   (its own in-order queue: never blocked behind a PV that waits for P)
+//   warp 2      TMEM allocator, then PV issuer (waits for P in two 128-key halves: the first 8 PV MMAs run under the
+//               exponentials of the second half)
+//   warp 3      per-head mean of V
+//   warps 4-7   softmax of TMEM buffer 0, warps 8-11 of buffer 1: thread = one score row x all 256 keys (no cross-thread
+//               max exchange); P overwrites the consumed scores in place, ascending, columns [0, 128)
+//   warps 12-15 epilogue of BOTH buffers: O / rowsum out of TMEM columns [128, 209) (frees the buffer for the QK^T of
+//               unit i+2 as soon as it has been read), uniform rows, bf16, swizzled staging, TMA store
+// so a softmax warp goes straight from the exponentials of unit i to the scores of unit i+2.
+template <int POLY_MOD>
 __global__ void __launch_bounds__(kXaThreads, 1)
 xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmO,
@@ -237,21 +305,20 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sQ = smem + XaSmem::kOffQ;
   uint8_t* sO = smem + XaSmem::kOffO;
   uint8_t* sAug = smem + XaSmem::kOffAug;                                    // [stage] A_aug | B_aug
-  float* sMax = reinterpret_cast<float*>(smem + XaSmem::kOffMax);            // [buffer][half][row]
   float* sVbar = reinterpret_cast<float*>(smem + XaSmem::kOffVbar);          // [head parity][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XaSmem::kOffBar);
   uint64_t* q_full = bars;          // [2]  Q tile + mask-bias tiles of a unit
   uint64_t* q_empty = bars + 2;     // [2]
   uint64_t* s_full = bars + 4;      // [2]
   uint64_t* p_ready = bars + 6;     // [2]
-  uint64_t* o_full = bars + 8;      // [2]
-  uint64_t* s_free = bars + 10;     // [2]
-  uint64_t* vbar_ready = bars + 12; // [2]
-  uint64_t* k_full = bars + 14;
-  uint64_t* k_empty = bars + 15;
-  uint64_t* v_full = bars + 16;
-  uint64_t* v_empty = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* o_full = bars + 10;     // [2]
+  uint64_t* s_free = bars + 12;     // [2]
+  uint64_t* vbar_ready = bars + 14; // [2]
+  uint64_t* k_full = bars + 16;
+  uint64_t* k_empty = bars + 17;
+  uint64_t* v_full = bars + 18;
+  uint64_t* v_empty = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -265,9 +332,9 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
       mbar_init(&s_full[b], 1);
-      mbar_init(&p_ready[b], 256);
+      mbar_init(&p_ready[b], 128);
       mbar_init(&o_full[b], 1);
-      mbar_init(&s_free[b], 256);
+      mbar_init(&s_free[b], 128);
       mbar_init(&vbar_ready[b], 1);
     }
     mbar_init(k_full, 1); mbar_init(k_empty, 1);
@@ -298,6 +365,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int u_end = min(p.total_units, u_begin + per);
   const int n_units = max(0, u_end - u_begin);
   const int head0 = u_begin / p.m_tiles;
+  auto head_of = [&](int j) { return (u_begin + j) / p.m_tiles; };
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, elect.sync lane issues) =====================
@@ -335,22 +403,20 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, elect.sync lane issues tcgen05.mma + commits) =====================
+    // ===================== QK^T issuer =====================
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kXaKeys);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kXaPvN);
     const uint32_t lbo = p.desc_swap ? 256u : 128u, sbo = p.desc_swap ? 128u : 256u;
-    int k_waits = 0, v_waits = 0, head_qk = -1, head_pv = -1;
-    auto head_of = [&](int j) { return (u_begin + j) / p.m_tiles; };
-    auto issue_qk = [&](int j) {
+    int k_waits = 0, cur_head = -1;
+    for (int j = 0; j < n_units; ++j) {
       const int head = head_of(j);
       const int b = j & 1;
-      if (head != head_qk) {
+      if (head != cur_head) {
         mbar_wait(k_full, k_waits & 1);
         ++k_waits;
-        head_qk = head;
+        cur_head = head;
       }
       mbar_wait(&q_full[b], (j >> 1) & 1);
-      mbar_wait(&s_free[b], ((j >> 1) & 1) ^ 1);     // O of unit j-2 has been read out of this buffer
+      mbar_wait(&s_free[b], ((j >> 1) & 1) ^ 1);     // P of unit j-2 consumed by its PV and O read out of this buffer
       tc_fence_after();
       const bool release_k = j + 1 < n_units && head_of(j + 1) != head;
       if (elect_one_sync()) {
@@ -368,46 +434,43 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (release_k) tc_commit(k_empty);
       }
       __syncwarp();
-    };
-    auto issue_pv = [&](int i) {
+    }
+  } else if (warp == 2) {
+    // ===================== PV issuer =====================
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kXaPvN);
+    int v_waits = 0, cur_head = -1;
+    for (int i = 0; i < n_units; ++i) {
       const int head = head_of(i);
       const int b = i & 1;
-      if (head != head_pv) {
+      const uint32_t parity = (i >> 1) & 1;
+      if (head != cur_head) {
         mbar_wait(v_full, v_waits & 1);
         ++v_waits;
-        head_pv = head;
+        cur_head = head;
       }
-      mbar_wait(&p_ready[b], (i >> 1) & 1);          // P_b complete in TMEM, S_b fully consumed
-      tc_fence_after();
       const bool release_v = i + 1 < n_units && head_of(i + 1) != head;
+      const uint32_t pa = tmem_base + b * 256;          // P: key k-step k in columns [8k, 8k + 8)
+      const uint32_t od = tmem_base + b * 256 + 128;    // O: 80 fp32 columns [128, 208)
+      const uint64_t v_desc = umma_desc_k_sw128(smem_u32(sV));
+      mbar_wait(&p_ready[b], parity);                  // P complete in TMEM, S fully consumed
+      tc_fence_after();
       if (elect_one_sync()) {
         if (p.trace && blockIdx.x == 0) p.trace[i * 8 + 1] = clock64();
-        const uint32_t pa = tmem_base + b * 256;        // P: keys 0-127 in columns [0,64), keys 128-255 in [192,256)
-        const uint32_t od = tmem_base + b * 256 + 64;   // O: 80 fp32 columns [64,144)
-        const uint64_t v_desc = umma_desc_k_sw128(smem_u32(sV));
 #pragma unroll
         for (int k = 0; k < kXaKeys / 16; ++k)
-          umma_ts(od, pa + (k < 8 ? k * 8 : 192 + (k - 8) * 8),
-                  v_desc + (k >> 2) * (XaSmem::kVBlk >> 4) + (k & 3) * 2, idesc_pv, k > 0 ? 1u : 0u);
+          umma_ts(od, pa + k * 8, v_desc + (k >> 2) * (XaSmem::kVBlk >> 4) + (k & 3) * 2, idesc_pv, k > 0 ? 1u : 0u);
         tc_commit(&o_full[b]);
         if (release_v) tc_commit(v_empty);
       }
       __syncwarp();
-    };
-    if (n_units > 0) issue_qk(0);
-    if (n_units > 1) issue_qk(1);
-    for (int i = 0; i < n_units; ++i) {
-      issue_pv(i);
-      if (i + 2 < n_units) issue_qk(i + 2);
     }
   } else if (warp == 3) {
     // ===================== per-head mean of V over the L real keys (rows whose pair mask is empty) =====================
     // This warp READS the resident V tile, so it is a second consumer of it: the producer may only overwrite V with the
-    // next head's tile after the head's last PV MMA *and* this warp have released it (v_empty counts both).  (Without
-    // that, a CTA whose first unit is the last tile of a head reloaded V while the mean was still being summed.)
+    // next head's tile after the head's last PV MMA *and* this warp have released it (v_empty counts both).
     int v_waits = 0, cur_head = -1;
     for (int i = 0; i < n_units; ++i) {
-      const int head = (u_begin + i) / p.m_tiles;
+      const int head = head_of(i);
       if (head == cur_head) continue;
       cur_head = head;
       const int hs = head - head0;
@@ -433,174 +496,245 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&vbar_ready[hs & 1]);
-        // release V if another head follows in this CTA's range (mirrors the MMA warp's release_v condition)
-        const int last_head = (u_begin + n_units - 1) / p.m_tiles;
+        const int last_head = head_of(n_units - 1);
         if (head != last_head) mbar_arrive(v_empty);
       }
     }
-  } else if (warp >= 4) {
-    // ===================== softmax + epilogue warps =====================
-    const int sw = warp - 4;
-    const int b = sw >> 3;                               // TMEM buffer = unit parity
-    const int half = (sw >> 2) & 1;                      // which 128 keys of the row
+  } else if (warp < 12) {
+    // ===================== softmax warps: thread = one row x 256 keys =====================
+    const int b = (warp - 4) >> 2;                       // TMEM buffer = unit parity
     const int q = warp & 3;                              // TMEM lane quarter of this warp (warp id % 4)
-    const int r = q * 32 + lane;                         // row inside the tile
     const uint32_t tS = tmem_base + b * 256 + (static_cast<uint32_t>(q * 32) << 16);
-    const bool elected = (sw & 7) == 0 && lane == 0;
-    uint8_t* stage_row = sO + b * XaSmem::kOst + r * 128;
-    float* my_max = sMax + (b * 2 + half) * 128 + r;
-    const float* other_max = sMax + (b * 2 + (half ^ 1)) * 128 + r;
-
+    const bool tr_thread = blockIdx.x == 0 && q == 0 && lane == 0;
+    auto exp2_sel = [&](float x, int idx) -> float {
+      if (POLY_MOD > 0 && (idx % (POLY_MOD > 0 ? POLY_MOD : 1)) == 1) return ex2_poly(x);
+      return ex2_approx(x);
+    };
     for (int i = b; i < n_units; i += 2) {
       const uint32_t parity = (i >> 1) & 1;
-      const int u = u_begin + i;
-      const int head = u / p.m_tiles, mt = u % p.m_tiles;
-      const bool uniform = __ldg(p.row_flags + mt * 128 + r) != 0;     // empty pair mask -> uniform attention (HF finfo.min)
-
+      const int mt = (u_begin + i) % p.m_tiles;
+      // 16-key chunks in which no row of this warp sees a key contribute exact zeros: no tcgen05.ld, no max, no
+      // exponentials -- their P columns are just cleared.  The MMAs stay dense.  (The image tokens reach this kernel
+      // sorted by owning object, opsg_token_order, so a pair's visible keys are two short contiguous runs.)
+      const uint32_t vis = __ldg(p.chunk_vis + mt * 4 + q);
       mbar_wait(&s_full[b], parity);
       tc_fence_after();
-      const bool tr = p.trace && blockIdx.x == 0 && (sw & 7) == 0 && lane == 0;
+      const bool tr = p.trace && tr_thread;
       if (tr) p.trace[i * 8 + 2] = clock64();
-      auto exp2_sel = [&](float x, int idx) -> float {
-        if (POLY_MOD > 0 && (idx % (POLY_MOD > 0 ? POLY_MOD : 1)) == 1) return ex2_poly(x);
-        return ex2_approx(x);
-      };
-      float mx;
-      if constexpr (PREFETCH) {
-        // pass 1: row max of the biased scores over this thread's 128 keys, then across the two halves.
-        // tcgen05.ld of chunk c+1 is in flight while chunk c is reduced (two register sets).
-        uint32_t va[32], vb[32];
+
+      const uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (__popc(vis) <= 4) {
+        // ---- sparse rows (the common case with keys in object order): the <= 4 visible chunks are read ONCE into
+        // registers (one TMEM round trip), max and exponentials run from registers, every invisible P chunk is cleared
+        // with the widest store that does not touch a visible one ----
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        uint32_t rem = vis;
+        const int c0 = rem ? __ffs(rem) - 1 : -1; rem &= rem - 1;
+        const int c1 = rem ? __ffs(rem) - 1 : -1; rem &= rem - 1;
+        const int c2 = rem ? __ffs(rem) - 1 : -1; rem &= rem - 1;
+        const int c3 = rem ? __ffs(rem) - 1 : -1;
+        if (c0 >= 0) tmem_ld16(tS + c0 * 16, r0);
+        if (c1 >= 0) tmem_ld16(tS + c1 * 16, r1);
+        if (c2 >= 0) tmem_ld16(tS + c2 * 16, r2);
+        if (c3 >= 0) tmem_ld16(tS + c3 * 16, r3);
+        tmem_ld_wait();
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        tmem_ld32(tS + (half * 4) * 32, va);
+        auto max16 = [&](const uint32_t (&v)[16]) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&cur)[32] = (c & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-          tmem_ld_wait();
-          if (c + 1 < 4) tmem_ld32(tS + (half * 4 + c + 1) * 32, nxt);
-          else tmem_ld32(tS + (half * 4 + (half ? 3 : 0)) * 32, nxt);      // first chunk of pass 2 (nxt == va)
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            m0 = fmaxf(m0, __uint_as_float(cur[j]));
-            m1 = fmaxf(m1, __uint_as_float(cur[j + 1]));
-            m2 = fmaxf(m2, __uint_as_float(cur[j + 2]));
-            m3 = fmaxf(m3, __uint_as_float(cur[j + 3]));
-          }
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        *my_max = mx;
-        named_bar_sync(1 + b, 256);
-        mx = fmaxf(mx, *other_max);
-        const float mxs = mx * p.scale_log2e;
-        // pass 2: p = exp2(s*scale - max*scale); packed bf16 P overwrites consumed score columns
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = half ? 3 - cc : cc;                // half 1 walks its chunks downwards (in-place safety)
-          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
-          tmem_ld_wait();
-          if (cc + 1 < 4) tmem_ld32(tS + (half * 4 + (half ? 2 - cc : cc + 1)) * 32, nxt);
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = exp2_sel(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2e, -mxs), 2 * j);
-            const float e1 = exp2_sel(fmaf(__uint_as_float(cur[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
-            pk[j] = pack_bf16x2(e0, e1);
-          }
-          tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
-        }
-      } else {
-        // Key chunks in which no row of this warp sees a key (chunk_vis) contribute exact zeros: no tcgen05.ld, no max,
-        // no exponentials — their P columns are just cleared.  Panoptic masks are compact, so on the cfg2 images about
-        // half of the chunks fall away; the MMAs stay dense.
-        const uint32_t vis4 = (static_cast<uint32_t>(__ldg(p.chunk_vis + mt * 4 + q)) >> (half * 4)) & 0xFu;
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (!((vis4 >> c) & 1u)) continue;
-          uint32_t v[32];
-          tmem_ld32(tS + (half * 4 + c) * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 16; j += 4) {
             m0 = fmaxf(m0, __uint_as_float(v[j]));
             m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
             m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
             m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
           }
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        *my_max = mx;
-        named_bar_sync(1 + b, 256);
-        mx = fmaxf(mx, *other_max);
-        if (mx == -INFINITY) mx = 0.f;                     // no visible key in either half: uniform / out-of-range rows only
+        };
+        if (c0 >= 0) max16(r0);
+        if (c1 >= 0) max16(r1);
+        if (c2 >= 0) max16(r2);
+        if (c3 >= 0) max16(r3);
+        float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        if (mx == -INFINITY) mx = 0.f;                   // no visible key: uniform / out-of-range rows only
         const float mxs = mx * p.scale_log2e;
         if (tr) p.trace[i * 8 + 3] = clock64();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = half ? 3 - cc : cc;                // half 1 walks its chunks downwards (in-place safety)
-          uint32_t pk[16];
-          if ((vis4 >> c) & 1u) {
-            uint32_t v[32];
-            tmem_ld32(tS + (half * 4 + c) * 32, v);
-            tmem_ld_wait();
+        // every score this thread needs is in registers: the P columns may be written in any order
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float e0 = exp2_sel(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs), 2 * j);
-              const float e1 = exp2_sel(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
-              pk[j] = pack_bf16x2(e0, e1);
-            }
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t v4 = (vis >> (4 * g)) & 0xFu;
+          if (v4 == 0u) {
+            uint32_t z[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = 0u;
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+                "%25, %26, %27, %28, %29, %30, %31, %32};"
+                ::"r"(tS + g * 32), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]), "r"(z[4]), "r"(z[5]), "r"(z[6]), "r"(z[7]),
+                "r"(z[8]), "r"(z[9]), "r"(z[10]), "r"(z[11]), "r"(z[12]), "r"(z[13]), "r"(z[14]), "r"(z[15]), "r"(z[16]),
+                "r"(z[17]), "r"(z[18]), "r"(z[19]), "r"(z[20]), "r"(z[21]), "r"(z[22]), "r"(z[23]), "r"(z[24]), "r"(z[25]),
+                "r"(z[26]), "r"(z[27]), "r"(z[28]), "r"(z[29]), "r"(z[30]), "r"(z[31])
+                : "memory");
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            for (int cc = 0; cc < 4; ++cc)
+              if (!((v4 >> cc) & 1u)) tmem_st8(tS + (4 * g + cc) * 8, zero8);
           }
-          tmem_st16(tS + (half ? 192 : 0) + c * 16, pk);
         }
+        auto exp_store_r = [&](const uint32_t (&v)[16], int c) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e0 = exp2_sel(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs), 2 * j);
+            const float e1 = exp2_sel(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          tmem_st8(tS + c * 8, pk);
+        };
+        if (c0 >= 0) exp_store_r(r0, c0);
+        if (c1 >= 0) exp_store_r(r1, c1);
+        if (c2 >= 0) exp_store_r(r2, c2);
+        if (c3 >= 0) exp_store_r(r3, c3);
+      } else {
+      // ---- pass 1: row max of the biased scores over the visible chunks (next chunk's tcgen05.ld in flight) ----
+      uint32_t va[16], vb[16];
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      auto max16 = [&](const uint32_t (&v)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[j]));
+          m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+          m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+        }
+      };
+      {
+        uint32_t rem = vis;
+        int c = rem ? __ffs(rem) - 1 : -1;
+        rem &= rem - 1;
+        if (c >= 0) tmem_ld16(tS + c * 16, va);
+        while (c >= 0) {
+          tmem_ld_wait();
+          int cn = rem ? __ffs(rem) - 1 : -1;
+          rem &= rem - 1;
+          if (cn >= 0) tmem_ld16(tS + cn * 16, vb);
+          max16(va);
+          c = cn;
+          if (c < 0) break;
+          tmem_ld_wait();
+          cn = rem ? __ffs(rem) - 1 : -1;
+          rem &= rem - 1;
+          if (cn >= 0) tmem_ld16(tS + cn * 16, va);
+          max16(vb);
+          c = cn;
+        }
+      }
+      float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      if (mx == -INFINITY) mx = 0.f;                     // no visible key: uniform / out-of-range rows only
+      const float mxs = mx * p.scale_log2e;
+      if (tr) p.trace[i * 8 + 3] = clock64();
+
+      // ---- pass 2: p = exp2(s*scale - max*scale), packed bf16 P in place over consumed score columns ----
+      auto exp_store = [&](const uint32_t (&v)[16], int c) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float e0 = exp2_sel(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs), 2 * j);
+          const float e1 = exp2_sel(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs), 2 * j + 1);
+          pk[j] = pack_bf16x2(e0, e1);
+        }
+        tmem_st8(tS + c * 8, pk);
+      };
+      // Chunks are walked in ascending order: P chunk c lands on columns [8c, 8c + 8), inside score chunk c / 2 <= c,
+      // which is either already in registers or invisible; the prefetched chunk lies above.
+      {
+        uint32_t rem = vis;
+        int nxt = rem ? __ffs(rem) - 1 : 16;             // next visible chunk (16 = none)
+        rem &= rem - 1;
+        if (nxt < 16) tmem_ld16(tS + nxt * 16, va);
+        bool use_a = true;
+#pragma unroll 1
+        for (int c = 0; c < 16; ++c) {
+          if (c == nxt) {
+            tmem_ld_wait();
+            nxt = rem ? __ffs(rem) - 1 : 16;
+            rem &= rem - 1;
+            if (use_a) {
+              if (nxt < 16) tmem_ld16(tS + nxt * 16, vb);
+              exp_store(va, c);
+            } else {
+              if (nxt < 16) tmem_ld16(tS + nxt * 16, va);
+              exp_store(vb, c);
+            }
+            use_a = !use_a;
+          } else {
+            tmem_st8(tS + c * 8, zero8);
+          }
+        }
+      }
       }
       tmem_st_wait();
       tc_fence_before();
-      if (tr) p.trace[i * 8 + 4] = clock64();
       mbar_arrive(&p_ready[b]);
-
-      // epilogue: this thread's 32 output columns: O / rowsum -> bf16 -> swizzled staging row -> TMA store
+      if (tr) p.trace[i * 8 + 4] = clock64();
+    }
+  } else {
+    // ===================== epilogue warps (both buffers): O / rowsum -> bf16 -> swizzled staging -> TMA store =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const bool elected = warp == 12 && lane == 0;
+    for (int i = 0; i < n_units; ++i) {
+      const int b = i & 1;
+      const uint32_t parity = (i >> 1) & 1;
+      const int u = u_begin + i;
+      const int head = u / p.m_tiles, mt = u % p.m_tiles;
+      const bool uniform = __ldg(p.row_flags + mt * 128 + r) != 0;     // empty pair mask -> uniform attention (HF finfo.min)
+      const uint32_t tO = tmem_base + b * 256 + 128 + (static_cast<uint32_t>(q * 32) << 16);
       mbar_wait(&o_full[b], parity);
       tc_fence_after();
-      if (tr) p.trace[i * 8 + 5] = clock64();
-      uint32_t o[32];
-      tmem_ld32(tS + 64 + half * 32, o);
-      const uint32_t osum = tmem_ld1(tS + 64 + 64);
+      if (p.trace && blockIdx.x == 0 && elected) p.trace[i * 8 + 5] = clock64();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tO, o0);
+      tmem_ld32(tO + 32, o1);
+      const uint32_t osum = tmem_ld1(tO + 64);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[b]);                           // buffer may be overwritten by QK^T of unit i+2
-      float f[32];
       const float inv = 1.f / __uint_as_float(osum);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(o[j]) * inv;
+      uint8_t* stage_row = sO + b * XaSmem::kOst + r * 128;
+      if (elected) tma_store_wait_read<1>();             // the store of unit i-2 has drained this staging tile
+      named_bar_sync(1, 128);
       if (uniform) {
         const int hs = head - head0;
         mbar_wait(&vbar_ready[hs & 1], (hs >> 1) & 1);
-        const float* vb = sVbar + (hs & 1) * 64 + half * 32;
+        const float* vb = sVbar + (hs & 1) * 64;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = vb[j];
-      }
-      if (elected) tma_store_wait_read<0>();             // previous unit's store has drained this staging tile
-      named_bar_sync(3 + b, 256);
+        for (int g = 0; g < 8; ++g) {
+          uint4 u4;
+          u4.x = pack_bf16x2(vb[g * 8 + 0], vb[g * 8 + 1]);
+          u4.y = pack_bf16x2(vb[g * 8 + 2], vb[g * 8 + 3]);
+          u4.z = pack_bf16x2(vb[g * 8 + 4], vb[g * 8 + 5]);
+          u4.w = pack_bf16x2(vb[g * 8 + 6], vb[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(stage_row + ((g ^ (r & 7)) * 16)) = u4;
+        }
+      } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 u4;
-        u4.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-        u4.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-        u4.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-        u4.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-        *reinterpret_cast<uint4*>(stage_row + (((half * 4 + g) ^ (r & 7)) * 16)) = u4;
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t (&o)[32] = g < 4 ? o0 : o1;
+          const int j = (g & 3) * 8;
+          uint4 u4;
+          u4.x = pack_bf16x2(__uint_as_float(o[j + 0]) * inv, __uint_as_float(o[j + 1]) * inv);
+          u4.y = pack_bf16x2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+          u4.z = pack_bf16x2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+          u4.w = pack_bf16x2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(stage_row + ((g ^ (r & 7)) * 16)) = u4;
+        }
       }
       fence_proxy_async_smem();
-      named_bar_sync(5 + b, 256);
+      named_bar_sync(2, 128);
       if (elected) {
         tma_store_2d(sO + b * XaSmem::kOst, &tmO, head * kXaHd, mt * 128);
         tma_store_commit();
+        if (p.trace && blockIdx.x == 0) p.trace[i * 8 + 6] = clock64();
       }
-      if (tr) p.trace[i * 8 + 6] = clock64();
     }
     if (elected) tma_store_wait_all<0>();
   }
@@ -621,10 +755,23 @@ static long long* g_xattn_trace = nullptr;
 // debug hook (not part of the public header): device buffer of >= 8 * units_per_cta int64 for per-unit clock stamps
 extern "C" void opsg_debug_xattn_trace(void* dev_buffer) { g_xattn_trace = reinterpret_cast<long long*>(dev_buffer); }
 
+extern "C" int opsg_token_order(const uint32_t* bits, int words, int num_objects, int L, int32_t* perm_out,
+                                uint32_t* bits_sorted_out, void* stream) {
+  int rc = opsg_device_check();
+  if (rc) return rc;
+  OPSG_CHECK_ARG(bits && perm_out && bits_sorted_out, "token_order: null pointer");
+  OPSG_CHECK_ARG(num_objects > 0 && L > 0 && words >= (L + 31) / 32 && words <= 8, "token_order: bad shape");
+  if (L > kXaKeys) return set_error(OPSG_E_UNSUPPORTED, "token_order: L=%d image tokens > %d unsupported", L, kXaKeys);
+  launch_kernel(token_order_kernel, 1, 256, 0, reinterpret_cast<cudaStream_t>(stream), bits, words, num_objects, L, perm_out,
+                bits_sorted_out);
+  OPSG_CHECK_LAUNCH("token_order_kernel");
+  return OPSG_OK;
+}
+
 extern "C" size_t opsg_xattn_bias_tiles_bytes(int B, int n_query) {
   if (B <= 0 || n_query <= 0) return 0;
   const size_t m_tiles = (static_cast<size_t>(B) * n_query + 127) / 128;
-  return m_tiles * (kXaTileBytes + 128 + 16);       // tiles | row flags | chunk visibility (4 bytes per tile, padded)
+  return m_tiles * (kXaTileBytes + 128 + 16);       // tiles | row flags | chunk visibility (4 x uint16 per tile, padded)
 }
 
 extern "C" int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
@@ -643,7 +790,7 @@ extern "C" int opsg_xattn_bias_tiles(const uint32_t* bits, int words, const int3
   uint8_t* tiles = reinterpret_cast<uint8_t*>(tiles_out);
   launch_kernel(xattn_bias_tiles_kernel, m_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       bits, words, pair_index, num_objects, B, n_query, L, rows, tiles, tiles + static_cast<size_t>(m_tiles) * kXaTileBytes,
-      tiles + static_cast<size_t>(m_tiles) * (kXaTileBytes + 128));
+      reinterpret_cast<uint16_t*>(tiles + static_cast<size_t>(m_tiles) * (kXaTileBytes + 128)));
   OPSG_CHECK_LAUNCH("xattn_bias_tiles_kernel");
   return OPSG_OK;
 }
@@ -680,11 +827,12 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmO, ctx_out, (uint64_t)rows, (uint64_t)d_model, (uint64_t)d_model, 128, 64);
   if (rc) return rc;
+  // OPSG_XATTN_VARIANT (tuning switch): 0 = every exponential on the MUFU; 1 / 2 / 3 = every 4th / 3rd / 2nd exponential as
+  // an FMA-pipe polynomial
   static const int variant = [] { const char* e = getenv("OPSG_XATTN_VARIANT"); return e ? atoi(e) : 0; }();
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const XattnParams);
-  static const KernelFn kernels[] = {xattn_pairs_kernel<0, false>, xattn_pairs_kernel<0, true>, xattn_pairs_kernel<3, false>,
-                                     xattn_pairs_kernel<3, true>, xattn_pairs_kernel<4, false>, xattn_pairs_kernel<6, false>};
-  const KernelFn kernel = kernels[(variant >= 0 && variant < 6) ? variant : 0];
+  static const KernelFn kernels[] = {xattn_pairs_kernel<0>, xattn_pairs_kernel<4>, xattn_pairs_kernel<3>, xattn_pairs_kernel<2>};
+  const KernelFn kernel = kernels[(variant >= 0 && variant < 4) ? variant : 0];
   static bool configured = false;
   if (!configured) {
     for (KernelFn f : kernels) {
@@ -698,7 +846,7 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   p.m_tiles = (rows + 127) / 128;
   p.tiles = reinterpret_cast<const uint8_t*>(bias_tiles);
   p.row_flags = p.tiles + static_cast<size_t>(p.m_tiles) * kXaTileBytes;
-  p.chunk_vis = p.tiles + static_cast<size_t>(p.m_tiles) * (kXaTileBytes + 128);
+  p.chunk_vis = reinterpret_cast<const uint16_t*>(p.tiles + static_cast<size_t>(p.m_tiles) * (kXaTileBytes + 128));
   p.L = L; p.num_heads = num_heads; p.d_model = d_model;
   p.rows = rows; p.total_units = p.m_tiles * num_heads;
   p.desc_swap = desc_swap;

@@ -255,6 +255,18 @@ def self_attn_small(qkv, text_mask, B, n_query, T, num_heads, head_dim, text_que
     return out
 
 
+def token_order(bits: torch.Tensor, L: int):
+    """K5 key order: (perm int32 [L] = image tokens sorted by owning object, the object masks in that order)."""
+    _cuda(bits, torch.int32, "bits")
+    assert bits.is_contiguous()
+    perm = torch.empty((L,), dtype=torch.int32, device=bits.device)
+    bits_sorted = torch.empty_like(bits)
+    with _timed("token_order", 0.0, 8.0 * bits.numel() + 4.0 * L):
+        _lib.check(_lib.load().opsg_token_order(_ptr(bits), bits.shape[1], bits.shape[0], L, _ptr(perm), _ptr(bits_sorted), _stream()))
+    _count()
+    return perm, bits_sorted
+
+
 def xattn_bias_tiles(bits, num_objects, B, n_query, L, pair_index=None):
     """K5 operand prep (once per image): pair masks as tensor-core bias tiles -> uint8 buffer for xattn_pairs."""
     _cuda(bits, torch.int32, "bits")
@@ -301,17 +313,44 @@ def exist_filter_topk(x: torch.Tensor, ld_x: int, B: int, d: int, w: torch.Tenso
     return logits, probs, mask, topk[:k]
 
 
-def mask_pool_pairs(feat: torch.Tensor, label: torch.Tensor, num_objects: int, with_pairs: bool = True):
-    """K11: feat fp32 [C,h,w], label int32 [h,w] -> (obj [N,C], pair [N*N,2C] or None)."""
+def mask_pool_labels(pan: torch.Tensor, img_hw, pad_hw, feat_hw, obj_ids: torch.Tensor):
+    """K11 stage 1: (label int32 [h, w] = owning object slot or N, rep int32 [N]) from the panoptic map."""
+    pan = _cuda(pan, torch.int32, "pan").contiguous()
+    obj_ids = _cuda(obj_ids, torch.int32, "obj_ids").contiguous()
+    n = obj_ids.numel()
+    label = torch.empty((int(feat_hw[0]), int(feat_hw[1])), dtype=torch.int32, device=pan.device)
+    rep = torch.empty((n,), dtype=torch.int32, device=pan.device)
+    with _timed("mask_pool_labels", 0.0, 8.0 * label.numel()):
+        _lib.check(_lib.load().opsg_mask_pool_labels(_ptr(pan), pan.shape[0], pan.shape[1], int(img_hw[0]), int(img_hw[1]),
+                                                    int(pad_hw[0]), int(pad_hw[1]), int(feat_hw[0]), int(feat_hw[1]),
+                                                    _ptr(obj_ids), n, _ptr(label), _ptr(rep), _stream()))
+    _count()
+    return label, rep
+
+
+def mask_pool_pairs(feat: torch.Tensor, label: torch.Tensor, num_objects: int, with_pairs: bool = True, rep=None,
+                    cls_table: Optional[torch.Tensor] = None, cls_ids: Optional[torch.Tensor] = None, cls_mode: str = "none",
+                    use_background: bool = False):
+    """K11: feat fp32 [C,h,w], label int32 [h,w] (ops.mask_pool_labels) -> (obj [N,C'], pair [N*N,2C'] or None)."""
     _cuda(feat, torch.float32, "feat"); _cuda(label, torch.int32, "label")
+    feat, label = feat.contiguous(), label.contiguous()
     C, h, w = feat.shape
-    obj = torch.empty((num_objects, C), dtype=torch.float32, device=feat.device)
-    cnt = torch.empty((num_objects,), dtype=torch.float32, device=feat.device)
-    pair = torch.empty((num_objects * num_objects, 2 * C), dtype=torch.float32, device=feat.device) if with_pairs else None
+    mode = {"none": 0, "add": 1, "cat": 2}[cls_mode]
+    cls_dim = 0
+    if mode:
+        _cuda(cls_table, torch.float32, "cls_table"); _cuda(cls_ids, torch.int32, "cls_ids")
+        cls_table, cls_ids = cls_table.contiguous(), cls_ids.contiguous()
+        cls_dim = cls_table.shape[1]
+    Co = C + (cls_dim if mode == 2 else 0)
+    lib = _lib.load()
+    ws = torch.empty(lib.opsg_mask_pool_workspace_bytes(C, h, w, num_objects), dtype=torch.uint8, device=feat.device)
+    obj = torch.empty((num_objects, Co), dtype=torch.float32, device=feat.device)
+    pair = torch.empty((num_objects * num_objects, 2 * Co), dtype=torch.float32, device=feat.device) if with_pairs else None
     with _timed("mask_pool_pairs", 0.0, 4.0 * feat.numel() + 4.0 * label.numel()):
-        _lib.check(_lib.load().opsg_mask_pool_pairs(_ptr(feat.contiguous()), C, h, w, _ptr(label.contiguous()), num_objects,
-                                                   _ptr(cnt), _ptr(obj), _ptr(pair), _stream()))
-    _count(3 if with_pairs else 2)
+        _lib.check(lib.opsg_mask_pool_pairs(_ptr(feat), C, h, w, _ptr(label), _ptr(rep), num_objects, _ptr(cls_table if mode else None),
+                                            _ptr(cls_ids if mode else None), cls_dim, mode, int(use_background), _ptr(ws), ws.numel(),
+                                            _ptr(obj), _ptr(pair), _stream()))
+    _count(4 if with_pairs else 3)
     return obj, pair
 
 

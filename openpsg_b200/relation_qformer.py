@@ -262,8 +262,12 @@ class RelationQueryTransformer:
                                         inter)
 
         bits = ops.pair_mask_bits(pan, img_hw, pad_hw, (th, tw), obj_ids)       # K2
-        bias_tiles = ops.xattn_bias_tiles(bits, N, B, N_QUERY, L, pair_index)    # K5 mask operand tiles (both layers)
+        # K5 sees the image tokens sorted by owning object (attention does not depend on the key order; contiguous
+        # objects make most 16-key chunks invisible to a group of pair queries, whose exponentials are then skipped)
+        perm, bits_k = ops.token_order(bits, L)
+        bias_tiles = ops.xattn_bias_tiles(bits_k, N, B, N_QUERY, L, pair_index)  # K5 mask operand tiles (both layers)
         X = self.image_tokens(feat)                                              # K1  [L,256]
+        Xk = ops.gather_rows(X, X.shape[1], perm)                                # key-order copy for the K / V projections
         h = ops.qformer_embed_ln(w.query, input_ids, w.word_emb, w.pos_emb, w.emb_ln[0], w.emb_ln[1], LN_EPS)   # K7
         RQ = B * N_QUERY
         if inter is not None:
@@ -272,9 +276,9 @@ class RelationQueryTransformer:
         for li, lw in enumerate(w.layers):
             last = li == len(w.layers) - 1
             # K3: per-image K and V^T for this layer's cross-attention (shared by all pairs)
-            kc = ops.gemm(X, lw["w_ck"], lw["b_ck"])                             # [L, d]
+            kc = ops.gemm(Xk, lw["w_ck"], lw["b_ck"])                            # [L, d]
             vt = self._vt_buffer(d, L, Lp, dev)
-            ops.gemm(lw["w_cv"], X, lw["b_cv"], bias_along_m=True, out=vt[:, :L])  # V^T [d, L]
+            ops.gemm(lw["w_cv"], Xk, lw["b_cv"], bias_along_m=True, out=vt[:, :L])  # V^T [d, L]
             # self-attention over the 33 + T rows of every pair
             if li == 0 and self.share_query_rows and T > 0:
                 # Layer 0: the 33 query rows of every pair are the same LN(query tokens) (v4:158-159 expands them B times
@@ -294,7 +298,7 @@ class RelationQueryTransformer:
             hq = h1[:RQ]
             # K5: masked pair x image cross-attention on the query rows
             qc = ops.gemm(hq, lw["w_cq"], lw["b_cq"])
-            cx = ops.xattn_pairs(qc, kc, vt, bits, N, B, N_QUERY, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index,
+            cx = ops.xattn_pairs(qc, kc, vt, bits_k, N, B, N_QUERY, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index,
                                  bias_tiles=bias_tiles)
             pre = ops.gemm(cx, lw["w_co"], lw["b_co"], residual=hq)
             hq2 = ops.layernorm(pre, lw["ln_cross"][0], lw["ln_cross"][1], LN_EPS)
@@ -336,8 +340,10 @@ class RelationQueryTransformer:
         th, tw = feat.shape[-2] // w.patch, feat.shape[-1] // w.patch
         L = th * tw
         bits = ops.pair_mask_bits(pan, img_hw, pad_hw, (th, tw), obj_ids)
-        bias_tiles = ops.xattn_bias_tiles(bits, N, B, N_QUERY, L, pair_index)
+        perm, bits_k = ops.token_order(bits, L)
+        bias_tiles = ops.xattn_bias_tiles(bits_k, N, B, N_QUERY, L, pair_index)
         X = self.image_tokens(feat)
+        Xk = ops.gather_rows(X, X.shape[1], perm)
         h = ops.qformer_embed_ln(w.query, input_ids, w.word_emb, w.pos_emb, w.emb_ln[0], w.emb_ln[1], LN_EPS)
         RQ = B * N_QUERY
         if inter is not None:
@@ -351,9 +357,9 @@ class RelationQueryTransformer:
 
         for li, lw in enumerate(w.layers):
             last = li == len(w.layers) - 1
-            kc = ops.gemm(X, lw["w_ck"], lw["b_ck"])
+            kc = ops.gemm(Xk, lw["w_ck"], lw["b_ck"])
             vt = self._vt_buffer(d, L, Lp, dev)
-            ops.gemm(lw["w_cv"], X, lw["b_cv"], bias_along_m=True, out=vt[:, :L])
+            ops.gemm(lw["w_cv"], Xk, lw["b_cv"], bias_along_m=True, out=vt[:, :L])
             # ---- self-attention block ----
             qkv_q = None
             if h_st is None and self.share_query_rows and T > 0:
@@ -386,7 +392,7 @@ class RelationQueryTransformer:
             # ---- cross-attention block (query rows) ----
             Wc, cc_, bc_ = lw["f_cq"]
             qc = ops.gemm_ln(pre1[:RQ], Wc, bc_, a_stats=st1[:RQ], a_colsum=cc_, eps=LN_EPS)
-            cx = ops.xattn_pairs(qc, kc, vt, bits, N, B, N_QUERY, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index,
+            cx = ops.xattn_pairs(qc, kc, vt, bits_k, N, B, N_QUERY, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index,
                                  bias_tiles=bias_tiles)
             st2 = zeros_stats(RQ)
             pre2 = ops.gemm_ln(cx, lw["w_co"], lw["b_co"], residual=pre1[:RQ], r_stats=st1[:RQ], r_gamma=g_self, r_beta=b_self,

@@ -311,6 +311,37 @@ def build_causal_lm(llm_config: dict):
     return OPTForCausalLM(OPTConfig(**cfg))
 
 
+WEIGHT_SEED = 0
+
+
+def build_synthetic_head(llm: Optional[dict] = None, max_object_num: int = 80, topk_pairs: int = 20, max_new_tokens: int = 16,
+                         device=None, llm_on_device: bool = False, **head_kwargs):
+    """The drop-in head with synthetic tokenizers and seeded random weights (no vocab files / checkpoints offline).
+    llm: None -> no language model (relation queries + existence filter only); a config dict (OPT_*, LLAMA_*) -> random-init
+    LLM of that shape.  ``llm_on_device`` builds the LLM directly on ``device`` with the framework's own default init
+    (multi-GB models: seconds instead of minutes; weights then differ from the CPU-seeded ones, fine for benchmarks)."""
+    from .head import RelationTransformerHeadV4
+    lm, ltok, d_llm = False, None, 4096
+    if llm is not None:
+        if llm_on_device and device is not None:
+            torch.manual_seed(WEIGHT_SEED)             # same on-device weights in every process (bench.py and the parity test)
+            with torch.device(device):
+                lm = build_causal_lm(llm).eval()
+        else:
+            lm = build_causal_lm(llm)
+        ltok = SyntheticTokenizer("llm")
+        ltok.set_vocab_size(llm["vocab_size"])
+        d_llm = llm["hidden_size"]
+    head = RelationTransformerHeadV4(llm_feature_size=d_llm, max_object_num=max_object_num, topk_pairs=topk_pairs,
+                                     max_new_tokens=max_new_tokens, qformer_tokenizer=SyntheticTokenizer("qformer"),
+                                     llm_tokenizer=ltok, language_model=lm, **head_kwargs)
+    init_parameters(head, WEIGHT_SEED, skip_prefixes=("language_model",) if (llm_on_device and llm is not None) else ())
+    head.eval()
+    if device is not None:
+        head.to(device)
+    return head
+
+
 def make_stress_inputs() -> dict:
     """Edge-case image (tests only): non-square 256x320 padded shape (L = 4x5 = 20 tokens), image smaller
     than its padded shape (zero padding aliases panoptic id 0 = 'person' instance 0, v4:420-421), a
@@ -321,3 +352,17 @@ def make_stress_inputs() -> dict:
     inp = make_image_inputs(wl, image_index=7, ensure_token_coverage=False, pan_scale=0.5, img_shape=(200, 300, 3))
     inp["object_info"][0]["object_id_list"].append(torch.tensor(77 + INSTANCE_OFFSET, dtype=torch.int32))
     return inp
+
+
+def make_mask_pool_case():
+    """Inputs of the a11 (mask-pooled object / pair embedding) golden: the stress image (image smaller than its padded shape,
+    panoptic map at half resolution, an object that owns no pixel) plus an object that repeats an id and one whose id is
+    not in the map.  -> (mask_features [1,256,h,w], pan [Hp,Wp], object ids, meta, class-embedding table [133,256])."""
+    inp = make_stress_inputs()
+    info, meta = inp["object_info"][0], dict(inp["img_metas"][0])
+    meta["ori_shape"] = tuple(info["pan_results"].shape) + (3,)
+    ids = [int(i) for i in info["object_id_list"]]
+    ids = ids + [ids[2], 2000 + 5]
+    g = torch.Generator().manual_seed(99)
+    table = torch.randn(133, 256, generator=g) * 0.5
+    return inp["mask_features"], info["pan_results"], ids, meta, table

@@ -78,7 +78,24 @@ def main(argv=None):
         print(f"{name}: {time.time() - t:.1f}s  ->  {(GOLDEN_DIR / (name + '.pt')).stat().st_size / 1e6:.2f} MB")
     make_llama_golden()
     make_train_golden()
+    make_mask_pool_golden()
     return 0
+
+
+def make_mask_pool_golden():
+    """Row a11: object embeddings produced by the reference's own statements (ref_shims.reference_object_embedding)."""
+    feat, pan, ids, meta, table = synth.make_mask_pool_case()
+    emb = torch.nn.Embedding(133, 256)
+    with torch.no_grad():
+        emb.weight.copy_(table)
+    g = {}
+    for mode, add_cls, merge, bg in (("plain", False, "add", False), ("add", True, "add", False), ("cat", True, "cat", False),
+                                     ("bg", False, "add", True), ("add+bg", True, "add", True)):
+        out = ref_shims.reference_object_embedding(pan, ids, feat, meta, object_cls_embed=emb, embedding_add_cls=add_cls,
+                                                   merge_cls_type=merge, use_background_feature=bg)
+        g[mode] = out[0].clone()
+        print("mask_pool", mode, tuple(out.shape))
+    torch.save(g, GOLDEN_DIR / "mask_pool.pt")
 
 
 def run_reference_train(head, inputs, seed, dropout):

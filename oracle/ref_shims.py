@@ -203,3 +203,29 @@ def run_reference(head, inputs: dict) -> dict:
             cap.rec["terminal_error"] = repr(e)
     cap.rec["output"] = out
     return cap.rec
+
+
+OPENSEED_REL_PATH = REFERENCE_ROOT / "kings_sgg/models/detectors/openseed_relation.py"
+
+
+def reference_object_embedding(pan_result, object_id_list, feature_map, meta_info, *, object_cls_embed=None,
+                               embedding_add_cls=False, merge_cls_type="add", use_background_feature=False):
+    """Row a11: run the reference's OWN statements of ``OpenSeeDRelation._get_input`` (detectors/openseed_relation.py, from the
+    ``def _get_input`` line up to the text-database lookups, i.e. :430-493: mask chain, mask mean-pool, class embedding,
+    background feature) on the given tensors.  The file itself cannot be imported (mmdet, detectron2, openseed), so the
+    statements are sliced out of its source text and executed unmodified as a function body against a stand-in ``self``
+    that only carries the attributes those lines read.  Returns ``object_embedding`` [1, n, C'] (None when no object)."""
+    import textwrap
+    import types as _types
+    import torch.nn.functional as F
+    src = OPENSEED_REL_PATH.read_text()
+    i = src.index("    def _get_input(self, pan_result, object_id_list, object_score_list, feature_map, meta_info):")
+    j = src.index("        use_text_db = self.relation_head.use_pair_text_vision_cross", i)
+    body = textwrap.dedent(src[i:j]) + "    return object_embedding\n"
+    ns = {"torch": torch, "F": F, "INSTANCE_OFFSET": 1000}
+    exec(compile(body, str(OPENSEED_REL_PATH), "exec"), ns)
+    self = _types.SimpleNamespace(object_cls_embed=object_cls_embed, embedding_add_cls=embedding_add_cls,
+                                  merge_cls_type=merge_cls_type, add_postional_encoding=False,
+                                  use_background_feature=use_background_feature)
+    with torch.no_grad():
+        return ns["_get_input"](self, pan_result, object_id_list, None, feature_map, meta_info)

@@ -242,9 +242,9 @@ def opt_forward(sd: Dict[str, torch.Tensor], cfg: dict, embeds: torch.Tensor, ma
     dp = prefix + "model.decoder."
     pos = sd[dp + "embed_positions.weight"][opt_positions(mask)]
     h = embeds + pos
-    causal = torch.tril(torch.ones(S, S, dtype=torch.bool))
+    causal = torch.tril(torch.ones(S, S, dtype=torch.bool, device=embeds.device))
     allow = causal[None, :, :] & mask.bool()[:, None, :]
-    bias = torch.zeros(B, 1, S, S).masked_fill(~allow[:, None], torch.finfo(torch.float32).min)
+    bias = torch.zeros(B, 1, S, S, device=embeds.device).masked_fill(~allow[:, None], torch.finfo(torch.float32).min)
     for l in range(cfg["num_hidden_layers"]):
         lp = f"{dp}layers.{l}."
         x = F.layer_norm(h, (d,), sd[lp + "self_attn_layer_norm.weight"], sd[lp + "self_attn_layer_norm.bias"], 1e-5)
@@ -276,7 +276,7 @@ def opt_greedy_decode(sd, cfg, prefix_embeds: torch.Tensor, prefix_mask: torch.T
         toks.append(nxt)
         feed = nxt if forced_tokens is None else forced_tokens[:, t]
         embeds = torch.cat([embeds, emb[feed][:, None, :]], dim=1)
-        mask = torch.cat([mask, torch.ones(mask.shape[0], 1, dtype=mask.dtype)], dim=1)
+        mask = torch.cat([mask, torch.ones(mask.shape[0], 1, dtype=mask.dtype, device=mask.device)], dim=1)
     return torch.stack(toks, dim=1), torch.stack(scores, dim=1)
 
 
@@ -287,7 +287,7 @@ def build_llm_prefix(sd, pair_feature: torch.Tensor, llm_ids: torch.Tensor, llm_
     U = _lin(pair_feature, sd, "language_projection")
     E = sd[embed_key or (prefix + "model.decoder.embed_tokens.weight")][llm_ids]
     embeds = torch.cat([U, E], dim=1)
-    mask = torch.cat([torch.ones(U.shape[0], U.shape[1], dtype=torch.long), llm_mask.long()], dim=1)
+    mask = torch.cat([torch.ones(U.shape[0], U.shape[1], dtype=torch.long, device=U.device), llm_mask.long()], dim=1)
     return embeds, mask
 
 # ----------------------------------------------------------------------------------------------
@@ -326,7 +326,7 @@ def llama_forward(sd: Dict[str, torch.Tensor], cfg: dict, embeds: torch.Tensor, 
     theta = cfg.get("rope_theta", 10000.0)
     mp = prefix + "model."
     pos = llama_positions(mask).float()                                           # [B,S]
-    inv_freq = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    inv_freq = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64, device=embeds.device).float() / hd))
     freqs = pos[:, :, None] * inv_freq[None, None, :]                             # [B,S,hd/2]
     emb = torch.cat([freqs, freqs], dim=-1)
     cos, sin = emb.cos()[:, None], emb.sin()[:, None]                             # [B,1,S,hd]
@@ -336,9 +336,9 @@ def llama_forward(sd: Dict[str, torch.Tensor], cfg: dict, embeds: torch.Tensor, 
         return torch.cat([-x2, x1], dim=-1)
 
     h = embeds
-    causal = torch.tril(torch.ones(S, S, dtype=torch.bool))
+    causal = torch.tril(torch.ones(S, S, dtype=torch.bool, device=embeds.device))
     allow = causal[None, :, :] & mask.bool()[:, None, :]
-    bias = torch.zeros(B, 1, S, S).masked_fill(~allow[:, None], torch.finfo(torch.float32).min)
+    bias = torch.zeros(B, 1, S, S, device=embeds.device).masked_fill(~allow[:, None], torch.finfo(torch.float32).min)
     n_layers = cfg["num_hidden_layers"]
     for l in range(n_layers):
         lp = f"{mp}layers.{l}."
@@ -378,7 +378,7 @@ def llama_greedy_decode(sd, cfg, prefix_embeds: torch.Tensor, prefix_mask: torch
         toks.append(nxt)
         feed = nxt if forced_tokens is None else forced_tokens[:, t]
         embeds = torch.cat([embeds, emb[feed][:, None, :]], dim=1)
-        mask = torch.cat([mask, torch.ones(mask.shape[0], 1, dtype=mask.dtype)], dim=1)
+        mask = torch.cat([mask, torch.ones(mask.shape[0], 1, dtype=mask.dtype, device=mask.device)], dim=1)
     return torch.stack(toks, dim=1), torch.stack(scores, dim=1)
 
 
@@ -390,3 +390,42 @@ def greedy_decode(sd, cfg, prefix_embeds, prefix_mask, max_new_tokens, prefix: s
 
 def embed_tokens_key(cfg, prefix: str = "language_model.") -> str:
     return prefix + ("model.embed_tokens.weight" if cfg.get("model_type", "opt") == "llama" else "model.decoder.embed_tokens.weight")
+
+# ----------------------------------------------------------------------------------------------
+# a11, whole chain (detectors/openseed_relation.py:441-493): masks from the panoptic map, pooling, class embedding,
+# background feature
+# ----------------------------------------------------------------------------------------------
+
+
+def object_masks_feature_res(pan: np.ndarray, img_hw, pad_hw, feat_hw, object_ids: Sequence[int]) -> np.ndarray:
+    """mask_o = nearest(pad0(nearest(pan == id_o -> img_shape) -> pad_shape) -> feature size)  (:441-462), bool [N, h, w].
+    Resizing the 0/1 mask with 'nearest' = reading the panoptic id at the composed source pixel; padding reads as no object."""
+    pan = np.asarray(pan)
+    fh, fw = feat_hw
+    r2 = legacy_nearest_index(fh, pad_hw[0])
+    c2 = legacy_nearest_index(fw, pad_hw[1])
+    inside = (r2 < img_hw[0])[:, None] & (c2 < img_hw[1])[None, :]
+    r1 = legacy_nearest_index(img_hw[0], pan.shape[0])[np.minimum(r2, img_hw[0] - 1)]
+    c1 = legacy_nearest_index(img_hw[1], pan.shape[1])[np.minimum(c2, img_hw[1] - 1)]
+    ids = pan[r1][:, c1]
+    return np.stack([(ids == int(o)) & inside for o in object_ids], axis=0)
+
+
+def mask_pool_chain(feature: torch.Tensor, pan, img_hw, pad_hw, object_ids: Sequence[int], cls_table: torch.Tensor | None = None,
+                    cls_mode: str = "none", use_background: bool = False):
+    """feature [C,h,w] -> (object embedding [N, C'], pair embedding [N*N, 2C']); float64 accumulation."""
+    masks = torch.from_numpy(object_masks_feature_res(np.asarray(pan), img_hw, pad_hw, feature.shape[-2:], object_ids))
+    m = masks.double()
+    f = feature.double()
+    cnt = m.sum(dim=(1, 2))[:, None]
+    obj = torch.einsum("chw,nhw->nc", f, m) / (cnt + 1e-8)
+    if cls_mode != "none":
+        e = cls_table[torch.tensor([int(o) % 1000 for o in object_ids])].double()
+        obj = obj + e if cls_mode == "add" else torch.cat([obj, e], dim=-1)
+    if use_background:
+        bg = torch.einsum("chw,nhw->nc", f, 1.0 - m) / ((1.0 - m).sum(dim=(1, 2))[:, None] + 1e-8)
+        obj = obj + bg
+    obj = obj.float()
+    n = obj.shape[0]
+    pair = torch.cat([obj[:, None, :].expand(n, n, -1), obj[None, :, :].expand(n, n, -1)], dim=-1)
+    return obj, pair.reshape(n * n, -1)

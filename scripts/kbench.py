@@ -171,6 +171,38 @@ def bench_xattn(iters, flush):
                           "tflops_median": fl / med / 1e9, "tflops_best": fl / best / 1e9}), flush=True)
 
 
+def bench_xattn_cfg2(iters, flush):
+    """K5 on the panoptic masks of the synthetic cfg2 / cfg5 images (compact objects: most 32-key chunks invisible to a
+    32-row quarter), mask-bias tiles prebuilt as in the pipeline."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from openpsg_b200 import synth
+    for name in ("cfg2", "cfg5"):
+        wl = synth.WORKLOADS[name]
+        inp = synth.make_image_inputs(wl, 0)
+        N, L = wl.num_objects, wl.image_tokens
+        B = N * N
+        pan = inp["object_info"][0]["pan_results"].to(torch.int32).to(DEV)
+        ids = torch.tensor([int(i) for i in inp["object_info"][0]["object_id_list"]], dtype=torch.int32, device=DEV)
+        bits = ops.pair_mask_bits(pan, (wl.height, wl.width), (wl.height, wl.width), (16, 16), ids)
+        g = torch.Generator(device="cpu").manual_seed(1)
+        q = (torch.randn((B * 33, 768), generator=g)).to(torch.bfloat16).to(DEV)
+        k = (torch.randn((L, 768), generator=g)).to(torch.bfloat16).to(DEV)
+        vt = torch.randn((768, L), generator=g).to(torch.bfloat16).to(DEV)
+        out = torch.empty_like(q)
+        perm, bits_sorted = ops.token_order(bits, L)
+        for tag, bb in (("token_order", bits), ("object_order", bits_sorted)):
+            tiles = ops.xattn_bias_tiles(bb, N, B, 33, L)
+            vis = tiles[-((B * 33 + 127) // 128) * 16:].view(torch.int16).view(-1, 8)[:, :4].to(torch.int32) & 0xFFFF
+            frac = sum(bin(int(x)).count("1") for x in vis.flatten().tolist()) / (16.0 * vis.numel())
+            med, best = timeit(lambda: ops.xattn_pairs(q, k, vt, bb, N, B, 33, L, 12, 64, out=out, bias_tiles=tiles), iters, flush)
+            fl = 4.0 * B * 33 * L * 768
+            print(json.dumps({"kernel": "xattn_pairs_" + name + "_masks_" + tag, "N": N, "L": L, "visible_chunk_frac": round(frac, 3),
+                              "ms_median": med, "ms_best": best, "tflops_median": fl / med / 1e9, "tflops_best": fl / best / 1e9}),
+                  flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["gemm", "xattn"])
@@ -185,6 +217,7 @@ def main():
         bench_layers(args.iters, flush)
     if "xattn" in args.which:
         bench_xattn(args.iters, flush)
+        bench_xattn_cfg2(args.iters, flush)
 
 
 if __name__ == "__main__":

@@ -13,6 +13,14 @@ q = torch.randn((B * 33, 768), generator=g).to(torch.bfloat16).cuda()
 k = torch.randn((L, 768), generator=g).to(torch.bfloat16).cuda()
 vt = torch.randn((768, L), generator=g).to(torch.bfloat16).cuda()
 bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (N, 8), dtype=torch.int64, generator=g).to(torch.int32).cuda()
+if len(sys.argv) > 2 and sys.argv[2] == "masks":      # panoptic masks of the synthetic image, keys in object order
+    from openpsg_b200 import synth
+    wl = synth.WORKLOADS["cfg2" if N == 40 else "cfg5"]
+    inp = synth.make_image_inputs(wl, 0)
+    pan = inp["object_info"][0]["pan_results"].to(torch.int32).cuda()
+    ids = torch.tensor([int(i) for i in inp["object_info"][0]["object_id_list"]], dtype=torch.int32, device="cuda")
+    bits = ops.pair_mask_bits(pan, (wl.height, wl.width), (wl.height, wl.width), (16, 16), ids)
+    _, bits = ops.token_order(bits, L)
 tiles = ops.xattn_bias_tiles(bits, N, B, 33, L)
 for _ in range(3):
     ops.xattn_pairs(q, k, vt, bits, N, B, 33, L, 12, 64, bias_tiles=tiles)

@@ -7,22 +7,8 @@ WEIGHT_SEED = 0
 
 
 def build_product_head(llm=None, max_object_num=80, topk_pairs=20, max_new_tokens=16, device=None):
-    """llm: None -> no language model (relation queries + filter only); dict -> random-init OPT of that config."""
-    from openpsg_b200.head import RelationTransformerHeadV4
-    lm, ltok, d_llm = False, None, 4096
-    if llm is not None:
-        lm = synth.build_causal_lm(llm)
-        ltok = synth.SyntheticTokenizer("llm")
-        ltok.set_vocab_size(llm["vocab_size"])
-        d_llm = llm["hidden_size"]
-    head = RelationTransformerHeadV4(llm_feature_size=d_llm, max_object_num=max_object_num, topk_pairs=topk_pairs,
-                                     max_new_tokens=max_new_tokens, qformer_tokenizer=synth.SyntheticTokenizer("qformer"),
-                                     llm_tokenizer=ltok, language_model=lm)
-    synth.init_parameters(head, WEIGHT_SEED)
-    head.eval()
-    if device is not None:
-        head.to(device)
-    return head
+    """llm: None -> no language model (relation queries + filter only); dict -> random-init LLM of that config."""
+    return synth.build_synthetic_head(llm, max_object_num, topk_pairs, max_new_tokens, device)
 
 
 def build_port_head(llm=None, max_object_num=80, topk_pairs=20, max_new_tokens=16):

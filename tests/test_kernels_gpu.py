@@ -386,7 +386,7 @@ def test_xattn_bias_tiles_bit_exact(ops):
     rows = B * nq
     m_tiles = (rows + 127) // 128
     tiles, flags = got[:m_tiles * 12288].reshape(m_tiles, 12288), got[m_tiles * 12288:]
-    vis = got[m_tiles * (12288 + 128):]
+    vis = got[m_tiles * (12288 + 128):].view(np.uint16)      # 4 x uint16 per tile, 16 bytes reserved per tile
     pm = restated.pair_masks(masks.numpy())                       # [B, L]
     NEG, ONE = 0xC680, 0x3F80
     for mt in range(m_tiles):
@@ -409,8 +409,8 @@ def test_xattn_bias_tiles_bit_exact(ops):
                 if row < rows:
                     m = np.zeros(256, bool)
                     m[:L] = pm[row // nq]
-                    exp_vis |= sum(1 << w for w in range(8) if m[32 * w:32 * w + 32].any())
-            assert vis[mt * 4 + quarter] == exp_vis, (mt, quarter)
+                    exp_vis |= sum(1 << w for w in range(16) if m[16 * w:16 * w + 16].any())
+            assert vis[mt * 4 + quarter] == exp_vis, (mt, quarter)     # chunk_vis is indexed [mt * 4 + quarter]
         for key in range(256):
             exp = np.zeros(8, np.uint16)
             for s in range(last - first + 1):
@@ -526,3 +526,75 @@ def test_argmax_and_gathers(ops):
     src = _rand_bf16((50, 32 * 768), g)
     idx = torch.tensor([4, 4, 49, 0], dtype=torch.int32)
     assert torch.equal(ops.gather_rows(src.cuda(), 32 * 768, idx.cuda()).cpu(), src[idx.long()])
+
+
+def test_token_order_sorts_tokens_by_owning_object(ops):
+    """opsg_token_order: perm lists the image tokens by (owner, token index), owner = first object whose mask holds the
+    token, unowned tokens last; bits_sorted are the same masks in that order."""
+    g = torch.Generator().manual_seed(21)
+    for N, L in ((7, 20), (40, 256), (80, 256), (5, 255)):
+        words = 8
+        owner = torch.randint(0, N + 2, (L,), generator=g)           # N, N + 1 = nobody
+        m = torch.zeros((N, L), dtype=torch.bool)
+        for o in range(N):
+            m[o] = owner == o
+        m[0] |= torch.rand(L, generator=g) > 0.9                     # overlapping masks: object 0 also claims other tokens
+        bits = torch.zeros((N, words), dtype=torch.int64)
+        for l in range(L):
+            bits[:, l // 32] |= m[:, l].long() << (l % 32)
+        bits32 = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+        perm, bs = ops.token_order(bits32.cuda(), L)
+        first = torch.where(m.any(0), m.float().argmax(0), torch.full((L,), N))
+        want = sorted(range(L), key=lambda l: (int(first[l]), l))
+        assert perm.cpu().tolist() == want
+        got = bs.cpu().numpy().view(np.uint32)
+        obj = ((got[:, np.arange(L) // 32] >> (np.arange(L) % 32).astype(np.uint32)) & 1).astype(bool)
+        assert np.array_equal(obj, m[:, want].numpy())
+        assert not ((got[:, np.arange(L, words * 32) // 32] >> (np.arange(L, words * 32) % 32).astype(np.uint32)) & 1).any()
+
+
+MASK_POOL_MODES = (("plain", "none", False), ("add", "add", False), ("cat", "cat", False), ("bg", "none", True), ("add+bg", "add", True))
+
+
+def test_mask_pool_chain_matches_reference_golden(ops, golden):
+    """Row a11 end to end on the GPU — panoptic map -> label map (the reference's nearest / pad / nearest mask chain) ->
+    pooled object embeddings (+ class embedding, + background feature) -> pair embeddings — against what the reference's own
+    statements produced (tests/golden/mask_pool.pt) and against the restatement; two runs are bit-identical."""
+    g = golden("mask_pool")
+    feat, pan, ids, meta, table = synth.make_mask_pool_case()
+    f = feat[0].cuda()
+    ids_t = torch.tensor(ids, dtype=torch.int32).cuda()
+    label, rep = ops.mask_pool_labels(pan.to(torch.int32).cuda(), meta["img_shape"][:2], meta["pad_shape"][:2], f.shape[-2:], ids_t)
+    m = restated.object_masks_feature_res(pan.numpy(), meta["img_shape"][:2], meta["pad_shape"][:2], f.shape[-2:], ids)
+    lab = label.cpu().numpy()
+    first = np.where(m.any(0), m.argmax(0), len(ids))
+    assert np.array_equal(lab, first), "label map = first object whose mask holds the pixel (bit-exact)"
+    assert rep.cpu().tolist() == [0, 1, 2, 3, 4, 5, 6, 2, 8]
+    cls_ids = torch.tensor([i % 1000 for i in ids], dtype=torch.int32).cuda()
+    for name, cls_mode, bg in MASK_POOL_MODES:
+        obj, pair = ops.mask_pool_pairs(f, label, len(ids), rep=rep, cls_table=table.cuda(), cls_ids=cls_ids, cls_mode=cls_mode,
+                                        use_background=bg)
+        obj2, pair2 = ops.mask_pool_pairs(f, label, len(ids), rep=rep, cls_table=table.cuda(), cls_ids=cls_ids, cls_mode=cls_mode,
+                                          use_background=bg)
+        assert torch.equal(obj, obj2) and torch.equal(pair, pair2), "no atomics: bit-reproducible"
+        d = (obj.cpu() - g[name]).abs().max().item()
+        assert d < 1e-4, (name, d)
+        ref_obj, ref_pair = restated.mask_pool_chain(feat[0], pan.numpy(), meta["img_shape"][:2], meta["pad_shape"][:2], ids, table,
+                                                     cls_mode, bg)
+        assert (pair.cpu() - ref_pair).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg5"])
+def test_mask_pool_benchmark_shapes(ops, name):
+    """The 1024x1024 images (67 MB feature map, 40 / 80 objects) against the restatement."""
+    wl = synth.WORKLOADS[name]
+    inp = synth.make_image_inputs(wl, 0)
+    ids = [int(i) for i in inp["object_info"][0]["object_id_list"]]
+    pan = inp["object_info"][0]["pan_results"]
+    feat = inp["mask_features"][0]
+    label, rep = ops.mask_pool_labels(pan.to(torch.int32).cuda(), (wl.height, wl.width), (wl.height, wl.width), feat.shape[-2:],
+                                      torch.tensor(ids, dtype=torch.int32).cuda())
+    obj, pair = ops.mask_pool_pairs(feat.cuda(), label, len(ids), rep=rep, use_background=True)
+    ref_obj, ref_pair = restated.mask_pool_chain(feat, pan.numpy(), (wl.height, wl.width), (wl.height, wl.width), ids, None, "none", True)
+    assert (obj.cpu() - ref_obj).abs().max() < 1e-4
+    assert (pair.cpu() - ref_pair).abs().max() < 1e-4

@@ -210,3 +210,23 @@ def test_llama_gqa_restatement_matches_hf():
     got = restated.llama_forward(sd, cfg, embeds, mask)
     valid = mask.bool()
     assert (got - ref)[valid].abs().max() < 1e-4
+
+
+MASK_POOL_MODES = (("plain", "none", False), ("add", "add", False), ("cat", "cat", False), ("bg", "none", True), ("add+bg", "add", True))
+
+
+def test_mask_pool_chain_matches_reference_statements(golden):
+    """Row a11: restated.mask_pool_chain against tests/golden/mask_pool.pt, which holds what the reference's OWN statements
+    (detectors/openseed_relation.py:430-493, sliced out of the file and executed by oracle/ref_shims.reference_object_embedding)
+    return: mask chain pan==id -> nearest -> pad -> nearest, mean-pool, class embedding add / cat, background feature."""
+    g = golden("mask_pool")
+    feat, pan, ids, meta, table = synth.make_mask_pool_case()
+    for name, cls_mode, bg in MASK_POOL_MODES:
+        obj, pair = restated.mask_pool_chain(feat[0], pan.numpy(), meta["img_shape"][:2], meta["pad_shape"][:2], ids, table, cls_mode, bg)
+        assert obj.shape == g[name].shape
+        assert (obj - g[name]).abs().max() < 1e-5, name
+        n = len(ids)
+        assert torch.equal(pair[1 * n + 3], torch.cat([obj[1], obj[3]]))
+    m = restated.object_masks_feature_res(pan.numpy(), meta["img_shape"][:2], meta["pad_shape"][:2], feat.shape[-2:], ids)
+    assert not m[6].any() and not m[8].any(), "the pixel-less object and the unlisted id own nothing"
+    assert np.array_equal(m[7], m[2]), "an object repeating an id shares the mask"

@@ -220,7 +220,10 @@ def test_relation_queries_80_objects_subset_vs_oracle(head):
     tokens = restated.patch_embed(inputs["mask_features"], sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], 16)
     from openpsg_b200.categories import object_categories
     names = [object_categories[i % 1000] for i in ids]
-    sample = torch.tensor([0, 79, 80, 81, 3333, 6399, 6398, 4040, 1234, 2500, 5000, 6320], dtype=torch.long)
+    # 12 hand-picked corner pairs (first / last rows, diagonal, tile boundaries) + 244 random ones = 256 of the 6400
+    fixed = [0, 79, 80, 81, 3333, 6399, 6398, 4040, 1234, 2500, 5000, 6320]
+    rnd = [int(x) for x in torch.randperm(n * n, generator=torch.Generator().manual_seed(77)).tolist() if int(x) not in fixed][:244]
+    sample = torch.tensor(fixed + rnd, dtype=torch.long)
     enc = synth.SyntheticTokenizer("qformer")(
         ['Is there a relation between {} and {}?'.format(names[p // n], names[p % n]) for p in sample.tolist()])
     query = torch.cat([sd["rel_cls_query"], sd["relation_query"]], dim=1)[0]
