@@ -263,6 +263,16 @@ int opsg_splitk_reduce_bf16(const float* partials, int splits, int rows, int col
                             int ld_out, void* stream);
 int opsg_transpose_i32(const int32_t* src, int rows, int cols, int32_t* dst, void* stream);
 
+/* ---- f1 / f2: the integer passes either side of the head in the reference's inference loop --------------------------
+ * opsg_pan_relabel: detectors/openseed_relation_v2.py:112-128 on the device: pan_out[p] = new_ids[s] for the LAST listed
+ *   segment s with seg_ids[s] == pan_in[p], 0 if none (the reference: D2H, one np.where pass per segment, H2D).
+ * opsg_pan_colorize: tools/infer.py:149-169: out_rgb uint8 [n_pixels, 3] = sum over the listed objects whose id equals the
+ *   pixel of that object's colour (uint8 wrap-around), 0 elsewhere: the RGB-encoded panoptic map of the submission PNG. */
+int opsg_pan_relabel(const int32_t* pan_in, long long n_pixels, const int32_t* seg_ids, const int32_t* new_ids, int n_segments,
+                     int32_t* pan_out, void* stream);
+int opsg_pan_colorize(const int32_t* pan, long long n_pixels, const int32_t* obj_ids, const uint8_t* colors, int n_objects,
+                      uint8_t* out_rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,9 +34,6 @@
 #include "common.cuh"
 #include "host_util.h"
 
-extern "C" int opsg_xattn_pairs_v1(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
-                                   const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
-                                   int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream);
 extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
                                    const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                                    int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream);
@@ -57,6 +54,7 @@ struct XattnParams {
   int rows;          // B * n_query
   int m_tiles;
   int total_units;
+  int ctas_per_head; // > 0: grid = num_heads x ctas_per_head, every CTA walks m-tiles of a single head
   int desc_swap;     // debug: swap LBO / SBO of the no-swizzle descriptors
   long long* trace;  // debug: per-unit clock64 stamps of CTA 0 ([unit][8]); NULL in production
   float scale_log2e;
@@ -322,6 +320,8 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return static_cast<long long>(t); };
+  if (p.trace && threadIdx.x == 0) p.trace[2048 + 4 * blockIdx.x + 0] = gtime();      // debug: per-CTA wall-clock stamps (ns)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -360,9 +360,18 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_wait_then_trigger();          // everything above overlaps the previous kernel (programmatic dependent launch)
 
   // contiguous, head-major unit range of this CTA
-  const int per = (p.total_units + gridDim.x - 1) / gridDim.x;
-  const int u_begin = blockIdx.x * per;
-  const int u_end = min(p.total_units, u_begin + per);
+  // Unit range of this CTA.  With ctas_per_head > 0 the grid is num_heads x ctas_per_head and a CTA stays inside ONE head
+  // (its K / V tiles are loaded once, no reload bubble); otherwise a contiguous head-major range.
+  int u_begin, u_end;
+  if (p.ctas_per_head > 0) {
+    const int head = blockIdx.x / p.ctas_per_head, c = blockIdx.x % p.ctas_per_head;
+    u_begin = head * p.m_tiles + static_cast<int>(static_cast<long long>(c) * p.m_tiles / p.ctas_per_head);
+    u_end = head * p.m_tiles + static_cast<int>(static_cast<long long>(c + 1) * p.m_tiles / p.ctas_per_head);
+  } else {
+    const int per = (p.total_units + gridDim.x - 1) / gridDim.x;
+    u_begin = blockIdx.x * per;
+    u_end = min(p.total_units, u_begin + per);
+  }
   const int n_units = max(0, u_end - u_begin);
   const int head0 = u_begin / p.m_tiles;
   auto head_of = [&](int j) { return (u_begin + j) / p.m_tiles; };
@@ -421,6 +430,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool release_k = j + 1 < n_units && head_of(j + 1) != head;
       if (elect_one_sync()) {
         if (p.trace && blockIdx.x == 0) p.trace[j * 8 + 0] = clock64();
+        if (p.trace && j == 0) p.trace[2048 + 4 * blockIdx.x + 2] = gtime();
         const uint64_t a_desc = umma_desc_k_sw128(smem_u32(sQ + b * XaSmem::kQ));
         const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK));
         const uint32_t aug = smem_u32(sAug + b * XaSmem::kAug);
@@ -741,6 +751,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0) p.trace[2048 + 4 * blockIdx.x + 3] = gtime();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -799,13 +810,9 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
                                 const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                                 int n_query, int L, int num_heads, int head_dim, const void* bias_tiles,
                                 opsg_bf16* ctx_out, void* stream) {
-  static const int impl = [] { const char* e = getenv("OPSG_XATTN_IMPL"); return e ? atoi(e) : 3; }();
   static const int desc_swap = [] { const char* e = getenv("OPSG_XATTN_DESC_SWAP"); return e ? atoi(e) : 0; }();
-  if (impl == 1)
-    return opsg_xattn_pairs_v1(q, k, ld_k, vt, ld_vt, bits, words, pair_index, num_objects, B, n_query, L, num_heads,
-                               head_dim, ctx_out, stream);
   // without precomputed mask-bias tiles (or for shapes they do not cover) the self-contained v2 kernel runs
-  if (impl == 2 || !bias_tiles || n_query <= 0 || 127 / n_query + 2 > kXaSlots)
+  if (!bias_tiles || n_query <= 0 || 127 / n_query + 2 > kXaSlots)
     return opsg_xattn_pairs_v2(q, k, ld_k, vt, ld_vt, bits, words, pair_index, num_objects, B, n_query, L, num_heads,
                                head_dim, ctx_out, stream);
   int rc = opsg_device_check();
@@ -852,7 +859,13 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   p.desc_swap = desc_swap;
   p.trace = g_xattn_trace;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
-  const int grid = p.total_units < opsg_num_sms() ? p.total_units : opsg_num_sms();
+  const int sms = opsg_num_sms();
+  int grid = p.total_units < sms ? p.total_units : sms;
+  p.ctas_per_head = 0;
+  if (num_heads <= sms && p.m_tiles >= 2 * (sms / num_heads)) {      // enough tiles per head: pin every CTA to one head
+    p.ctas_per_head = sms / num_heads;
+    grid = p.ctas_per_head * num_heads;
+  }
   launch_kernel(kernel, grid, kXaThreads, XaSmem::kTotal, reinterpret_cast<cudaStream_t>(stream), tmQ, tmK, tmVt, tmO, p);
   OPSG_CHECK_LAUNCH("xattn_pairs_kernel");
   return OPSG_OK;

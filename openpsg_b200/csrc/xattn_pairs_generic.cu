@@ -1,4 +1,6 @@
-// K5 (v2, kept for A/B: OPSG_XATTN_IMPL=2; superseded by xattn_pairs.cu v3) — pair-query x image-feature masked cross-attention on tcgen05 tensor cores (the north-star kernel).
+// K5, generic variant — the self-contained kernel opsg_xattn_pairs falls back to when the caller passes no prebuilt mask-bias
+// tiles or n_query puts more than 8 pairs into a 128-row tile (xattn_pairs.cu handles the head's own shape, n_query = 33):
+// pair-query x image-feature masked cross-attention on tcgen05 tensor cores, masks applied by the softmax warps from the bit words.
 //
 // All pairs' query rows are stacked along M (row = pair * n_query + r); K and V are projected once per image
 // and shared by every pair, so per head the whole thing is  softmax(Q[M x 64] . K^T[64 x L] + mask(pair)) . V.

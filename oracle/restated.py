@@ -429,3 +429,39 @@ def mask_pool_chain(feature: torch.Tensor, pan, img_hw, pad_hw, object_ids: Sequ
     n = obj.shape[0]
     pair = torch.cat([obj[:, None, :].expand(n, n, -1), obj[None, :, :].expand(n, n, -1)], dim=-1)
     return obj, pair.reshape(n * n, -1)
+
+# ----------------------------------------------------------------------------------------------
+# f1 / f2: detector glue and result wire format (numpy restatements; integer work -> bit-exact)
+# ----------------------------------------------------------------------------------------------
+
+
+def relabel_panoptic(pan_seg: np.ndarray, segments_info) -> Tuple[np.ndarray, List[int]]:
+    """detectors/openseed_relation_v2.py:112-124: per segment, in list order, pan[pan_seg == id] = category + 1000 * (number of
+    earlier segments of that category); everything else 0.  -> (pan_results, object ids)."""
+    pan_seg = np.asarray(pan_seg)
+    out = np.zeros_like(pan_seg)
+    record: Dict[int, int] = {}
+    ids = []
+    for seg in segments_info:
+        cat = int(seg["category_id"])
+        record[cat] = record.get(cat, -1) + 1
+        new = cat + 1000 * record[cat]
+        out[np.where(pan_seg == int(seg["id"]))] = new
+        ids.append(new)
+    return out, ids
+
+
+def submission_image(pan_results: np.ndarray, object_id_list, rng):
+    """tools/infer.py:149-168: (uint8 [H, W, 3] image in R, G, B order as the PNG stores it, segments_info)."""
+    pan_results = np.asarray(pan_results)
+    acc = np.zeros(pan_results.shape + (3,), dtype=np.int64)
+    segments_info = []
+    for object_id in object_id_list:
+        object_id = int(object_id)
+        mask = pan_results == object_id
+        if object_id == 133:
+            continue
+        r, g, b = rng.choices(range(0, 255), k=3)
+        acc = acc + mask[..., None].astype(np.int64) * np.array([r, g, b]).reshape(1, 1, 3)
+        segments_info.append(dict(category_id=int(object_id % 1000 + 1), id=r + 256 * g + 256 * 256 * b))
+    return acc.astype(np.uint8), segments_info

@@ -24,7 +24,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "masks":      # panoptic masks of the sy
 tiles = ops.xattn_bias_tiles(bits, N, B, 33, L)
 for _ in range(3):
     ops.xattn_pairs(q, k, vt, bits, N, B, 33, L, 12, 64, bias_tiles=tiles)
-trace = torch.zeros(8 * 256, dtype=torch.int64, device="cuda")
+trace = torch.zeros(8 * 256 + 4 * 160, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 lib.opsg_debug_xattn_trace.argtypes = [ctypes.c_void_p]
 lib.opsg_debug_xattn_trace.restype = None
@@ -32,12 +32,26 @@ lib.opsg_debug_xattn_trace(trace.data_ptr())
 ops.xattn_pairs(q, k, vt, bits, N, B, 33, L, 12, 64, bias_tiles=tiles)
 torch.cuda.synchronize()
 lib.opsg_debug_xattn_trace(None)
-t = trace.cpu().view(-1, 8)
+full = trace.cpu()
+t = full[:2048].view(-1, 8)
 n = int((t[:, 0] != 0).sum())
 t0 = int(t[0, 0])
 print("unit  qk_issue pv_issue | s_full pass1_end pass2_end o_full epi_end   (cycles since first QK issue; buffers alternate)")
-for i in range(min(n, 40)):
+for i in range(min(n, 64)):
     r = [int(x) - t0 if x else -1 for x in t[i, :7]]
     print(f"{i:4d}  {r[0]:8d} {r[1]:8d} | {r[2]:7d} {r[3]:8d} {r[4]:8d} {r[5]:7d} {r[6]:8d}   pass1={r[3]-r[2]} pass2={r[4]-r[3]} p_ready->pv={r[1]-r[4]} pv->o_full={r[5]-r[1]} epi={r[6]-r[5]}")
 if n > 12:
     print("steady-state cycles/unit:", (int(t[n - 2, 0]) - int(t[8, 0])) / (n - 10))
+
+w = full[2048:].view(-1, 4)
+w = w[w[:, 0] != 0]
+if len(w):
+    t_min = int(w[:, 0].min())
+    rel = (w - t_min).float() / 1e3
+    print(f"per-CTA wall clock (us since the first CTA started), {len(w)} CTAs:")
+    print(f"  entry      : min {rel[:,0].min():.2f} max {rel[:,0].max():.2f}")
+    print(f"  setup done : min {rel[:,1].min():.2f} max {rel[:,1].max():.2f}")
+    print(f"  first QK   : min {rel[:,2].min():.2f} median {rel[:,2].median():.2f} max {rel[:,2].max():.2f}")
+    print(f"  exit       : min {rel[:,3].min():.2f} median {rel[:,3].median():.2f} max {rel[:,3].max():.2f}")
+    d = rel[:, 3] - rel[:, 2]
+    print(f"  first QK -> exit: min {d.min():.2f} median {d.median():.2f} max {d.max():.2f}")
