@@ -719,6 +719,9 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_q
 
 using namespace opsg;
 
+int launch_self_attn_pairs(const opsg_bf16* qkv, const opsg_bf16* shared_query_qkv, const int32_t* text_mask, int B, int n_query,
+                           int T, int num_heads, int head_dim, int text_queries, opsg_bf16* ctx_out, cudaStream_t stream);
+
 extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* shared_query_qkv, const int32_t* text_mask, int B,
                                     int n_query, int T, int num_heads, int head_dim, int text_queries, opsg_bf16* ctx_out,
                                     void* stream) {
@@ -736,6 +739,14 @@ extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* share
   p.out = reinterpret_cast<__nv_bfloat16*>(ctx_out);
   p.num_heads = num_heads; p.d_model = num_heads * head_dim; p.ld_out = p.d_model;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+  // tcgen05 + TMA tiles (self_attn_pairs.cu: two pairs stacked per 128-row tile) for the head's shape; the warp-level
+  // mma.sync kernels below remain the fallback for other shapes (head_dim != 64, more than 64 rows per pair)
+  static const int use_tc = [] { const char* e = getenv("OPSG_SELF_ATTN_TC"); return e ? atoi(e) : 1; }();
+  if (use_tc) {
+    rc = launch_self_attn_pairs(qkv, shared_query_qkv, text_mask, B, n_query, T, num_heads, head_dim, text_queries, ctx_out,
+                                reinterpret_cast<cudaStream_t>(stream));
+    if (rc != OPSG_E_UNSUPPORTED) return rc;
+  }
   static const int use_pipelined = [] { const char* e = getenv("OPSG_SELF_ATTN_PIPELINED"); return e ? atoi(e) : 1; }();
   if (use_pipelined && head_dim == kQfHD && n_query + T <= kQfNK && (((uintptr_t)qkv | (uintptr_t)ctx_out) & 15) == 0) {
     constexpr int smem = kQfStages * kQfStageBytes;
