@@ -719,6 +719,9 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_q
 
 using namespace opsg;
 
+int launch_llm_prefill_attn_tc(const opsg_bf16* q, int ld_q, const opsg_bf16* k_cache, const opsg_bf16* v_cache, int max_ctx,
+                               const uint8_t* key_mask, int nseq, int q_len, int q_pos0, int num_heads, int head_dim, float scale,
+                               opsg_bf16* out, int ld_out, cudaStream_t stream);
 int launch_self_attn_pairs(const opsg_bf16* qkv, const opsg_bf16* shared_query_qkv, const int32_t* text_mask, int B, int n_query,
                            int T, int num_heads, int head_dim, int text_queries, opsg_bf16* ctx_out, cudaStream_t stream);
 
@@ -791,6 +794,13 @@ extern "C" int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_ca
     if (head_dim == 64) return launch_decode_attn<64>(p, nseq, st);
     if (head_dim == 80) return launch_decode_attn<80>(p, nseq, st);
     return launch_decode_attn<128>(p, nseq, st);
+  }
+  // prefill of prompts up to 64 tokens: tcgen05 + TMA tiles, two sequences stacked per 128-row tile (llm_prefill_attn.cu)
+  static const int use_tc = [] { const char* e = getenv("OPSG_LLM_PREFILL_TC"); return e ? atoi(e) : 1; }();
+  if (use_tc && q_len > 1) {
+    rc = launch_llm_prefill_attn_tc(q, ld_q, k_cache, v_cache, max_ctx, key_mask, nseq, q_len, q_pos0, num_heads, head_dim, scale, out,
+                                    ld_out, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != OPSG_E_UNSUPPORTED) return rc;
   }
   return dispatch_hd(p, nseq, q_pos0 + q_len, head_dim, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -255,7 +255,10 @@ def test_self_attn_small(ops, text_queries):
 
 
 @pytest.mark.parametrize("hd,heads,q_len,pos0", [(80, 32, 1, 48), (80, 32, 1, 80), (80, 32, 1, 127), (64, 12, 1, 17),
-                                                 (128, 8, 1, 63), (80, 32, 49, 0), (64, 12, 5, 3)])
+                                                 (128, 8, 1, 63), (80, 32, 49, 0), (64, 12, 5, 3),
+                                                 # prefill from position 0, <= 64 tokens: the tcgen05 + TMA kernel
+                                                 (128, 8, 49, 0), (128, 32, 64, 0), (64, 12, 33, 0), (80, 32, 64, 0), (80, 5, 2, 0),
+                                                 (128, 4, 17, 0), (64, 3, 65, 0)])
 def test_llm_attn_static_cache(ops, hd, heads, q_len, pos0):
     """K10a/b: causal attention of q_len new tokens (positions pos0 ..) over a static KV cache with a key-validity mask
     (left padding); q_len == 1 takes the shared-memory decode kernel.  tol 2e-2 abs (bf16 P and output)."""
@@ -598,3 +601,35 @@ def test_mask_pool_benchmark_shapes(ops, name):
     ref_obj, ref_pair = restated.mask_pool_chain(feat, pan.numpy(), (wl.height, wl.width), (wl.height, wl.width), ids, None, "none", True)
     assert (obj.cpu() - ref_obj).abs().max() < 1e-4
     assert (pair.cpu() - ref_pair).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("hd,heads,q_len", [(128, 32, 49), (80, 32, 49), (64, 12, 64), (128, 8, 20), (80, 7, 33)])
+def test_llm_prefill_attn_left_padding(ops, hd, heads, q_len):
+    """K10a on the tcgen05 + TMA kernel with LEFT-PADDED prompts (v4:262, pads sit between the 32 relation rows and the text in
+    the real prompt; here at the front): valid query rows against fp32; rows that sit on padding come out finite (zeros)."""
+    g = torch.Generator().manual_seed(hd * 3 + q_len)
+    nseq, max_ctx = 9, q_len + 32
+    d = heads * hd
+    qkv = _rand_bf16((nseq * q_len, 3 * d), g)
+    kc = _rand_bf16((nseq, max_ctx, d), g)
+    vc = _rand_bf16((nseq, max_ctx, d), g)
+    pad = torch.randint(0, q_len // 2, (nseq,), generator=g)
+    pad[0] = 0
+    kmask = (torch.arange(max_ctx)[None, :] >= pad[:, None]).to(torch.uint8)
+    kmask[3, pad[3] + 2] = 0                                            # a hole in the middle (mid-sequence pads, v4:298-299)
+    out = torch.full((nseq * q_len, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.llm_attn(qkv.cuda(), kc.cuda(), vc.cuda(), kmask.cuda(), nseq, q_len, 0, heads, hd, hd ** -0.5, out)
+    q = qkv[:, :d].float().reshape(nseq, q_len, heads, hd).permute(0, 2, 1, 3)
+    k = kc[:, :q_len].float().reshape(nseq, q_len, heads, hd).permute(0, 2, 1, 3)
+    v = vc[:, :q_len].float().reshape(nseq, q_len, heads, hd).permute(0, 2, 1, 3)
+    sc = q @ k.transpose(-1, -2) * hd ** -0.5
+    causal = torch.arange(q_len)[None, :] <= torch.arange(q_len)[:, None]
+    ok = causal[None, None] & kmask[:, None, None, :q_len].bool()
+    any_key = ok.any(-1)                                                # [nseq, 1, q_len]
+    ref = torch.softmax(sc.masked_fill(~ok, float("-inf")), -1)
+    ref = torch.nan_to_num(ref, nan=0.0) @ v
+    ref = ref.permute(0, 2, 1, 3).reshape(nseq * q_len, d)
+    got = out.float().cpu()
+    assert torch.isfinite(got).all(), "every row is written and finite"
+    rows = any_key[:, 0].reshape(-1)
+    assert (got[rows] - ref[rows]).abs().max() < 2e-2
