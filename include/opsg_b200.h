@@ -38,11 +38,6 @@ enum {
 
 enum { OPSG_ACT_NONE = 0, OPSG_ACT_GELU = 1, OPSG_ACT_RELU = 2 };
 enum { OPSG_OUT_BF16 = 0, OPSG_OUT_F32 = 1, OPSG_OUT_F32_ATOMIC = 2 };
-/* OR-ed into out_mode of opsg_gemm_bf16_streamk: W is a constant of the stream (model weights; nothing queued earlier on the
- * stream writes it).  The kernel then starts streaming W before the preceding kernel of the stream has completed
- * (programmatic dependent launch; only the loads of A wait) -- the LLM decode loop's GEMMs fill their pipelines under the
- * small kernels that precede them. */
-enum { OPSG_GEMM_W_CONST = 0x100 };
 
 int opsg_version(void);
 const char* opsg_last_error_string(void);
@@ -100,8 +95,7 @@ int opsg_gemm_bf16_ln(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, 
  * through a caller-provided workspace of opsg_gemm_streamk_workspace_bytes(N, K) bytes and a second kernel sums them in
  * a fixed order and applies bias / activation / residual (csrc/gemm_skinny.cu).  Deterministic (no atomics).
  * Layouts that kernel does not take (N, ldd or ldr not a multiple of 4) and OPSG_SKINNY=0 use the older stream-K
- * decomposition over 256-wide tiles (gemm.cu) behind the same entry.  out_mode: OPSG_OUT_BF16 or OPSG_OUT_F32, optionally
- * | OPSG_GEMM_W_CONST. */
+ * decomposition over 256-wide tiles (gemm.cu) behind the same entry.  out_mode: OPSG_OUT_BF16 or OPSG_OUT_F32. */
 size_t opsg_gemm_streamk_workspace_bytes(int N, int K);
 int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, void* D, int ldd, int M, int N,
                            int K, const float* bias, const opsg_bf16* residual, int ldr, int act, int out_mode,

@@ -15,7 +15,6 @@ _lib = None
 OPSG_OK, OPSG_E_INVALID, OPSG_E_CUDA, OPSG_E_NO_DEVICE, OPSG_E_UNSUPPORTED = 0, -1, -2, -3, -4
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
-GEMM_W_CONST = 0x100      # OR-ed into out_mode of opsg_gemm_bf16_streamk (include/opsg_b200.h)
 
 P, I, F = c_void_p, c_int, c_float
 

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams 
 // ------------------------------------------------------------------------------------------------
 template <int HD, int R>
 __global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnParams p, int warps_per_cta) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   constexpr int C = HD / 8;                                 // 16-byte chunks per key row
   constexpr int RS = HD * 2 + 16;                           // padded row stride (bytes)

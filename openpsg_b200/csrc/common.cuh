@@ -48,10 +48,6 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // Called right after pdl_wait: one kernel of look-ahead, no pile-up of waiting grids.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_then_trigger() { pdl_wait(); pdl_trigger(); }
-// Small kernels of the LLM decode loop: let the NEXT kernel be scheduled before this one has even started its work, so a
-// weight-streaming GEMM two launches down the stream can already fill its ring (gemm_skinny.cu, OPSG_GEMM_W_CONST).  Safe
-// for any kernel: a dependent still blocks in its own pdl_wait until this grid -- which itself waits here -- has completed.
-__device__ __forceinline__ void pdl_trigger_then_wait() { pdl_trigger(); pdl_wait(); }
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier

@@ -533,8 +533,6 @@ extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf
   OPSG_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm_streamk: lda/ldw must be multiples of 8 elements (TMA)");
   OPSG_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
                  "gemm_streamk: A/W/workspace must be 16-byte aligned");
-  const int w_const = out_mode & OPSG_GEMM_W_CONST;
-  out_mode &= ~OPSG_GEMM_W_CONST;
   OPSG_CHECK_ARG(out_mode == OPSG_OUT_BF16 || out_mode == OPSG_OUT_F32, "gemm_streamk: out_mode must be BF16 or F32");
   OPSG_CHECK_ARG(act >= OPSG_ACT_NONE && act <= OPSG_ACT_RELU, "gemm_streamk: bad activation");
   OPSG_CHECK_ARG(!residual || ldr >= N, "gemm_streamk: ldr too small");
@@ -542,7 +540,7 @@ extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf
   // layout it does not take (N or a leading dimension not a multiple of 4) falls through to stream-K below
   static const bool skinny = [] { const char* e = getenv("OPSG_SKINNY"); return e ? atoi(e) != 0 : true; }();
   if (skinny) {
-    rc = launch_gemm_skinny(A, lda, W, ldw, D, ldd, M, N, K, bias, residual, ldr, act, out_mode | w_const, workspace, workspace_bytes,
+    rc = launch_gemm_skinny(A, lda, W, ldw, D, ldd, M, N, K, bias, residual, ldr, act, out_mode, workspace, workspace_bytes,
                             reinterpret_cast<cudaStream_t>(stream));
     if (rc != OPSG_E_UNSUPPORTED) return rc;
   }

@@ -11,16 +11,12 @@
 //     (TMA -> small shared-memory ring -> tcgen05.st by the warp that owns the lane quadrant), never re-read from L2,
 //     and no shared-memory operand traffic for A at all;
 //   * CTA (slice s, lane g of G = floor(SMs / S)) streams only weights: n-tiles g, g+G, ... of 64 weight rows, one 8 KB
-//     K-block per pipeline stage, 20 stages (160 KB of weights in flight per SM), issued by THREE producer warps;
+//     K-block per pipeline stage, 23 stages (184 KB of weights in flight per SM);
 //   * tcgen05.mma A-from-TMEM ("TS"), M = 128, N = 64: 32 cycles per K = 16 step, fp32 accumulators double-buffered;
-//     Round 1 measured ~3.8 TB/s whatever the number of stages and blamed the TMA unit.  scripts/ubench/tma_stream.cu
-//     (profiles/r2_tma_stream.md) shows what it is: ONE warp's wait / expect_tx / cp.async.bulk.tensor loop issues only
-//     ~2.9 M requests/s, i.e. 3.5 TB/s over the chip with 8 KB boxes and 6.4 TB/s with 16 KB boxes or with two issuing
-//     warps; ring depth beyond 64 KB per SM changes nothing.  Hence kWProducers warps, each taking every 3rd stage;
-//   * with OPSG_GEMM_W_CONST (model weights) the producers do not wait for the preceding kernel of the stream (programmatic
-//     dependent launch): the ring fills while the reduction / LayerNorm kernels before this GEMM still run.  The kernel
-//     therefore leaves 19 KB of the SM's shared memory free -- a waiting grid that fills the SM cannot become resident
-//     next to the small kernels it is supposed to overlap;
+//     Measured (scripts/kbench.py streamk, profiles/r1_llm_decode.md): the stream runs at ~3.8 TB/s whatever the number of
+//     stages -- one SM's TMA unit keeps only ~32 KB of requests outstanding, ~14 B/clk at DRAM latency; weights pre-tiled so that
+//     every stage is one contiguous 8 KB read change nothing and a cp.async loader (4 warps, ~140 KB in flight)
+//     was slower (2.2-3 TB/s), so the TMA producer stays;
 //   * the epilogue warps write this slice's fp32 partial rows to a workspace [S][M][N] with plain stores, and
 //     skinny_finalize_kernel sums the S partials in a fixed order (deterministic, no atomics) and applies
 //     bias / activation / residual.  The workspace (<= 16 MB for the decoder GEMMs) lives in L2 between the two kernels.
@@ -35,15 +31,12 @@ namespace sk {
 constexpr int kBN = 64;                 // weight rows per n-tile (= MMA N)
 constexpr int kBK = 64;                 // 64 bf16 = 128 B = one swizzle span
 constexpr int kStageBytes = kBN * 128;  // one K-block of one n-tile
-constexpr int kThreads = 288;           // warps 0,7,8 W producers, warp 1 MMA, warps 2-5 epilogue (lane quadrants 2,3,0,1), warp 6 A producer
-constexpr int kWProducers = 3;          // one warp issues ~2.9 M TMA requests/s (8 KB each: 3.5 TB/s over the chip, scripts/ubench/tma_stream.cu)
+constexpr int kThreads = 224;           // warp 0 W producer, warp 1 MMA, warps 2-5 epilogue (lane quadrants 2,3,0,1), warp 6 A producer
 constexpr int kMaxStages = 24;
 constexpr int kMaxKS = 12;              // K-blocks per slice: 12 x 32 TMEM columns of A + 2 x 64 accumulator columns = 512
 constexpr int kMaxAStages = 12;          // (ring depth is Params::a_stages)
 //             // shared-memory ring the activation K-blocks pass through on their way to TMEM
-// 208 KB, not the full 227: the small kernels around a decode GEMM (reduction, LayerNorm) need 1 KB of shared memory per
-// resident CTA, and this kernel must be able to become resident NEXT to them to stream its weights ahead (w_const)
-constexpr int kSmemLimit = 212992;
+constexpr int kSmemLimit = 232448;
 constexpr int kBarrierBytes = 1024;
 constexpr int kAccCols = 2 * kBN;
 
@@ -56,7 +49,6 @@ struct Params {
   int MR;               // M rounded up to 8 rows (rows of an activation K-block in the ring: MR * 128 B)
   int stages;
   int a_stages;         // depth of the shared-memory ring the activation K-blocks pass through on their way to TMEM
-  int w_const;          // W is a constant of the stream (model weights): stream it before the preceding kernel has completed
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -94,11 +86,6 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int kb0 = slice * p.KS;
   const int nkb = min(p.KS, kb_total - kb0);               // >= 1 by construction (host)
 
-  // Constant weights (OPSG_GEMM_W_CONST): let the next kernel of the stream be scheduled at once and do NOT wait for the
-  // preceding kernel before streaming W -- only the activation producer waits (the epilogue's workspace writes follow the
-  // MMAs, which follow the activations, so they are ordered behind that wait too).  The ring (184 KB per SM, 27 MB over the
-  // chip) fills while the small kernels between two GEMMs of a decode step (reduction, LayerNorm, attention) still run.
-  if (p.w_const) pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -126,27 +113,25 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_a = tmem_base + kAccCols;            // A slice: 32 columns per K-block
-  if (!p.w_const) pdl_wait_then_trigger();   // everything above overlaps the previous kernel (programmatic dependent launch)
+  pdl_wait_then_trigger();          // everything above overlaps the previous kernel (programmatic dependent launch)
 
-  if (warp == 0 || warp >= 7) {
-    // ===================== weight producers (TMA): warp w takes every kWProducers-th stage =====================
-    // A single warp's issue loop tops out at ~2.9 M requests/s whatever the ring depth; three warps lift the cap above HBM speed.
-    const int my_tiles = (p.n_tiles - g + p.G - 1) / p.G;
-    const int total = my_tiles * nkb;
-    for (int i = (warp == 0 ? 0 : warp - 6); i < total; i += kWProducers) {
-      const int stage = i % p.stages;
-      const uint32_t phase = (i / p.stages) & 1;
-      const int n_t = g + (i / nkb) * p.G, kb = i % nkb;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (elect_one_sync()) {
-        mbar_expect_tx(&full_bar[stage], kStageBytes);
-        tma_load_2d(smem_w + stage * kStageBytes, &tmW, &full_bar[stage], (kb0 + kb) * kBK, n_t * kBN);
+  if (warp == 0) {
+    // ===================== weight producer (TMA) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int n_t = g; n_t < p.n_tiles; n_t += p.G) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_2d(smem_w + stage * kStageBytes, &tmW, &full_bar[stage], (kb0 + kb) * kBK, n_t * kBN);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
     }
   } else if (warp == 6) {
     // ===================== activation producer: the slice's K-blocks through the ring, once =====================
-    if (p.w_const) pdl_wait();
     for (int kb = 0; kb < nkb; ++kb) {
       const int b = kb % p.a_stages;
       mbar_wait(&a_empty[b], ((kb / p.a_stages) & 1) ^ 1);
@@ -273,7 +258,7 @@ struct FinalizeParams {
 
 // out[m][n] = act(sum_s ws[s][m][n] + bias[n]) + residual[m][n]; 4 columns per thread, slices summed in index order
 __global__ void __launch_bounds__(256) skinny_finalize_kernel(const FinalizeParams p) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   const int n4 = p.N >> 2;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(p.M) * n4) return;
@@ -347,8 +332,6 @@ int launch_gemm_skinny(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw,
                        const float* bias, const opsg_bf16* residual, int ldr, int act, int out_mode, void* workspace,
                        size_t workspace_bytes, cudaStream_t stream) {
   using namespace sk;
-  const int w_const = (out_mode & OPSG_GEMM_W_CONST) ? 1 : 0;
-  out_mode &= ~OPSG_GEMM_W_CONST;
   if ((N % 4) != 0 || (ldd % 4) != 0 || (residual && (ldr % 4) != 0)) return OPSG_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(D) & 15) != 0 || (bias && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) ||
       (residual && (reinterpret_cast<uintptr_t>(residual) & 7) != 0))
@@ -359,7 +342,6 @@ int launch_gemm_skinny(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw,
   p.MR = (M + 7) / 8 * 8;
   if (p.S > sms) return OPSG_E_UNSUPPORTED;
   p.M = M; p.N = N; p.K = K;
-  p.w_const = w_const;
   p.n_tiles = (N + kBN - 1) / kBN;
   p.G = sms / p.S;
   if (p.G > p.n_tiles) p.G = p.n_tiles;

@@ -282,7 +282,7 @@ __global__ void gather_rows_bf16_kernel(const uint4* __restrict__ src, int row_v
 __global__ void embed_gather_kernel(const __nv_bfloat16* __restrict__ table, int d, const int32_t* __restrict__ ids,
                                     const __nv_bfloat16* __restrict__ pos_table, const int32_t* __restrict__ pos, int n_rows,
                                     __nv_bfloat16* __restrict__ out, int ld_out) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   const int vec = d / 8;
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(n_rows) * vec) return;
@@ -328,7 +328,7 @@ __global__ void llm_build_prefix_kernel(const __nv_bfloat16* __restrict__ proj, 
 // flight per thread (the first cut walked the row with dependent 4-byte loads: 94 us for 100 x 50272 logits).
 __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
                                                            int32_t* __restrict__ out) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   const int row = blockIdx.x;
@@ -474,7 +474,7 @@ template <int CH>                                         // CH x 256 x 8 column
 __global__ void __launch_bounds__(256) layernorm_row_cta_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float eps,
                                                                 __nv_bfloat16* __restrict__ y, int cols) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   __shared__ float red[2][8];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const __nv_bfloat16* xr = x + static_cast<size_t>(blockIdx.x) * cols;

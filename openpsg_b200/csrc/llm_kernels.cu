@@ -12,7 +12,7 @@ static inline int ceil_div_ll(long long a, long long b) { return static_cast<int
 __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld_x,
                                                            const float* __restrict__ weight, float eps,
                                                            __nv_bfloat16* __restrict__ y, int ld_y, int cols) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   __shared__ float red[8];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const __nv_bfloat16* xr = x + static_cast<size_t>(blockIdx.x) * ld_x;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) rope_bf16_kernel(__nv_bfloat16* __restric
                                                         int num_heads, int head_dim, const int32_t* __restrict__ pos,
                                                         const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                         int table_rows) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   const int half = head_dim / 2, vec = half / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(rows) * n_parts * num_heads * vec;
@@ -104,7 +104,7 @@ __device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g))
 // out[r, c] = silu(gu[r, c]) * gu[r, ffn + c]   (gate | up halves of one fused projection)
 __global__ void __launch_bounds__(256) swiglu_bf16_kernel(const __nv_bfloat16* __restrict__ gu, int ld_gu, int rows, int ffn,
                                                           __nv_bfloat16* __restrict__ out, int ld_out) {
-  pdl_trigger_then_wait();
+  pdl_wait_then_trigger();
   const int vec = ffn / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * vec) return;

@@ -11,10 +11,13 @@
 //   1. mask_pool_labels_kernel: the three-stage mask chain of ALL objects collapses into one label map at feature
 //      resolution (label = first listed object whose id equals the source pixel of the panoptic map, N = nobody / padding);
 //      objects that repeat an id share the label of the first one (`rep`).
-//   2. mask_pool_accum_kernel: CTA = 16 channels x a strip of pixels.  A warp takes 128 consecutive pixels: 16-byte loads
-//      of the labels and of 16 channel rows (all in flight together), then for every distinct label of the segment a
-//      recursive-halving shuffle reduction (16 values x 32 lanes in 16 shuffles) into the warp's PRIVATE shared-memory
-//      accumulator [label][channel].  No atomics anywhere: the CTA sums its warps in a fixed order and writes one partial
+//   2. mask_pool_accum_kernel: CTA = 16 channels x a strip of pixel tiles.  A warp takes a 32 x 4 pixel tile (8 lanes x 16
+//      bytes per row = full 128-byte lines, 4 rows): 16-byte loads of the labels and of 16 channel rows (all in flight
+//      together), then for every distinct label of the tile a recursive-halving shuffle reduction (16 values x 32 lanes
+//      in 16 shuffles) into the warp's PRIVATE shared-memory accumulator [label][channel].  The tile is 2-D because the
+//      kernel is instruction-bound on those reduction rounds (round 2 ncu: ALU pipe 54 %, 2.5 TB/s with 128 x 1 pixel
+//      segments that cross ~3 panoptic regions each); a 32 x 4 tile mostly sees one label, which also takes a path
+//      without per-pixel selects.  No atomics anywhere: the CTA sums its warps in a fixed order and writes one partial
 //      per strip; the reduction over strips is a second small kernel, also in fixed order -> bit-reproducible.
 //   3. mask_pool_finalize_kernel: division, class embedding, background feature; pair_concat_kernel: the N^2 gather.
 // Algorithmic bytes: C*h*w*4 (features) + h*w*4 (labels, re-read per channel block from L2).
@@ -26,7 +29,6 @@ namespace opsg {
 constexpr int kMpCB = 16;            // channels per CTA
 constexpr int kMpSegPx = 128;        // pixels per warp step (32 lanes x 4)
 constexpr int kMpWarps = 8;
-constexpr int kMpSegsPerStrip = 16;  // 2048 pixels per CTA
 
 __device__ __forceinline__ int mp_nearest_src(int dst, int in_size, int out_size) {
   const float scale = __fdiv_rn(static_cast<float>(in_size), static_cast<float>(out_size));
@@ -94,8 +96,8 @@ __device__ __forceinline__ float mp_reduce16(float (&v)[16], int lane) {
 }
 
 __global__ void __launch_bounds__(kMpWarps * 32)
-mask_pool_accum_kernel(const float* __restrict__ feat, int C, int hw, const int32_t* __restrict__ label, int n_labels,
-                       float* __restrict__ partial, float* __restrict__ pcount) {
+mask_pool_accum_kernel(const float* __restrict__ feat, int C, int h, int w, int segs_per_strip, const int32_t* __restrict__ label,
+                       int n_labels, float* __restrict__ partial, float* __restrict__ pcount) {
   pdl_wait_then_trigger();
   extern __shared__ float s_acc[];                      // [warp][label][16 channels] (+ [warp][label] counts)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,13 +108,32 @@ mask_pool_accum_kernel(const float* __restrict__ feat, int C, int hw, const int3
   for (int i = lane; i < n_labels * kMpCB; i += 32) acc[i] = 0.f;
   for (int i = lane; i < n_labels; i += 32) cnt[i] = 0.f;
   __syncwarp();
-  const bool vec = (hw & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(label) & 15) == 0;
-  for (int seg = warp; seg < kMpSegsPerStrip; seg += kMpWarps) {
-    const int px = (strip * kMpSegsPerStrip + seg) * kMpSegPx + lane * 4;
-    if ((strip * kMpSegsPerStrip + seg) * kMpSegPx >= hw) break;            // warp-uniform
+  const int hw = h * w;
+  // 2-D tiles need 16-byte aligned rows; otherwise a segment is 128 consecutive pixels of the flattened map
+  const bool vec = (w & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(label) & 15) == 0;
+  const int tiles_x = (w + 31) >> 5;
+  const int n_segs = vec ? tiles_x * ((h + 3) >> 2) : (hw + kMpSegPx - 1) / kMpSegPx;
+  for (int seg = warp; seg < segs_per_strip; seg += kMpWarps) {
+    const int sg = strip * segs_per_strip + seg;
+    if (sg >= n_segs) break;                                                // warp-uniform
+    int px = sg * kMpSegPx + lane * 4;
+    bool inb = true;
+    if (vec) {
+      const int ty = sg / tiles_x, tx = sg - ty * tiles_x;
+      const int y = ty * 4 + (lane >> 3), x = tx * 32 + (lane & 7) * 4;
+      inb = y < h && x < w;
+      px = y * w + x;
+    }
     int lab[4];
     float v[kMpCB][4];
-    if (vec && px + 3 < hw) {
+    if (vec && !inb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lab[j] = -1;
+#pragma unroll
+      for (int cc = 0; cc < kMpCB; ++cc)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[cc][j] = 0.f;
+    } else if (vec) {
       const int4 l4 = __ldg(reinterpret_cast<const int4*>(label + px));
       lab[0] = l4.x; lab[1] = l4.y; lab[2] = l4.z; lab[3] = l4.w;
 #pragma unroll
@@ -148,12 +169,17 @@ mask_pool_accum_kernel(const float* __restrict__ feat, int C, int hw, const int3
 #pragma unroll
       for (int j = 0; j < 4; ++j) hit |= (((todo >> j) & 1u) && lab[j] == cur) ? (1u << j) : 0u;
       todo &= ~hit;
+      if (__all_sync(0xffffffffu, hit == 0xFu)) {                           // the whole tile is one label: no selects
 #pragma unroll
-      for (int cc = 0; cc < kMpCB; ++cc) {
-        float s = 0.f;
+        for (int cc = 0; cc < kMpCB; ++cc) part[cc] = (v[cc][0] + v[cc][1]) + (v[cc][2] + v[cc][3]);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s += ((hit >> j) & 1u) ? v[cc][j] : 0.f;
-        part[cc] = s;
+        for (int cc = 0; cc < kMpCB; ++cc) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s += ((hit >> j) & 1u) ? v[cc][j] : 0.f;
+          part[cc] = s;
+        }
       }
       const float total = mp_reduce16(part, lane);
       if (!(lane & 1)) acc[cur * kMpCB + (lane >> 1)] += total;
@@ -240,7 +266,21 @@ __global__ void pair_concat_kernel(const float* __restrict__ obj, int N, int C, 
 }
 
 static inline int mp_ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
-static inline int mp_strips(int hw) { return mp_ceil_div(hw, kMpSegsPerStrip * kMpSegPx); }
+// Strip layout of the accumulation kernel: the map is cut into segments (32 x 4 pixel tiles when rows are 16-byte aligned,
+// else 128 consecutive pixels); a CTA takes `per_strip` consecutive segments of 16 channels.  The strip count is chosen so
+// that strips x channel blocks fills the SMs twice (two resident CTAs per SM at 116 registers) in ONE wave.
+static inline void mp_layout(int channels, int h, int w, int* strips, int* per_strip) {
+  const int segs = (w & 3) == 0 ? ((w + 31) >> 5) * ((h + 3) >> 2) : mp_ceil_div(static_cast<long long>(h) * w, kMpSegPx);
+  const int cblks = mp_ceil_div(channels, kMpCB);
+  int sms = opsg_num_sms();
+  if (sms <= 0) sms = kNumSMsB200;
+  int want = 2 * sms / cblks;
+  if (want < 1) want = 1;
+  if (want > segs) want = segs;
+  *per_strip = mp_ceil_div(segs, want);
+  if (*per_strip < kMpWarps && segs >= kMpWarps) *per_strip = kMpWarps;     // every warp of a CTA gets a segment
+  *strips = mp_ceil_div(segs, *per_strip);
+}
 
 }  // namespace opsg
 
@@ -265,7 +305,9 @@ extern "C" int opsg_mask_pool_labels(const int32_t* pan, int pan_h, int pan_w, i
 
 extern "C" size_t opsg_mask_pool_workspace_bytes(int channels, int h, int w, int num_objects) {
   if (channels <= 0 || h <= 0 || w <= 0 || num_objects <= 0) return 0;
-  const size_t nl = static_cast<size_t>(num_objects) + 1, strips = mp_strips(h * w);
+  int n_strips, per_strip;
+  mp_layout(channels, h, w, &n_strips, &per_strip);
+  const size_t nl = static_cast<size_t>(num_objects) + 1, strips = static_cast<size_t>(n_strips);
   return (strips * nl * channels + strips * nl + nl * channels + nl) * sizeof(float);
 }
 
@@ -283,7 +325,9 @@ extern "C" int opsg_mask_pool_pairs(const float* feat, int channels, int h, int 
   OPSG_CHECK_ARG(!(cls_mode == 2 && use_background), "mask_pool_pairs: background feature cannot be added to a 'cat' embedding "
                                                      "(the reference's broadcast fails there too)");
   OPSG_CHECK_ARG(workspace_bytes >= opsg_mask_pool_workspace_bytes(channels, h, w, num_objects), "mask_pool_pairs: workspace too small");
-  const int hw = h * w, nl = num_objects + 1, strips = mp_strips(hw);
+  const int hw = h * w, nl = num_objects + 1;
+  int strips, per_strip;
+  mp_layout(channels, h, w, &strips, &per_strip);
   float* partial = workspace;
   float* pcount = partial + static_cast<size_t>(strips) * nl * channels;
   float* sums = pcount + static_cast<size_t>(strips) * nl;
@@ -297,7 +341,7 @@ extern "C" int opsg_mask_pool_pairs(const float* feat, int channels, int h, int 
     configured_bytes = 160 * 1024;
   }
   launch_kernel(mask_pool_accum_kernel, dim3(strips, mp_ceil_div(channels, kMpCB)), kMpWarps * 32, smem, ST(stream), feat, channels,
-                hw, label, nl, partial, pcount);
+                h, w, per_strip, label, nl, partial, pcount);
   OPSG_CHECK_LAUNCH("mask_pool_accum_kernel");
   launch_kernel(mask_pool_reduce_kernel, mp_ceil_div(static_cast<long long>(nl) * channels, 256), 256, 0, ST(stream), partial, pcount,
                 strips, nl, channels, sums, counts);

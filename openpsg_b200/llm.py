@@ -201,7 +201,6 @@ class LLMDecodeEngine:
         self.use_cuda_graphs = use_cuda_graphs
         # decode steps (rows <= 128) take the K-sliced small-M GEMM (csrc/gemm_skinny.cu); OPSG_LLM_SMALL_M=0 keeps the tiled one
         self.small_m = os.environ.get("OPSG_LLM_SMALL_M", "1") == "1"
-        self.w_const = os.environ.get("OPSG_LLM_WCONST", "1") == "1"     # decode GEMMs stream their weights ahead of the dependency
         self.prefetch = int(os.environ.get("OPSG_LLM_PREFETCH", "0"))         # L2 prefetch of the next GEMM's weights (decode): 0 off
         self._graphs = GraphCache(max_entries=2)        # (hidden shape, k, T, max_new_tokens) -> captured generate()
 
@@ -219,8 +218,7 @@ class LLMDecodeEngine:
         # 17 / 11 / 21 / 20 us for qkv / out / fc1 / fc2 at k = 100 inside a graph against 22 / 13 / 24 / 40 us for the tiled
         # kernel (scripts/kbench.py streamk, profiles/r1_llm_decode.md).
         decode = self.small_m and h.shape[0] <= 128
-        # the packed weights are constants of the stream: the small-M kernel streams them before the preceding kernel completes
-        gemm = (lambda *a, **kw: ops.gemm_small_m(*a, w_const=self.w_const, **kw)) if decode else ops.gemm
+        gemm = ops.gemm_small_m if decode else ops.gemm
         # decode, optional (self.prefetch, off by default): start pulling the NEXT GEMM's weights into L2 while the small kernels
         # between two GEMMs run (mode 2: issued after a GEMM, before attention / LayerNorm) or already while the current GEMM
         # streams (mode 1).  Measured on cfg3: mode 1 164 ms per image against 121 ms without (the prefetch competes with the

@@ -10,7 +10,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, GEMM_W_CONST, OUT_BF16, OUT_F32, OUT_F32_ATOMIC  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, OUT_BF16, OUT_F32, OUT_F32_ATOMIC  # noqa: F401
 
 launch_count = 0   # kernels enqueued through this module (bench.py reports it as gpu_launches)
 
@@ -164,11 +164,9 @@ _streamk_ws_keep = []  # outgrown workspaces stay alive: captured CUDA graphs ma
 
 def gemm_small_m(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
                  residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
-                 out_dtype=torch.bfloat16, w_const: bool = False) -> torch.Tensor:
+                 out_dtype=torch.bfloat16) -> torch.Tensor:
     """Weight-streaming GEMM for M <= 128 rows (LLM decode): K-sliced, activations resident in TMEM, deterministic
-    fp32 partial reduction in a second kernel (csrc/gemm_skinny.cu).  ``w_const``: ``w`` is a model weight that nothing
-    queued earlier on the stream writes -- the kernel streams it before the preceding kernel has completed
-    (OPSG_GEMM_W_CONST)."""
+    fp32 partial reduction in a second kernel (csrc/gemm_skinny.cu)."""
     _cuda(a, torch.bfloat16, "a"); _cuda(w, torch.bfloat16, "w")
     M, K = a.shape
     N = w.shape[0]
@@ -185,7 +183,7 @@ def gemm_small_m(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] 
         _streamk_ws[a.device] = ws
     if residual is not None:
         _cuda(residual, torch.bfloat16, "residual")
-    mode = (OUT_BF16 if out.dtype == torch.bfloat16 else OUT_F32) | (GEMM_W_CONST if w_const else 0)
+    mode = OUT_BF16 if out.dtype == torch.bfloat16 else OUT_F32
     with _timed("gemm_streamk", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)):
         _lib.check(lib.opsg_gemm_bf16_streamk(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
                                               _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,

@@ -74,7 +74,6 @@ def bench_streamk(iters, flush):
         bias = torch.randn(N, device=DEV)
         out = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
         for fn_name, fn in (("skinny", lambda w: ops.gemm_small_m(a, w, bias, out=out)),
-                            ("skinny_w_const", lambda w: ops.gemm_small_m(a, w, bias, out=out, w_const=True)),
                             ("tiled", lambda w: ops.gemm(a, w, bias, out=out))):
             for w in ws[:2]:
                 fn(w)

@@ -20,7 +20,7 @@ sel = torch.randperm(1600, generator=g)[:k].to(torch.int32).to(dev)
 ids = torch.randint(4, 50272, (k, T), generator=g).to(torch.int32).to(dev)
 mask = torch.ones((k, T), dtype=torch.int32, device=dev)
 ref = None
-for tag, kw in (("wait_for_predecessor", dict(w_const=False)), ("weights_streamed_ahead", dict(w_const=True))):
+for tag, kw in (("baseline", dict(prefetch=0)), ("prefetch_gaps", dict(prefetch=2))):
     eng = build_llm_engine(lm, proj, dev)
     for a, b in kw.items():
         setattr(eng, a, b)

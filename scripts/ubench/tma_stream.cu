@@ -17,7 +17,9 @@ struct P {
   int K;             // columns (elements) of the matrix
   int rows_total;
   long long unit0;   // first (row block, k block) unit of this launch
-  int mode;          // 0: 2-D tensor TMA, 1: 1-D bulk copies of box_rows*128 contiguous bytes, 2: as 0 but two producer warps
+  int mode;          // 0: 2-D tensor TMA, 1: 1-D bulk copies of box_rows*128 contiguous bytes, 2: as 0 but two producer warps,
+                     // 3: 2-D TMA in the small-M GEMM's traversal order (4 K slices x 37 CTAs, n-tiles g, g+37, ...; 10 K-blocks
+                     //    per tile), three producer warps, 4: 1-D bulk (pre-tiled weights), three producer warps
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -41,29 +43,44 @@ __global__ void __launch_bounds__(128, 1) stream_kernel(const __grid_constant__ 
   __syncthreads();
   // the matrix is walked as (row block, k block) pairs; CTA b takes pairs b, b + grid, ...
   const int kblocks = p.K / 64;
-  const int nprod = p.mode == 2 ? 2 : 1;
+  const int nprod = p.mode >= 3 ? 3 : (p.mode == 2 ? 2 : 1);
   if (warp < nprod) {
+    // incremental stage / phase / K-block counters: no integer divisions in the issue loop
+    int stage = warp % p.stages;
+    uint32_t phase = (warp / p.stages) & 1;
+    int t10 = warp / 10, k10 = warp % 10;                     // mode 3: tile-in-CTA and K-block counters
+    const int slice = blockIdx.x % 4, g = blockIdx.x / 4;
+    const long long tile0 = (p.unit0 / (static_cast<long long>(p.n_boxes) * 148)) * 850 + g;
+    long long unit = p.unit0 + static_cast<long long>(warp) * gridDim.x + blockIdx.x;
+    int rb = static_cast<int>(unit / kblocks), kbm = static_cast<int>(unit % kblocks);      // modes 0 / 2
+    const int d_rb = (nprod * static_cast<int>(gridDim.x)) / kblocks, d_kb = (nprod * static_cast<int>(gridDim.x)) % kblocks;
     for (int i = warp; i < p.n_boxes; i += nprod) {
-      const int stage = i % p.stages;
-      const uint32_t phase = (i / p.stages) & 1;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one_sync()) {
-        const long long unit = p.unit0 + static_cast<long long>(i) * gridDim.x + blockIdx.x;
         mbar_expect_tx(&full[stage], stage_bytes);
-        if (p.mode == 1) {
+        if (p.mode == 3) {
+          tma_load_2d(smem + stage * stage_bytes, &tm, &full[stage], (slice * 10 + k10) * 64, static_cast<int>((tile0 + t10 * 37) * p.box_rows));
+        } else if (p.mode == 1 || p.mode == 4) {
           bulk_load_1d(smem + stage * stage_bytes, base + unit * stage_bytes, stage_bytes, &full[stage]);
         } else {
-          const int rb = static_cast<int>(unit / kblocks), kb = static_cast<int>(unit % kblocks);
-          tma_load_2d(smem + stage * stage_bytes, &tm, &full[stage], kb * 64, rb * p.box_rows);
+          tma_load_2d(smem + stage * stage_bytes, &tm, &full[stage], kbm * 64, rb * p.box_rows);
         }
       }
       __syncwarp();
+      stage += nprod;
+      while (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+      k10 += nprod;
+      while (k10 >= 10) { k10 -= 10; ++t10; }
+      unit += static_cast<long long>(nprod) * gridDim.x;
+      rb += d_rb; kbm += d_kb;
+      if (kbm >= kblocks) { kbm -= kblocks; ++rb; }
     }
-  } else if (warp == 2) {
+  } else if (warp == 3) {
     unsigned acc = 0;
-    for (int i = 0; i < p.n_boxes; ++i) {
-      const int stage = i % p.stages;
-      const uint32_t phase = (i / p.stages) & 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < p.n_boxes; ++i, ++stage) {
+      if (stage == p.stages) { stage = 0; phase ^= 1; }
       mbar_wait(&full[stage], phase);
       acc += smem[stage * stage_bytes + (threadIdx.x & 31) * 4];
       __syncwarp();
@@ -85,13 +102,15 @@ int main() {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int box_rows_list[] = {64, 128, 256};
-  for (int mode = 0; mode < 3; ++mode)
+  for (int mode : {0, 2, 3})
     for (int br : box_rows_list)
       for (int smem_kb : {32, 64, 128, 192}) {
         P p;
         p.box_rows = br; p.K = K; p.rows_total = (int)rows; p.mode = mode;
         p.stages = smem_kb * 1024 / (br * 128);
         if (p.stages < 1 || p.stages > 64) continue;
+        if (mode == 3 && br != 64) continue;
+        if (p.stages < 3) continue;
         const long long total_boxes = rows / br * (K / 64);
         p.n_boxes = (int)(total_boxes / 148 / 8);          // 1/8 of the matrix per launch (~256 MB)
         CUtensorMap tm;
@@ -116,7 +135,7 @@ int main() {
         cudaEventElapsedTime(&ms, e0, e1);
         const double bytes = (double)p.n_boxes * 148 * br * 128 * reps;
         printf("mode %d (%s) box %3d rows (%2d KB) stages %2d (%3d KB in flight): %.2f TB/s\n", mode,
-               mode == 0 ? "2-D TMA" : mode == 1 ? "1-D bulk" : "2-D TMA, 2 producer warps", br, br * 128 / 1024, p.stages,
+               mode == 0 ? "2-D TMA" : mode == 1 ? "1-D bulk" : mode == 2 ? "2-D TMA, 2 producer warps" : mode == 3 ? "2-D TMA, GEMM order, 3 warps" : "1-D bulk, 3 warps", br, br * 128 / 1024, p.stages,
                smem_kb, bytes / (ms * 1e-3) / 1e12);
       }
   return 0;
