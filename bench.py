@@ -317,6 +317,36 @@ def _llm_legs(run: Runner, rank, world, steps, peaks):
     return out
 
 
+def _mask_pool_leg(dev, peaks, iters=10):
+    """K11 (a11: per-mask feature pooling + pair gather of the V3-era detectors) on one cfg2 image: label map from the
+    panoptic map, then opsg_mask_pool_pairs (accumulate / reduce / finalize / pair concat = 4 launches), L2 flushed between
+    timed calls (the 67 MB map would otherwise sit in the 126 MB L2)."""
+    from openpsg_b200 import ops
+    wl = synth.WORKLOADS[WORKLOAD]
+    inp = synth.make_image_inputs(wl, 0)
+    ids = torch.tensor([int(i) for i in inp["object_info"][0]["object_id_list"]], dtype=torch.int32, device=dev)
+    pan = inp["object_info"][0]["pan_results"].to(torch.int32).to(dev)
+    feat = inp["mask_features"][0].to(dev)
+    label, rep_ = ops.mask_pool_labels(pan, (wl.height, wl.width), (wl.height, wl.width), feat.shape[-2:], ids)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ops.mask_pool_pairs(feat, label, len(ids), rep=rep_)
+    times = []
+    for _ in range(iters):
+        flush.zero_()
+        ops.profile_begin()
+        ops.mask_pool_pairs(feat, label, len(ids), rep=rep_)
+        times.append(ops.profile_end()["mask_pool_pairs"]["ms"])
+    times.sort()
+    ms = times[len(times) // 2]
+    nbytes = 4.0 * feat.numel() + 4.0 * label.numel()
+    t = _traffic().get("mask_pool_accum", {})
+    return {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": t.get("dram_bytes_per_launch"),
+            "traffic_source": t.get("source"), "launches": 4, "avg_launch_ms": ms, "algorithmic_bytes_per_launch": nbytes,
+            "note": "one opsg_mask_pool_pairs call = 4 launches (accumulate over the 67 MB map, fixed-order strip reduction, "
+                    "normalise, N^2 pair concat), median of %d calls, L2 flushed before each; traffic = the accumulate kernel" % iters}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from openpsg_b200 import ops
@@ -432,6 +462,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     peaks = _peaks()
+    mask_pool = _mask_pool_leg(dev, peaks) if rank == 0 else None
     llm = None if args.no_llm else _llm_legs(run, rank, world, max(2, args.steps // 5), peaks)
 
     if rank == 0:
@@ -490,6 +521,7 @@ def run_ours(args):
             "roofline_xattn": roof("xattn_pairs", x, peaks["tf_sustained"]),
             "roofline_hbm_kernels": {n: r for n in ("layernorm_bf16", "pair_mask_bits", "exist_filter_topk", "patch_im2col",
                                                     "qformer_embed_ln") if (r := roof_hbm(n))},
+            "roofline_mask_pool": mask_pool,
             "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
         }
         if llm is not None:

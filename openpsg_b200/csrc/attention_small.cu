@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(128) qformer_self_attn_kernel(const SmallAttnP
 template <int HD, int NK>
 static int launch_small_attn(const SmallAttnParams& p, int nseq, cudaStream_t st) {
   constexpr int smem = (64 * (HD + 8) + 2 * NK * (HD + 8)) * 2 + NK;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     int rc = check_cuda(cudaFuncSetAttribute(small_attn_kernel<HD, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                         "cudaFuncSetAttribute(small_attn)");
@@ -672,7 +673,8 @@ static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
   if (use_smem && ctx <= 256 && per_warp <= budget) {
     int wpc = budget / per_warp;
     if (wpc > 4) wpc = 4;
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
     if (!configured) {
       int rc = check_cuda(cudaFuncSetAttribute(decode_attn_smem_kernel<HD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
                           "cudaFuncSetAttribute(decode_attn_smem)");
@@ -753,7 +755,8 @@ extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* share
   static const int use_pipelined = [] { const char* e = getenv("OPSG_SELF_ATTN_PIPELINED"); return e ? atoi(e) : 1; }();
   if (use_pipelined && head_dim == kQfHD && n_query + T <= kQfNK && (((uintptr_t)qkv | (uintptr_t)ctx_out) & 15) == 0) {
     constexpr int smem = kQfStages * kQfStageBytes;
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
     if (!configured) {
       rc = check_cuda(cudaFuncSetAttribute(qformer_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                       "cudaFuncSetAttribute(qformer_self_attn)");

@@ -409,7 +409,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES>;
   static_assert(S::kTotal <= 232448, "shared memory budget exceeded");
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     int rc = check_cuda(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              S::kTotal), "cudaFuncSetAttribute(gemm)");
@@ -560,7 +561,8 @@ extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf
   p.stream_k = 1; p.max_segs = max_segs; p.ws = reinterpret_cast<float*>(workspace);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   using S = GemmSmem<256, 4>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     rc = check_cuda(cudaFuncSetAttribute(gemm_bf16_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
                     "cudaFuncSetAttribute(gemm streamk)");

@@ -394,7 +394,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     int tile_seq = 0;
     if (pair < total_tiles) park_vec(0, load_vec(pair % p.n_tiles));
+#ifdef OPSG_TRACE      // epilogue clock stamps (scripts/gemm_trace.py): only in the development build (make trace)
 #define G2_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && tracer && tile_seq < 24) p.trace[(tile_seq * 5 + (slab_for_trace)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define G2_TRACE(slot) do { (void)slab_for_trace; (void)tracer; } while (0)
+#endif
     for (int tile = pair; tile < total_tiles; tile += num_pairs, ++tile_seq) {
       const int n_t = tile % p.n_tiles, m2_t = tile / p.n_tiles;
       const int row0 = m2_t * 2 * kBM + static_cast<int>(rank) * kBM;
@@ -595,7 +599,8 @@ int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, o
   auto kernel = deep_ring ? gemm2_bf16_kernel<4, 4, 8> : (epiw == 16 ? gemm2_bf16_kernel<5, 3, 16> : gemm2_bf16_kernel<5, 3, 8>);
   const int threads = 128 + ((!deep_ring && epiw == 16) ? 16 : 8) * 32;
   const int smem_bytes = deep_ring ? smem_total<4, 4>() : smem_total<5, 3>();
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     rc = check_cuda(cudaFuncSetAttribute(gemm2_bf16_kernel<4, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<4, 4>()),
                     "cudaFuncSetAttribute(gemm 2cta <4,4,8>)");

@@ -362,7 +362,8 @@ int launch_gemm_skinny(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw,
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmW, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, kBN, kBK);
   if (rc) return rc;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     rc = check_cuda(cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit),
                     "cudaFuncSetAttribute(gemm skinny)");

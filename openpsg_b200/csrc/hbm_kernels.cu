@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(256) exist_logits_kernel(const __nv_bfloat16* 
 }
 
 // rank(i) = #{j : z_j > z_i or (z_j == z_i and j < i)};  rank < k  ->  topk[rank] = i.
+// NaN logits (never produced by finite weights) are ordered as -inf so that the order stays total: every rank is taken
+// exactly once and all k slots of topk are written.
 // Exact top-k by rank counting (ties -> lower index, as torch.topk / sort of the reference, v4:236-237): candidate i's
 // rank = #{j : z_j > z_i or (z_j == z_i and j < i)}.  A CTA ranks 32 candidates; each of its 8 warps counts over one
 // eighth of the list (lane = candidate), so a thread walks B / 8 values instead of B (25 us -> ~4 us at B = 1600).
@@ -254,12 +256,14 @@ __global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict_
   const int i = blockIdx.x * 32 + lane;
   if (threadIdx.x < 32) s_rank[threadIdx.x] = 0;
   __syncthreads();
-  const float zi = i < B ? __ldg(logits + i) : 0.f;
+  float zi = i < B ? __ldg(logits + i) : 0.f;
+  if (zi != zi) zi = -INFINITY;
   const int per = (B + 7) / 8;
   const int j0 = warp * per, j1 = min(B, j0 + per);
   int rank = 0;
   for (int j = j0; j < j1; ++j) {
-    const float zj = __ldg(logits + j);                  // same address across the warp: one broadcast load
+    float zj = __ldg(logits + j);                        // same address across the warp: one broadcast load
+    if (zj != zj) zj = -INFINITY;
     rank += (zj > zi || (zj == zi && j < i)) ? 1 : 0;
   }
   if (i < B) atomicAdd(&s_rank[lane], rank);

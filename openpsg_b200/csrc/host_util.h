@@ -27,6 +27,14 @@ struct GemmLnFold {
   float eps;
 };
 
+// Slot of the current device in a per-device flag array: function attributes (cudaFuncSetAttribute) are per device, so the
+// "already configured" flags of the launchers are kept per device ordinal.
+inline int device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+  return d;
+}
+
 #define OPSG_CHECK_ARG(cond, ...)                                   \
   do {                                                              \
     if (!(cond)) return ::opsg::set_error(OPSG_E_INVALID, __VA_ARGS__); \

@@ -300,7 +300,8 @@ llm_prefill_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 template <int HD>
 static int launch_prefill_hd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const PfParams& p,
                              cudaStream_t stream) {
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     int rc = check_cuda(cudaFuncSetAttribute(llm_prefill_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PfSmem<HD>::kTotal), "cudaFuncSetAttribute(llm_prefill_attn)");

@@ -333,7 +333,8 @@ extern "C" int opsg_mask_pool_pairs(const float* feat, int channels, int h, int 
   float* sums = pcount + static_cast<size_t>(strips) * nl;
   float* counts = sums + static_cast<size_t>(nl) * channels;
   const size_t smem = (static_cast<size_t>(kMpWarps) * nl * kMpCB + static_cast<size_t>(kMpWarps) * nl) * sizeof(float);
-  static int configured_bytes = 0;
+  static int configured_bytes_dev[64] = {};
+  int& configured_bytes = configured_bytes_dev[device_slot()];
   if (static_cast<int>(smem) > configured_bytes && smem > 48 * 1024) {
     rc = check_cuda(cudaFuncSetAttribute(mask_pool_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
                     "cudaFuncSetAttribute(mask_pool_accum)");

@@ -354,7 +354,8 @@ int launch_self_attn_pairs(const opsg_bf16* qkv, const opsg_bf16* shared_query_q
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmOt, ctx_out, (uint64_t)R_out, (uint64_t)d, (uint64_t)d, T > 0 ? T : 1, 64);
   if (rc) return rc;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     rc = check_cuda(cudaFuncSetAttribute(self_attn_pairs_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, SaSmem::kTotal),
                     "cudaFuncSetAttribute(self_attn_pairs)");

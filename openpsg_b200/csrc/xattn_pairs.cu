@@ -46,6 +46,14 @@ constexpr int kXaHd = 64;
 constexpr int kXaPvN = 80;         // PV MMA N: 64 value dims + 1 ones row (row sum) + 15 zero rows
 constexpr int kXaSlots = 8;        // tile-local pair slots carried by the mask k-step
 
+// Per-unit clock stamps (scripts/xattn_trace.py) are compiled in only with -DOPSG_TRACE (make trace): a runtime-null trace
+// pointer still costs a parameter load and a branch inside the elected MMA-issue blocks and the softmax loop.
+#ifdef OPSG_TRACE
+#define XA_TRACE (p.trace)
+#else
+#define XA_TRACE (static_cast<long long*>(nullptr))
+#endif
+
 struct XattnParams {
   const uint8_t* tiles;      // [m_tiles][kXaTileBytes] A_aug | B_aug in core-matrix order (xattn_bias_tiles_kernel)
   const uint8_t* row_flags;  // [m_tiles * 128] 1 = the row's pair has an empty union mask (uniform attention)
@@ -321,7 +329,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return static_cast<long long>(t); };
-  if (p.trace && threadIdx.x == 0) p.trace[2048 + 4 * blockIdx.x + 0] = gtime();      // debug: per-CTA wall-clock stamps (ns)
+  if (XA_TRACE && threadIdx.x == 0) XA_TRACE[2048 + 4 * blockIdx.x + 0] = gtime();      // debug: per-CTA wall-clock stamps (ns)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -429,8 +437,8 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       const bool release_k = j + 1 < n_units && head_of(j + 1) != head;
       if (elect_one_sync()) {
-        if (p.trace && blockIdx.x == 0) p.trace[j * 8 + 0] = clock64();
-        if (p.trace && j == 0) p.trace[2048 + 4 * blockIdx.x + 2] = gtime();
+        if (XA_TRACE && blockIdx.x == 0) XA_TRACE[j * 8 + 0] = clock64();
+        if (XA_TRACE && j == 0) XA_TRACE[2048 + 4 * blockIdx.x + 2] = gtime();
         const uint64_t a_desc = umma_desc_k_sw128(smem_u32(sQ + b * XaSmem::kQ));
         const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK));
         const uint32_t aug = smem_u32(sAug + b * XaSmem::kAug);
@@ -465,7 +473,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&p_ready[b], parity);                  // P complete in TMEM, S fully consumed
       tc_fence_after();
       if (elect_one_sync()) {
-        if (p.trace && blockIdx.x == 0) p.trace[i * 8 + 1] = clock64();
+        if (XA_TRACE && blockIdx.x == 0) XA_TRACE[i * 8 + 1] = clock64();
 #pragma unroll
         for (int k = 0; k < kXaKeys / 16; ++k)
           umma_ts(od, pa + k * 8, v_desc + (k >> 2) * (XaSmem::kVBlk >> 4) + (k & 3) * 2, idesc_pv, k > 0 ? 1u : 0u);
@@ -529,8 +537,8 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t vis = __ldg(p.chunk_vis + mt * 4 + q);
       mbar_wait(&s_full[b], parity);
       tc_fence_after();
-      const bool tr = p.trace && tr_thread;
-      if (tr) p.trace[i * 8 + 2] = clock64();
+      const bool tr = XA_TRACE && tr_thread;
+      if (tr) XA_TRACE[i * 8 + 2] = clock64();
 
       const uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
       if (__popc(vis) <= 4) {
@@ -565,7 +573,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         if (mx == -INFINITY) mx = 0.f;                   // no visible key: uniform / out-of-range rows only
         const float mxs = mx * p.scale_log2e;
-        if (tr) p.trace[i * 8 + 3] = clock64();
+        if (tr) XA_TRACE[i * 8 + 3] = clock64();
         // every score this thread needs is in registers: the P columns may be written in any order
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -640,7 +648,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       if (mx == -INFINITY) mx = 0.f;                     // no visible key: uniform / out-of-range rows only
       const float mxs = mx * p.scale_log2e;
-      if (tr) p.trace[i * 8 + 3] = clock64();
+      if (tr) XA_TRACE[i * 8 + 3] = clock64();
 
       // ---- pass 2: p = exp2(s*scale - max*scale), packed bf16 P in place over consumed score columns ----
       auto exp_store = [&](const uint32_t (&v)[16], int c) {
@@ -684,7 +692,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[b]);
-      if (tr) p.trace[i * 8 + 4] = clock64();
+      if (tr) XA_TRACE[i * 8 + 4] = clock64();
     }
   } else {
     // ===================== epilogue warps (both buffers): O / rowsum -> bf16 -> swizzled staging -> TMA store =====================
@@ -700,7 +708,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t tO = tmem_base + b * 256 + 128 + (static_cast<uint32_t>(q * 32) << 16);
       mbar_wait(&o_full[b], parity);
       tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && elected) p.trace[i * 8 + 5] = clock64();
+      if (XA_TRACE && blockIdx.x == 0 && elected) XA_TRACE[i * 8 + 5] = clock64();
       uint32_t o0[32], o1[32];
       tmem_ld32(tO, o0);
       tmem_ld32(tO + 32, o1);
@@ -743,7 +751,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (elected) {
         tma_store_2d(sO + b * XaSmem::kOst, &tmO, head * kXaHd, mt * 128);
         tma_store_commit();
-        if (p.trace && blockIdx.x == 0) p.trace[i * 8 + 6] = clock64();
+        if (XA_TRACE && blockIdx.x == 0) XA_TRACE[i * 8 + 6] = clock64();
       }
     }
     if (elected) tma_store_wait_all<0>();
@@ -751,7 +759,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (p.trace && threadIdx.x == 0) p.trace[2048 + 4 * blockIdx.x + 3] = gtime();
+  if (XA_TRACE && threadIdx.x == 0) XA_TRACE[2048 + 4 * blockIdx.x + 3] = gtime();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -840,7 +848,8 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const XattnParams);
   static const KernelFn kernels[] = {xattn_pairs_kernel<0>, xattn_pairs_kernel<4>, xattn_pairs_kernel<3>, xattn_pairs_kernel<2>};
   const KernelFn kernel = kernels[(variant >= 0 && variant < 4) ? variant : 0];
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     for (KernelFn f : kernels) {
       rc = check_cuda(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, XaSmem::kTotal),

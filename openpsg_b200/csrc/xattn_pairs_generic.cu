@@ -367,7 +367,8 @@ extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int l
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmO, ctx_out, (uint64_t)rows, (uint64_t)d_model, (uint64_t)d_model, 128, 64);
   if (rc) return rc;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     rc = check_cuda(cudaFuncSetAttribute(xattn_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XaSmem::kTotal),
                     "cudaFuncSetAttribute(xattn)");

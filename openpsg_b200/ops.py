@@ -28,6 +28,11 @@ def _cuda(t: torch.Tensor, dtype=None, name="tensor"):
         raise ValueError(f"{name} must be a CUDA tensor (libopsg_b200 has no CPU path)")
     if dtype is not None and t.dtype != dtype:
         raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels, TMA descriptors and the stream all belong to the CURRENT device: a tensor elsewhere would be launched on
+        # the wrong GPU.  One process per GPU sets the device once (torch.cuda.set_device), as bench.py / sharding.py do.
+        raise ValueError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         "call torch.cuda.set_device (or use `with torch.cuda.device(...)`) before calling the head")
     return t
 
 

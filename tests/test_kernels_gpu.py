@@ -497,6 +497,22 @@ def test_topk_ties_go_to_lower_index(ops):
     assert top.cpu().tolist() == [2 + 3 * i for i in range(10)]
 
 
+def test_topk_nan_logits_keep_a_total_order(ops):
+    """NaN logits (only possible with non-finite weights) rank as -inf: every slot of the top-k list is written with a
+    distinct in-range index, finite candidates first."""
+    d, nq, B, k = 768, 33, 64, 64
+    x = torch.zeros((B * nq, d), dtype=torch.bfloat16)
+    x[::nq, 0] = torch.arange(B, dtype=torch.float32).to(torch.bfloat16)
+    x[5 * nq, 0] = float("nan")
+    x[9 * nq, 0] = float("nan")
+    w = torch.zeros(d)
+    w[0] = 1.0
+    _, _, _, top = ops.exist_filter_topk(x.cuda(), nq * d, B, d, w.cuda(), torch.zeros(1).cuda(), 0.5, k)
+    got = top.cpu().tolist()
+    assert sorted(got) == list(range(B))
+    assert got[-2:] == [5, 9] and got[0] == B - 1
+
+
 # ----------------------------------------------------------------------------------------------
 # K11: mask mean-pool + pair gather (fp32 sums, different order: tol 1e-4 relative)
 # ----------------------------------------------------------------------------------------------
