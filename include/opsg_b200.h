@@ -262,9 +262,6 @@ int opsg_copy_bytes(void* dst, const void* src, size_t nbytes, void* stream);
 int opsg_splitk_reduce_bf16(const float* partials, int splits, int rows, int cols, const float* bias, opsg_bf16* out,
                             int ld_out, void* stream);
 int opsg_transpose_i32(const int32_t* src, int rows, int cols, int32_t* dst, void* stream);
-/* Asynchronous L2 prefetch of nbytes at ptr (the next weight matrix of a decode step, issued while the small kernels between
- * two weight-streaming GEMMs run); returns immediately, no effect on results. */
-int opsg_prefetch_l2(const void* ptr, size_t nbytes, void* stream);
 
 /* ---- f1 / f2: the integer passes either side of the head in the reference's inference loop --------------------------
  * opsg_pan_relabel: detectors/openseed_relation_v2.py:112-128 on the device: pan_out[p] = new_ids[s] for the LAST listed

@@ -665,12 +665,11 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_q
 template <int HD>
 static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
   p.B = nseq * p.num_heads;
-  static const int use_smem = [] { const char* e = getenv("OPSG_DECODE_ATTN_SMEM"); return e ? atoi(e) : 1; }();
   const int ctx = p.q_pos0 + 1;
   const int per_warp = ((2 * ctx * (HD * 2 + 16) + HD * 2 + ((ctx + 31) & ~31) * 4) + 15) & ~15;
   // contexts <= 128 keys: 110 KB of shared memory per CTA (two CTAs per SM); up to 256 keys: one CTA per SM
   const int budget = ctx <= 128 ? 110 * 1024 : 220 * 1024;
-  if (use_smem && ctx <= 256 && per_warp <= budget) {
+  if (ctx <= 256 && per_warp <= budget) {
     int wpc = budget / per_warp;
     if (wpc > 4) wpc = 4;
     static bool configured_dev[64] = {};
@@ -746,14 +745,12 @@ extern "C" int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* share
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   // tcgen05 + TMA tiles (self_attn_pairs.cu: two pairs stacked per 128-row tile) for the head's shape; the warp-level
   // mma.sync kernels below remain the fallback for other shapes (head_dim != 64, more than 64 rows per pair)
-  static const int use_tc = [] { const char* e = getenv("OPSG_SELF_ATTN_TC"); return e ? atoi(e) : 1; }();
-  if (use_tc) {
+  {
     rc = launch_self_attn_pairs(qkv, shared_query_qkv, text_mask, B, n_query, T, num_heads, head_dim, text_queries, ctx_out,
                                 reinterpret_cast<cudaStream_t>(stream));
     if (rc != OPSG_E_UNSUPPORTED) return rc;
   }
-  static const int use_pipelined = [] { const char* e = getenv("OPSG_SELF_ATTN_PIPELINED"); return e ? atoi(e) : 1; }();
-  if (use_pipelined && head_dim == kQfHD && n_query + T <= kQfNK && (((uintptr_t)qkv | (uintptr_t)ctx_out) & 15) == 0) {
+  if (head_dim == kQfHD && n_query + T <= kQfNK && (((uintptr_t)qkv | (uintptr_t)ctx_out) & 15) == 0) {
     constexpr int smem = kQfStages * kQfStageBytes;
     static bool configured_dev[64] = {};
   bool& configured = configured_dev[device_slot()];
@@ -799,8 +796,7 @@ extern "C" int opsg_llm_attn(const opsg_bf16* q, int ld_q, const opsg_bf16* k_ca
     return launch_decode_attn<128>(p, nseq, st);
   }
   // prefill of prompts up to 64 tokens: tcgen05 + TMA tiles, two sequences stacked per 128-row tile (llm_prefill_attn.cu)
-  static const int use_tc = [] { const char* e = getenv("OPSG_LLM_PREFILL_TC"); return e ? atoi(e) : 1; }();
-  if (use_tc && q_len > 1) {
+  if (q_len > 1) {
     rc = launch_llm_prefill_attn_tc(q, ld_q, k_cache, v_cache, max_ctx, key_mask, nseq, q_len, q_pos0, num_heads, head_dim, scale, out,
                                     ld_out, reinterpret_cast<cudaStream_t>(stream));
     if (rc != OPSG_E_UNSUPPORTED) return rc;

@@ -537,10 +537,9 @@ extern "C" int opsg_gemm_bf16_streamk(const opsg_bf16* A, int lda, const opsg_bf
   OPSG_CHECK_ARG(out_mode == OPSG_OUT_BF16 || out_mode == OPSG_OUT_F32, "gemm_streamk: out_mode must be BF16 or F32");
   OPSG_CHECK_ARG(act >= OPSG_ACT_NONE && act <= OPSG_ACT_RELU, "gemm_streamk: bad activation");
   OPSG_CHECK_ARG(!residual || ldr >= N, "gemm_streamk: ldr too small");
-  // default: K-sliced kernel with the activation slice resident in shared memory (gemm_skinny.cu); OPSG_SKINNY=0 or a
-  // layout it does not take (N or a leading dimension not a multiple of 4) falls through to stream-K below
-  static const bool skinny = [] { const char* e = getenv("OPSG_SKINNY"); return e ? atoi(e) != 0 : true; }();
-  if (skinny) {
+  // K-sliced kernel with the activation slice resident in tensor memory (gemm_skinny.cu); a layout it does not take (N or a
+  // leading dimension not a multiple of 4) falls through to stream-K below
+  {
     rc = launch_gemm_skinny(A, lda, W, ldw, D, ldd, M, N, K, bias, residual, ldr, act, out_mode, workspace, workspace_bytes,
                             reinterpret_cast<cudaStream_t>(stream));
     if (rc != OPSG_E_UNSUPPORTED) return rc;
@@ -602,8 +601,7 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
   OPSG_CHECK_ARG(!residual || ldr >= N, "gemm: ldr too small");
 
   // large bf16-output problems: CTA-pair kernel (cta_group::2, 256 x 256 tiles; gemm_2cta.cu)
-  static const int use_2cta = [] { const char* e = getenv("OPSG_GEMM_2CTA"); return e ? atoi(e) : 1; }();
-  if (use_2cta && out_mode == OPSG_OUT_BF16 && k_splits == 1) {
+  if (out_mode == OPSG_OUT_BF16 && k_splits == 1) {
     rc = launch_gemm_2cta(A, lda, W, ldw, reinterpret_cast<opsg_bf16*>(D), ldd, M, N, K, bias, bias_along_m, residual, ldr, act,
                           nullptr, reinterpret_cast<cudaStream_t>(stream));
     if (rc != OPSG_E_UNSUPPORTED) return rc;

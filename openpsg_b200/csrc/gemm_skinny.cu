@@ -348,8 +348,7 @@ int launch_gemm_skinny(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw,
   p.ws = reinterpret_cast<float*>(workspace);
   if (workspace_bytes < static_cast<size_t>(p.S) * M * N * sizeof(float))
     return set_error(OPSG_E_INVALID, "gemm_skinny: workspace too small (%zu bytes)", workspace_bytes);
-  static const int env_a = [] { const char* e = getenv("OPSG_SKINNY_ASTAGES"); return e ? atoi(e) : 3; }();
-  p.a_stages = env_a < 1 ? 1 : (env_a > kMaxAStages ? kMaxAStages : env_a);
+  p.a_stages = 3;        // deeper rings (6, 10) and more producer warps measured no faster: profiles/r2_decode_timeline.md
   if (p.a_stages > p.KS) p.a_stages = p.KS;
   const int a_bytes = p.a_stages * p.MR * 128;
   int stages = (kSmemLimit - 1024 - a_bytes - kBarrierBytes) / kStageBytes;

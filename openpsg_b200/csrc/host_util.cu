@@ -19,8 +19,8 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("OPSG_PDL"); return e ? atoi(e) != 0 : true; }();
-  return on;
+  const char* e = getenv("OPSG_PDL");      // read per launch (host side, ~100 ns): tests flip it inside one process
+  return e ? atoi(e) != 0 : true;
 }
 
 int check_cuda(cudaError_t e, const char* what) {

@@ -207,17 +207,6 @@ __global__ void __launch_bounds__(256) splitk_reduce_bf16_kernel(const float* __
 }
 
 
-// Fire-and-forget L2 prefetch of a weight matrix (cp.async.bulk.prefetch.L2): the decode step is a chain of small kernels
-// (LayerNorm, attention, reductions) between weight-streaming GEMMs; issuing the NEXT GEMM's weights towards L2 while those
-// run keeps HBM busy across the whole step instead of only inside the GEMM kernels.  Thread = one 16 KB chunk.
-__global__ void __launch_bounds__(128) prefetch_l2_kernel(const uint8_t* __restrict__ ptr, size_t bytes) {
-  pdl_wait_then_trigger();
-  constexpr size_t kChunk = 16384;
-  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * kChunk;
-  if (i >= bytes) return;
-  const size_t n = (bytes - i < kChunk ? bytes - i : kChunk) & ~static_cast<size_t>(15);
-  if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + i), "r"(static_cast<uint32_t>(n)) : "memory");
-}
 
 }  // namespace opsg
 
@@ -319,14 +308,3 @@ extern "C" int opsg_splitk_reduce_bf16(const float* partials, int splits, int ro
   return OPSG_OK;
 }
 
-extern "C" int opsg_prefetch_l2(const void* ptr, size_t nbytes, void* stream) {
-  int rc = opsg_device_check();
-  if (rc) return rc;
-  if (nbytes == 0) return OPSG_OK;
-  OPSG_CHECK_ARG(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "prefetch_l2: pointer must be 16-byte aligned");
-  const size_t chunks = (nbytes + 16383) / 16384;
-  launch_kernel(prefetch_l2_kernel, ceil_div_ll(static_cast<long long>(chunks), 128), 128, 0, ST(stream),
-                static_cast<const uint8_t*>(ptr), nbytes);
-  OPSG_CHECK_LAUNCH("prefetch_l2_kernel");
-  return OPSG_OK;
-}

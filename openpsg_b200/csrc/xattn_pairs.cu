@@ -1,36 +1,42 @@
-// K5 (v3) — pair-query x image-feature masked cross-attention on tcgen05 tensor cores (the north-star kernel).
+// K5 — pair-query x image-feature masked cross-attention on tcgen05 tensor cores (the north-star kernel; reference
+// HF modeling_instructblip.py:499-536 as called at relation_transformer_head_v4.py:179-185).
 //
-// All pairs' query rows are stacked along M (row = pair * n_query + r); K and V are projected once per image
-// and shared by every pair, so per head the whole thing is  softmax(Q[M x 64] . K^T[64 x L] + mask(pair)) . V.
-// Work unit = (128-row tile, head); a persistent CTA walks a contiguous, head-major range of units with the
-// head's K [256 x 64] and [V^T | 1 | 0] [80 x 256] resident in shared memory.
+// All pairs' query rows are stacked along M (row = pair * n_query + r); K and V are projected once per image and shared by
+// every pair, so per head the whole thing is  softmax(Q[M x 64] . K^T[64 x L] + mask(pair)) . V.
+// Work unit = (128-row tile, head).  The grid is num_heads x ctas_per_head persistent CTAs; a CTA walks m-tiles of ONE head
+// with that head's K [256 x 64] and [V^T | 1 | 0] [80 x 256] resident in shared memory.
 //
-// 640 threads:
-//   warp 0 (elected lane) TMA producer : K / V^T on a head change, Q tile + mask-bias tiles per unit (2 stages)
-//   warp 1 (elected lane) MMA issuer   : S_b  = Q.K^T + A_aug.B_aug^T   (128 x 256 x (64+16), SS, 5 MMAs)
-//                                     O_b  = P_b.[V|1]               (128 x 80 x 256, TS, 16 MMAs)
-//   warp 2             TMEM allocator (512 columns = two 256-column buffers)
-//   warp 3             per-head mean of V (output of uniform-attention rows)
-//   The pair mask enters the scores as an additive bias computed BY THE MMA: a fifth k-step multiplies
-//   A_aug[r, t] = 1 for the tile-local pair slot t of row r with B_aug[key, t] = 0 if the key belongs to
-//   bits[i_t] | bits[j_t] else -16384 (bf16-exact; keys >= L get -16384 in every slot).  Both operand tiles are
-//   built once per image by xattn_bias_tiles_kernel (they depend on the masks and the pair order only, not on the
-//   head or the layer), stored in global memory in the MMA's no-swizzle core-matrix order and fetched with one
-//   bulk copy per unit next to the Q tile.
-//   warps 4-19         softmax: two warpgroups per TMEM buffer split the 256 keys (thread = row x 128 keys); units
-//                      alternate between the buffers, so the MMAs of unit i+1 run under the softmax of unit i.
-//                      Row max (halves exchanged through smem), p = exp2(s*scale - max) with no per-element mask
-//                      work, packed bf16 P written IN PLACE over the consumed scores (half 0 ascending into columns
-//                      [0,64), half 1 descending into [192,256)) and used as the TMEM A operand of the PV MMA; the
-//                      row sum comes out of that MMA through the ones row of [V^T | 1]; O (columns [64,144)) is
-//                      scaled, packed and leaves through a swizzled staging tile and one TMA store per unit.
-// Mask semantics follow HF's `(1 - m) * finfo.min` additive bias: masked keys get weight exactly 0
-// (exp2(-16384 * scale) underflows to +0) and a pair whose union mask is empty attends uniformly to all L keys
-// (those rows are written as the fp32 mean of V).
+// 512 threads (<= 128 registers):
+//   warp 0      TMA producer: K / V^T once, then per unit the Q tile + the unit's mask-bias operand tiles (2 stages)
+//   warp 1      QK^T issuer:  S_b = Q.K^T + A_aug.B_aug^T  (128 x 256 x (64+16), SS, 5 MMAs) -- its own in-order queue, so it
+//               is never blocked behind a PV that waits for P
+//   warp 2      TMEM allocator (512 columns = two 256-column buffers), then PV issuer: O_b = P_b.[V | 1] (128 x 80 x 256, TS, 16 MMAs;
+//               the ones row makes the MMA deliver the row sum as column 64)
+//   warp 3      per-head mean of V (the output of uniform-attention rows)
+//   warps 4-7   softmax of TMEM buffer 0, warps 8-11 of buffer 1: thread = one score row x all 256 keys, so the row max
+//               needs no cross-thread exchange.  p = exp2(s*scale - max) with no per-element mask work; packed bf16 P
+//               overwrites the consumed scores in place (columns [0, 128)) and is the TMEM A operand of the PV MMA
+//   warps 12-15 epilogue of both buffers: O / row sum out of TMEM columns [128, 209) (which frees the buffer for the QK^T of unit i+2
+//               as soon as it has been read), 1 / row sum, uniform rows, bf16, swizzled staging tile, one TMA store per unit
+// so a softmax warp goes straight from the exponentials of unit i to the scores of unit i+2.
 //
-// Shape history: profiles/r1_ncu_xattn_a.md (v1: 9.7 % tensor-pipe activity, serial softmax),
-// profiles/r1_ncu_xattn_h.md (v2: 20 %, ALU pipe 45 % busy with FSEL/FMNMX/R2P mask work, MUFU 38 %),
-// profiles/r1_ncu_xattn_i.md (v3 with an in-kernel mask-builder warp: 17.6 %, softmax warps starved by the builder).
+// Mask inside the MMA: the pair mask enters the scores as an additive bias computed BY THE TENSOR CORE -- a fifth k-step
+// multiplies A_aug[r, t] = 1 for the tile-local pair slot t of row r with B_aug[key, t] = 0 if the key belongs to
+// bits[i_t] | bits[j_t] else -16384 (bf16-exact; keys >= L get -16384 in every slot).  Both operand tiles are built once per
+// image by xattn_bias_tiles_kernel (they depend on the masks and the pair order only, not on the head or the layer), stored
+// in the MMA's no-swizzle core-matrix order and fetched with one bulk copy per unit next to the Q tile.
+// Sparse softmax: the image tokens reach this kernel sorted by owning object (token_order_kernel), so a pair's visible keys
+// are two short runs; 16-key chunks in which no row of a warp sees a key are skipped (no tcgen05.ld, no max, no
+// exponentials; their P columns are cleared).  The MMAs stay dense.
+// Mask semantics follow HF's `(1 - m) * finfo.min` additive bias: masked keys get weight exactly 0 (exp2(-16384 * scale)
+// underflows to +0) and a pair whose union mask is empty attends uniformly to all L keys (those rows are written as the fp32
+// mean of V).
+//
+// History: profiles/r1_ncu_xattn_a.md (v1: 9.7 % tensor-pipe activity, serial softmax), r1_ncu_xattn_h.md (v2: 20 %, ALU pipe
+// busy with per-element mask work), r1_ncu_xattn_final3.md (v3: mask as an MMA k-step, 34 %), r2_ncu_xattn.md (v4: split
+// issuer warps, thread-per-row softmax, key order + chunk skipping: 43 % of elapsed at cfg2, 54 % at the cfg5 shape).
+// Tried in round 2 and dropped: row sums from the softmax threads + PV at N = 64 (55.3 us instead of 56.4 under ncu, but 6 %
+// slower on dense masks and 40 % tensor-pipe activity instead of 43: the unit time is not set by the PV MMAs).
 #include "common.cuh"
 #include "host_util.h"
 
@@ -63,7 +69,6 @@ struct XattnParams {
   int m_tiles;
   int total_units;
   int ctas_per_head; // > 0: grid = num_heads x ctas_per_head, every CTA walks m-tiles of a single head
-  int desc_swap;     // debug: swap LBO / SBO of the no-swizzle descriptors
   long long* trace;  // debug: per-unit clock64 stamps of CTA 0 ([unit][8]); NULL in production
   float scale_log2e;
 };
@@ -422,7 +427,7 @@ xattn_pairs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     // ===================== QK^T issuer =====================
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kXaKeys);
-    const uint32_t lbo = p.desc_swap ? 256u : 128u, sbo = p.desc_swap ? 128u : 256u;
+    const uint32_t lbo = 128u, sbo = 256u;      // no-swizzle core matrices: 128 B between the k-cores, 256 B between 8-row groups
     int k_waits = 0, cur_head = -1;
     for (int j = 0; j < n_units; ++j) {
       const int head = head_of(j);
@@ -818,7 +823,6 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
                                 const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                                 int n_query, int L, int num_heads, int head_dim, const void* bias_tiles,
                                 opsg_bf16* ctx_out, void* stream) {
-  static const int desc_swap = [] { const char* e = getenv("OPSG_XATTN_DESC_SWAP"); return e ? atoi(e) : 0; }();
   // without precomputed mask-bias tiles (or for shapes they do not cover) the self-contained v2 kernel runs
   if (!bias_tiles || n_query <= 0 || 127 / n_query + 2 > kXaSlots)
     return opsg_xattn_pairs_v2(q, k, ld_k, vt, ld_vt, bits, words, pair_index, num_objects, B, n_query, L, num_heads,
@@ -842,12 +846,10 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmO, ctx_out, (uint64_t)rows, (uint64_t)d_model, (uint64_t)d_model, 128, 64);
   if (rc) return rc;
-  // OPSG_XATTN_VARIANT (tuning switch): 0 = every exponential on the MUFU; 1 / 2 / 3 = every 4th / 3rd / 2nd exponential as
-  // an FMA-pipe polynomial
-  static const int variant = [] { const char* e = getenv("OPSG_XATTN_VARIANT"); return e ? atoi(e) : 0; }();
+  // every exponential on the MUFU (POLY_MOD = 0); moving every 4th / 3rd / 2nd one to an FMA-pipe polynomial measured slower
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const XattnParams);
-  static const KernelFn kernels[] = {xattn_pairs_kernel<0>, xattn_pairs_kernel<4>, xattn_pairs_kernel<3>, xattn_pairs_kernel<2>};
-  const KernelFn kernel = kernels[(variant >= 0 && variant < 4) ? variant : 0];
+  static const KernelFn kernels[] = {xattn_pairs_kernel<0>};
+  const KernelFn kernel = kernels[0];
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[device_slot()];
   if (!configured) {
@@ -865,7 +867,6 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
   p.chunk_vis = reinterpret_cast<const uint16_t*>(p.tiles + static_cast<size_t>(p.m_tiles) * (kXaTileBytes + 128));
   p.L = L; p.num_heads = num_heads; p.d_model = d_model;
   p.rows = rows; p.total_units = p.m_tiles * num_heads;
-  p.desc_swap = desc_swap;
   p.trace = g_xattn_trace;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   const int sms = opsg_num_sms();

@@ -346,7 +346,6 @@ using namespace opsg::xa2;
 extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt,
                                 const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                                 int n_query, int L, int num_heads, int head_dim, opsg_bf16* ctx_out, void* stream) {
-  static const int flags = [] { const char* e = getenv("OPSG_XATTN_FLAGS"); return e ? atoi(e) : 0; }();
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(q && k && vt && bits && ctx_out, "xattn_pairs: null pointer");
@@ -379,7 +378,7 @@ extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int l
   p.bits = bits; p.pair_index = pair_index;
   p.words = words; p.num_objects = num_objects; p.n_query = n_query; p.L = L; p.num_heads = num_heads; p.d_model = d_model;
   p.rows = rows; p.m_tiles = (rows + 127) / 128; p.total_units = p.m_tiles * num_heads;
-  p.flags = flags;
+  p.flags = 0;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   const int grid = p.total_units < opsg_num_sms() ? p.total_units : opsg_num_sms();
   // each CTA's contiguous unit range must span at most two heads (two resident K/V sets)

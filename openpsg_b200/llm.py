@@ -23,7 +23,6 @@ bf16 operands with fp32 accumulation, fp32 softmax / normalisation statistics an
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -200,8 +199,6 @@ class LLMDecodeEngine:
             raise ValueError(f"language_projection out_features {w_proj.shape[0]} != LLM hidden size {weights.d}")
         self.use_cuda_graphs = use_cuda_graphs
         # decode steps (rows <= 128) take the K-sliced small-M GEMM (csrc/gemm_skinny.cu); OPSG_LLM_SMALL_M=0 keeps the tiled one
-        self.small_m = os.environ.get("OPSG_LLM_SMALL_M", "1") == "1"
-        self.prefetch = int(os.environ.get("OPSG_LLM_PREFETCH", "0"))         # L2 prefetch of the next GEMM's weights (decode): 0 off
         self._graphs = GraphCache(max_entries=2)        # (hidden shape, k, T, max_new_tokens) -> captured generate()
 
     def _norm(self, x, nw, out=None):
@@ -211,25 +208,16 @@ class LLMDecodeEngine:
         return ops.rmsnorm(x, nw[0], w.norm_eps, out=out)
 
     # one decoder layer over `rows` = nseq * q_len token rows; h is updated in place.  rope_pos: int32 [rows] (Llama only)
-    def _layer(self, lw, h, k_cache, v_cache, key_mask, nseq, q_len, pos0, rope_pos, next_w=None):
+    def _layer(self, lw, h, k_cache, v_cache, key_mask, nseq, q_len, pos0, rope_pos):
         w = self.w
         d = w.d
         # Decode steps (rows <= 128) stream the weights through the K-sliced kernel with the activations resident in TMEM:
         # 17 / 11 / 21 / 20 us for qkv / out / fc1 / fc2 at k = 100 inside a graph against 22 / 13 / 24 / 40 us for the tiled
-        # kernel (scripts/kbench.py streamk, profiles/r1_llm_decode.md).
-        decode = self.small_m and h.shape[0] <= 128
-        gemm = ops.gemm_small_m if decode else ops.gemm
-        # decode, optional (self.prefetch, off by default): start pulling the NEXT GEMM's weights into L2 while the small kernels
-        # between two GEMMs run (mode 2: issued after a GEMM, before attention / LayerNorm) or already while the current GEMM
-        # streams (mode 1).  Measured on cfg3: mode 1 164 ms per image against 121 ms without (the prefetch competes with the
-        # GEMM's own stream and the extra launches sit on the critical path).
-        mode = self.prefetch if decode else 0
-        pf1 = ops.prefetch_l2 if mode == 1 else (lambda t: None)
-        pf2 = ops.prefetch_l2 if mode == 2 else (lambda t: None)
+        # kernel (scripts/kbench.py streamk).  Tried and dropped (profiles/r2_decode_timeline.md): L2 prefetch of the next
+        # GEMM's weights from a side kernel (164 ms per cfg3 image against 121), constant-weight early streaming inside the GEMM.
+        gemm = ops.gemm_small_m if h.shape[0] <= 128 else ops.gemm
         x = self._norm(h, lw["norm1"])
-        pf1(lw["w_o"])
         qkv = gemm(x, lw["w_qkv"], lw["b_qkv"])                                        # [rows, 3d]
-        pf2(lw["w_o"])
         if w.rope is not None:
             ops.rope(qkv, 2, w.heads, w.head_dim, rope_pos, w.rope[0], w.rope[1])      # q and k rotated in place
         ctx = torch.empty((nseq * q_len, d), dtype=torch.bfloat16, device=h.device)
@@ -239,20 +227,13 @@ class LLMDecodeEngine:
         else:
             ops.kv_append(qkv, nseq, q_len, pos0, d, k_cache, v_cache)
             ops.llm_attn(qkv, k_cache, v_cache, key_mask, nseq, q_len, pos0, w.heads, w.head_dim, w.head_dim ** -0.5, ctx)
-        pf1(lw["w_up"])
         gemm(ctx, lw["w_o"], lw["b_o"], residual=h, out=h)                             # h += out_proj(ctx)
-        pf2(lw["w_up"])
         x = self._norm(h, lw["norm2"])
-        pf1(lw["w_down"])
         if w.family == "opt":
             f = gemm(x, lw["w_up"], lw["b_up"], act=ops.ACT_RELU)                      # relu(fc1(x))
         else:
             f = ops.swiglu(gemm(x, lw["w_up"], lw["b_up"]), w.ffn)                     # silu(gate(x)) * up(x)
-        if next_w is not None:
-            pf1(next_w)
         gemm(f, lw["w_down"], lw["b_down"], residual=h, out=h)                         # h += fc2 / down_proj
-        if next_w is not None:
-            pf2(next_w)
         return h
 
     def _logits(self, h_last):
@@ -360,8 +341,7 @@ class LLMDecodeEngine:
             else:
                 ops.embed_gather(w.embed, feed, hd)
             for li, lw in enumerate(w.layers):
-                nxt = w.layers[li + 1]["w_qkv"] if li + 1 < w.n_layers else None
-                self._layer(lw, hd, k_cache[li], v_cache[li], lay.key_mask, k, 1, Tp + s - 1, step_pos, next_w=nxt)
+                self._layer(lw, hd, k_cache[li], v_cache[li], lay.key_mask, k, 1, Tp + s - 1, step_pos)
             logits = self._logits(hd)
             ops.argmax_rows(logits, out=tokens[s])
             if scores is not None:

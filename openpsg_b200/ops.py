@@ -539,11 +539,3 @@ def gemm_splitk(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
         _lib.check(_lib.load().opsg_splitk_reduce_bf16(_ptr(part), k_splits, M, N, _ptr(bias), _ptr(out), out.stride(0), _stream()))
     _count()
     return out
-
-
-def prefetch_l2(t: torch.Tensor) -> None:
-    """Start pulling a (weight) tensor into L2; returns immediately (decode: the next GEMM's weights, see llm.py)."""
-    nbytes = t.numel() * t.element_size()
-    with _timed("prefetch_l2", 0.0, 0.0):
-        _lib.check(_lib.load().opsg_prefetch_l2(_ptr(t), nbytes, _stream()))
-    _count()

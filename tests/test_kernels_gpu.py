@@ -71,6 +71,21 @@ def test_gemm(ops, case):
     assert err <= tol, f"max err {err} > {tol}"
 
 
+def test_gemm_gelu_tanh_option(ops, monkeypatch):
+    """OPSG_GELU_TANH=1 (tanh.approx GELU in the CTA-pair GEMM epilogue) stays within the GEMM tolerance of the exact GELU."""
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1000, 3072, 768
+    a, w, bias = _rand_bf16((M, K), g), _rand_bf16((N, K), g, 1.0 / math.sqrt(K)), torch.randn(N, generator=g)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().t() + bias)
+    exact = ops.gemm(a.cuda(), w.cuda(), bias.cuda(), act=1)
+    monkeypatch.setenv("OPSG_GELU_TANH", "1")
+    fast = ops.gemm(a.cuda(), w.cuda(), bias.cuda(), act=1)
+    torch.cuda.synchronize()
+    tol = 1.2e-2 * ref.abs().max().item()
+    assert (exact.float().cpu() - ref).abs().max().item() <= tol and (fast.float().cpu() - ref).abs().max().item() <= tol
+    assert (fast.float() - exact.float()).abs().max().item() <= 2.5e-4 * 6 + 2 ** -7 * 4      # formula error + one bf16 ulp near |x| ~ 4
+
+
 def test_gemm_bias_along_m_strided_out(ops):
     g = torch.Generator().manual_seed(5)
     for L in (16, 20, 252, 256):

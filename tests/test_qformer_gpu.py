@@ -203,6 +203,47 @@ def test_deterministic_patch_embed_is_bit_reproducible(monkeypatch):
     assert (ref.last_output.logits - z_a).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("switch", ["fold_ln", "unshared_query_rows", "atomic_patch_embed"])
+def test_engine_switches_agree_with_default(switch, monkeypatch):
+    """The three engine switches that remain (LayerNorm folded into the consuming GEMMs, OPSG_FOLD_LN=1; query rows of layer 0
+    projected per pair as the reference does, OPSG_SHARE_QUERY_ROWS=0; PatchEmbed split-K through fp32 atomics,
+    OPSG_PATCH_DETERMINISTIC=0) compute the same function as the default path: output rows, logits and the selected pairs agree
+    within the run-to-run budget of bf16 rounding (see test_graph_replay_and_forward_batch_equal_eager)."""
+    inputs = synth.inputs_to(_inputs("cfg1"), "cuda:0")
+    ref = build_product_head(device="cuda:0")
+    ref.use_cuda_graphs = False
+    ref(inputs)
+    h0, z0 = ref.last_output.hidden.float().cpu(), ref.last_output.logits.cpu()
+    monkeypatch.setenv({"fold_ln": "OPSG_FOLD_LN", "unshared_query_rows": "OPSG_SHARE_QUERY_ROWS",
+                        "atomic_patch_embed": "OPSG_PATCH_DETERMINISTIC"}[switch], "1" if switch == "fold_ln" else "0")
+    alt = build_product_head(device="cuda:0")
+    alt.use_cuda_graphs = False
+    alt(inputs)
+    h1, z1 = alt.last_output.hidden.float().cpu(), alt.last_output.logits.cpu()
+    d = (h1 - h0).abs()
+    assert d.max() < 8e-2 and d.mean() < 6e-3, (switch, float(d.max()), float(d.mean()))
+    assert (z1 - z0).abs().max() < 3e-2
+    ok, diff = margin_set_equal(alt.last_output.topk.cpu().tolist(), z0, 20, 3e-2)
+    assert ok, diff
+
+
+def test_programmatic_dependent_launch_does_not_change_results(monkeypatch):
+    """OPSG_PDL=0 (plain stream order) and the default (every kernel launched with programmatic stream serialization, its
+    prologue overlapping the previous kernel, griddepcontrol.wait before the first dependent access) are bit-identical on the
+    whole relation-query path: a kernel that touched its inputs before the wait would show up here."""
+    inputs = synth.inputs_to(_inputs("cfg1"), "cuda:0")
+    a = build_product_head(device="cuda:0")
+    a.use_cuda_graphs = False
+    for _ in range(3):
+        a(inputs)
+    ha, za, ta = a.last_output.hidden.clone(), a.last_output.logits.clone(), a.last_output.topk.clone()
+    monkeypatch.setenv("OPSG_PDL", "0")
+    b = build_product_head(device="cuda:0")
+    b.use_cuda_graphs = False
+    b(inputs)
+    assert torch.equal(b.last_output.hidden, ha) and torch.equal(b.last_output.logits, za) and torch.equal(b.last_output.topk, ta)
+
+
 def test_relation_queries_80_objects_subset_vs_oracle(head):
     """cfg5's image shape (80 objects, 6400 pair queries): the full run must agree with the fp32 oracle on a sample of
     pairs (the oracle evaluates only the sampled pairs through its pair_index argument)."""
