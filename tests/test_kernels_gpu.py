@@ -126,6 +126,11 @@ STREAMK_CASES = [
     (1, 1024, 320, True, False, 1, torch.bfloat16),
     (128, 72, 136, True, True, 0, torch.float32),
     (37, 300, 64, False, False, 0, torch.bfloat16),
+    # Llama-2-7B decode shapes (K = 4096 / 11008: 6 and 15 slices, the last one short)
+    (100, 12288, 4096, False, False, 0, torch.bfloat16),
+    (100, 4096, 11008, False, True, 0, torch.bfloat16),
+    (128, 1000, 4096, True, True, 0, torch.float32),
+    (3, 2560, 10240, True, True, 0, torch.bfloat16),
 ]
 
 
