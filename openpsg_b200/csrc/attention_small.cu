@@ -544,118 +544,239 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const SmallAttnParams 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K10b, second version — decode attention with the sequence's K / V head slices staged in shared memory.
-// The register version above keeps 16 loads per lane in flight and needs four dependent round trips per (sequence,
-// head) (two key batches for K, two for V) at 122 registers per thread: 1.35 waves of CTAs, 27 us per launch for ~60 MB.
-// Here a warp issues EVERY 16-byte piece of its item's K and V slices as cp.async at once (one round trip, ~26 KB per
-// warp, no registers held), computes the scores lane-per-key from shared memory while V is still landing, then the
-// context lane-per-dimension-pair.  Rows are padded by 16 bytes so that lane-per-key 16-byte reads are conflict-free.
+// K10b -- decode attention (one query token per sequence) over the static KV cache: one warp per (sequence, head) item.
+// History (all measured on B200, 32 heads x 80): register-held scalar version 27 us per launch at 100 sequences; K / V head
+// slices staged in shared memory by cp.async with scalar FMAs 15 us (166 us at 800 sequences: ~2700 warp instructions per item,
+// issue-bound); the same staging with warp-level mma.sync arithmetic 145 us; the kernel below (TMA staging, persistent warps)
+// 142 us = 3.7 TB/s of K / V.
+//   S  = Q K^T : A = the query row broadcast to all 16 rows, B = K rows straight from ldmatrix (keys = n, dims = k); the
+//                accumulator layout of S (keys along columns) is the A-fragment layout the PV product needs, so P never
+//                leaves registers (FlashAttention-2's trick);
+//   O  = P V   : B = V through ldmatrix.trans.  Every row of S / O is the same row; row-group g of the warp writes the
+//                output n-tiles g and g + 8.
+// Rows past the context (up to the next multiple of 16) are zero-filled so that 0 x garbage cannot produce NaN.
 // ------------------------------------------------------------------------------------------------
-template <int HD, int R>
-__global__ void __launch_bounds__(128) decode_attn_smem_kernel(const SmallAttnParams p, int warps_per_cta) {
-  pdl_wait_then_trigger();
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  constexpr int C = HD / 8;                                 // 16-byte chunks per key row
-  constexpr int RS = HD * 2 + 16;                           // padded row stride (bytes)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staging by TMA: one elected lane issues ONE tensor copy for the item's K slice and one for its V slice (box = [cached rows x head_dim] of the cache viewed as
+// [nseq * max_ctx, d_model]; the tensor maps are built per launch because the box height is the context length).  ncu of the
+// cp.async version at 800 sequences (profiles/r2_ncu_decode_attn.md): ~2000 warp instructions per item, 40 % of them the copy
+// loop, 0.32 IPC with two warps per scheduler -> the LOAD ISSUE itself took ~3 us per item and DRAM sat at 46 %.
+// head_dim 80: dense 160-byte rows (ldmatrix phases are 2-way bank conflicted, harmless); head_dim 64 / 128: 128-byte
+// swizzled boxes of 64 dims (a dense 128 / 256-byte pitch would put all 8 rows of an ldmatrix phase on the same banks).
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+struct KvSmem {
+  static constexpr bool kSwizzled = (HD % 64) == 0;
+  // heads per warp item.  Two adjacent 160-byte head rows (head_dim 80) as one 320-byte piece were measured SLOWER (203 against
+  // 142 us at 800 sequences): half as many warps fit, and a warp's serial mma.sync chain per head (~2.8 us), not the row-request
+  // rate, is what bounds the kernel (profiles/r2_ncu_decode_attn.md)
+  static constexpr int kHeads = 1;
+  static constexpr int kC = HD / 8;                         // 16-byte chunks per head row
+  static constexpr int kRowBytes = kHeads * HD * 2;
+  // byte offset of chunk c (of the item's kHeads * kC) of row r inside a K (or V) buffer of `rows16` rows
+  __device__ static __forceinline__ uint32_t at(int r, int c, int rows16) {
+    if constexpr (kSwizzled) return (c >> 3) * rows16 * 128 + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+    else return r * kRowBytes + c * 16;
+  }
+};
+
+// Persistent warps: the shared memory of an SM bounds the bytes in flight (8 warps x 26 KB), so a buffer should spend its time
+// LOADING, not waiting for its warp's arithmetic: a warp walks items warp, warp + W, ... and re-issues the K copy of its NEXT
+// item as soon as the scores of the current one are in registers, the V copy as soon as the context is -- single buffers, the
+// next item's loads overlap the rest of the current item's work.
+template <int HD, int NT>                                   // NT = key tiles of 16 the registers are sized for
+__global__ void __launch_bounds__(128) decode_attn_tma_kernel(const __grid_constant__ CUtensorMap tm_k,
+                                                              const __grid_constant__ CUtensorMap tm_v,
+                                                              const SmallAttnParams p, int warps_per_cta, int per_warp) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t bars[4][2];
+  using L = KvSmem<HD>;
+  constexpr int C = HD / 8, HW = L::kHeads, RB = L::kRowBytes;   // an item = HW adjacent heads of one sequence
+  const int groups = p.num_heads / HW;                      // (host-checked: divisible)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * warps_per_cta + warp;      // (sequence, head)
-  if (warp >= warps_per_cta || item >= p.B) return;         // p.B = nseq * num_heads (set by the launcher)
-  const int seq = item / p.num_heads, head = item % p.num_heads;
+  const int first = blockIdx.x * warps_per_cta + warp;     // items are (sequence, head group)
+  const int stride = gridDim.x * warps_per_cta;
+  const bool live = warp < warps_per_cta && first < p.B;    // p.B = nseq * num_heads (set by the launcher)
+  if (live && lane == 0) {
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  __syncwarp();
+  pdl_wait_then_trigger();
+  if (!live) return;
   const int ctx = p.q_pos0 + 1;                             // keys 0 .. q_pos0 (causal, the new token included)
-  const int ctx_pad = (ctx + 31) & ~31;
-  const int per_warp = 2 * ctx * RS + HD * 2 + ctx_pad * 4;
-  uint8_t* sK = smem_dyn + static_cast<size_t>(warp) * ((per_warp + 15) & ~15);
-  uint8_t* sV = sK + ctx * RS;
-  uint8_t* sQ = sV + ctx * RS;
-  float* sP = reinterpret_cast<float*>(sQ + HD * 2);
-  const __nv_bfloat16* kbase = p.k_cache + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
-  const __nv_bfloat16* vbase = p.v_cache + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
-  const uint8_t* kmask = p.key_mask + static_cast<size_t>(seq) * p.max_ctx;
-
-  const __nv_bfloat16* new_kv = p.q + static_cast<size_t>(seq) * p.ld_q + head * HD;      // + d_model: k, + 2 d_model: v
-  for (int idx = lane; idx < ctx * C; idx += 32) {
-    const int key = idx / C, c = idx - key * C;
-    const __nv_bfloat16* src = (p.append_kv && key == ctx - 1) ? new_kv + p.d_model + c * 8
-                                                               : kbase + static_cast<size_t>(key) * p.d_model + c * 8;
-    cp_async16(sK + key * RS + c * 16, src, true);
-  }
-  if (lane < C) cp_async16(sQ + lane * 16, p.q + static_cast<size_t>(seq) * p.ld_q + head * HD + lane * 8, true);
-  cp_async_commit();
-  for (int idx = lane; idx < ctx * C; idx += 32) {
-    const int key = idx / C, c = idx - key * C;
-    const __nv_bfloat16* src = (p.append_kv && key == ctx - 1) ? new_kv + 2 * p.d_model + c * 8
-                                                               : vbase + static_cast<size_t>(key) * p.d_model + c * 8;
-    cp_async16(sV + key * RS + c * 16, src, true);
-  }
-  cp_async_commit();
-
-  // ---- scores: lane-per-key ----------------------------------------------------------------------------
-  cp_async_wait<1>();
-  __syncwarp();
-  float sc[R];                                              // ctx <= 32 * R (host-checked)
-  float mx = -INFINITY;
+  const int ctx16 = (ctx + 15) & ~15;
+  const int cached = p.append_kv ? ctx - 1 : ctx;           // rows that come from the caches
+  const uint32_t bytes = static_cast<uint32_t>(cached) * RB;
+  uint8_t* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u) + static_cast<size_t>(warp) * per_warp;
+  uint8_t* sK = base;
+  uint8_t* sV = sK + ctx16 * RB;
+  uint8_t* sQ = sV + ctx16 * RB;
+  uint64_t* bar_k = &bars[warp][0];
+  uint64_t* bar_v = &bars[warp][1];
+  auto issue = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int item) {      // lane 0 only
+    const int seq = item / groups, head = (item - seq * groups) * HW;
+    mbar_expect_tx(bar, bytes);
+    if constexpr (L::kSwizzled) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int key = r * 32 + lane;
-    float d = -INFINITY;
-    if (key < ctx && __ldg(kmask + key) != 0) {
-      d = 0.f;
-      const uint8_t* kr = sK + key * RS;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const uint4 k4 = *reinterpret_cast<const uint4*>(kr + c * 16);
-        const uint4 q4 = *reinterpret_cast<const uint4*>(sQ + c * 16);
-        d = fmaf(bf16_lo(k4.x), bf16_lo(q4.x), d); d = fmaf(bf16_hi(k4.x), bf16_hi(q4.x), d);
-        d = fmaf(bf16_lo(k4.y), bf16_lo(q4.y), d); d = fmaf(bf16_hi(k4.y), bf16_hi(q4.y), d);
-        d = fmaf(bf16_lo(k4.z), bf16_lo(q4.z), d); d = fmaf(bf16_hi(k4.z), bf16_hi(q4.z), d);
-        d = fmaf(bf16_lo(k4.w), bf16_lo(q4.w), d); d = fmaf(bf16_hi(k4.w), bf16_hi(q4.w), d);
+      for (int r = 0; r < HD / 64; ++r) tma_load_2d(dst + r * ctx16 * 128, tm, bar, head * HD + r * 64, seq * p.max_ctx);
+    } else {
+      tma_load_2d(dst, tm, bar, head * HD, seq * p.max_ctx);
+    }
+  };
+  if (lane == 0 && cached > 0) {
+    issue(sK, &tm_k, bar_k, first);
+    issue(sV, &tm_v, bar_v, first);
+  }
+  // V rows past the context stay zero for the whole launch (P is zero there, 0 x garbage must not be NaN)
+  for (int i = lane; i < (ctx16 - ctx) * C * HW; i += 32) {
+    const int r = ctx + i / (C * HW), c = i % (C * HW);
+    *reinterpret_cast<uint4*>(sV + L::at(r, c, ctx16)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  const int quad = lane & 3, grp = lane >> 2;
+  // ldmatrix rows of this lane.  K: matrix lane/8 = (keys +0 dims +0) (keys +0 dims +8) (keys +8 dims +0) (keys +8 dims +8);
+  // V (.trans): (keys +0 dims +0) (keys +8 dims +0) (keys +0 dims +8) (keys +8 dims +8)
+  const int k_r = ((lane >> 4) & 1) * 8 + (lane & 7), k_c = (lane >> 3) & 1;
+  const int v_r = ((lane >> 3) & 1) * 8 + (lane & 7), v_c = (lane >> 4) & 1;
+  uint32_t phase = 0;
+
+  for (int item = first; item < p.B; item += stride, phase ^= 1u) {
+    const int seq = item / groups, head = (item - seq * groups) * HW;
+    const int next = item + stride;
+    __nv_bfloat16* kbase = const_cast<__nv_bfloat16*>(p.k_cache) + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
+    __nv_bfloat16* vbase = const_cast<__nv_bfloat16*>(p.v_cache) + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
+    const uint8_t* kmask = p.key_mask + static_cast<size_t>(seq) * p.max_ctx;
+    const __nv_bfloat16* new_kv = p.q + static_cast<size_t>(seq) * p.ld_q + head * HD;    // + d_model: k, + 2 d_model: v
+    // the query row and the new token's k / v: into shared memory (rows the tensor copies do not touch) AND into the caches
+    // (replaces a kv_append launch)
+    if (lane < C * HW) {
+      *reinterpret_cast<uint4*>(sQ + lane * 16) = __ldg(reinterpret_cast<const uint4*>(new_kv + lane * 8));
+      if (p.append_kv) {
+        const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(new_kv + p.d_model + lane * 8));
+        const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(new_kv + 2 * p.d_model + lane * 8));
+        *reinterpret_cast<uint4*>(sK + L::at(ctx - 1, lane, ctx16)) = k4;
+        *reinterpret_cast<uint4*>(sV + L::at(ctx - 1, lane, ctx16)) = v4;
+        const size_t off = static_cast<size_t>(ctx - 1) * p.d_model + lane * 8;
+        *reinterpret_cast<uint4*>(kbase + off) = k4;
+        *reinterpret_cast<uint4*>(vbase + off) = v4;
       }
     }
-    sc[r] = d;
-    mx = fmaxf(mx, d);
-  }
-  mx = warp_max(mx);
-  if (mx == -INFINITY) mx = 0.f;
-  float sum = 0.f;
+    // key validity of this lane's score columns (keys t*16 + quad*2 + {0, 1} and + 8): read while the copies are in flight
+    uint32_t valid[NT];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const float e = ex2f((sc[r] - mx) * p.scale_log2e);     // exp2(-inf) = 0 for masked / out-of-range keys
-    // P is rounded to bf16 like the tensor-core path (and HF's bf16 softmax output) before multiplying V
-    if (r * 32 + lane < ctx_pad) sP[r * 32 + lane] = __bfloat162float(__float2bfloat16(e));
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.f / sum;
-
-  // ---- context: lane-per-dimension-pair ------------------------------------------------------------------
-  cp_async_wait<0>();
-  __syncwarp();
-  if (p.append_kv && lane < C) {            // the new token's head slice joins the caches (replaces a kv_append launch)
-    const size_t off = static_cast<size_t>(ctx - 1) * p.d_model + lane * 8;
-    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(kbase) + off) = *reinterpret_cast<const uint4*>(sK + (ctx - 1) * RS + lane * 16);
-    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(vbase) + off) = *reinterpret_cast<const uint4*>(sV + (ctx - 1) * RS + lane * 16);
-  }
+    for (int t = 0; t < NT; ++t) {
+      valid[t] = 0;
+      if (t * 16 < ctx) {
 #pragma unroll
-  for (int pass = 0; pass < (HD / 2 + 31) / 32; ++pass) {
-    const int dp = pass * 32 + lane;
-    if (dp < HD / 2) {
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-      int key = 0;
-      for (; key + 1 < ctx; key += 2) {
-        const uint32_t va = *reinterpret_cast<const uint32_t*>(sV + key * RS + dp * 4);
-        const uint32_t vb = *reinterpret_cast<const uint32_t*>(sV + (key + 1) * RS + dp * 4);
-        const float pa = sP[key], pb = sP[key + 1];
-        o0 = fmaf(pa, bf16_lo(va), o0); o1 = fmaf(pa, bf16_hi(va), o1);
-        o2 = fmaf(pb, bf16_lo(vb), o2); o3 = fmaf(pb, bf16_hi(vb), o3);
+        for (int j = 0; j < 4; ++j) {
+          const int key = t * 16 + (j >> 1) * 8 + quad * 2 + (j & 1);
+          if (key < ctx && __ldg(kmask + key) != 0) valid[t] |= 1u << j;
+        }
       }
-      if (key < ctx) {
-        const uint32_t va = *reinterpret_cast<const uint32_t*>(sV + key * RS + dp * 4);
-        const float pa = sP[key];
-        o0 = fmaf(pa, bf16_lo(va), o0); o1 = fmaf(pa, bf16_hi(va), o1);
-      }
-      *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(seq) * p.ld_out + head * HD + dp * 2) =
-          pack_bf16x2((o0 + o2) * inv, (o1 + o3) * inv);
     }
+
+    // ---- S = q K^T --------------------------------------------------------------------------------------
+    __syncwarp();
+    if (cached > 0) mbar_wait(bar_k, phase);
+    uint32_t pa[HW][NT][2];                                 // P as bf16 A fragments (rounded like the tensor-core prefill path)
+    float inv[HW];
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh) {
+    uint32_t qa[HD / 16][2];                                // A fragments of the broadcast query row: a0 = a1, a2 = a3
+#pragma unroll
+    for (int kb = 0; kb < HD / 16; ++kb) {
+      qa[kb][0] = *reinterpret_cast<const uint32_t*>(sQ + (hh * HD + kb * 16 + quad * 2) * 2);
+      qa[kb][1] = *reinterpret_cast<const uint32_t*>(sQ + (hh * HD + kb * 16 + 8 + quad * 2) * 2);
+    }
+    float sc[NT][4];                                        // [t][0..1]: keys t*16 + quad*2 + {0,1}; [t][2..3]: the same + 8
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (t * 16 < ctx) {
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kb = 0; kb < HD / 16; ++kb) {
+          uint32_t b[4];
+          ldmatrix_x4(b, sK + L::at(t * 16 + k_r, hh * C + kb * 2 + k_c, ctx16));
+          const uint32_t a[4] = {qa[kb][0], qa[kb][0], qa[kb][1], qa[kb][1]};
+          mma_bf16_16816(c0, a, b[0], b[1]);
+          mma_bf16_16816(c1, a, b[2], b[3]);
+        }
+        sc[t][0] = (valid[t] & 1u) ? c0[0] : -INFINITY; sc[t][1] = (valid[t] & 2u) ? c0[1] : -INFINITY;
+        sc[t][2] = (valid[t] & 4u) ? c1[0] : -INFINITY; sc[t][3] = (valid[t] & 8u) ? c1[1] : -INFINITY;
+        mx = fmaxf(fmaxf(mx, fmaxf(sc[t][0], sc[t][1])), fmaxf(sc[t][2], sc[t][3]));
+      }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    if (mx == -INFINITY) mx = 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (t * 16 < ctx) {
+        float e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          e[j] = ex2f((sc[t][j] - mx) * p.scale_log2e);     // exp2(-inf) = 0 for masked / out-of-range keys
+          sum += e[j];
+        }
+        pa[hh][t][0] = pack_bf16x2(e[0], e[1]);
+        pa[hh][t][1] = pack_bf16x2(e[2], e[3]);
+      }
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    inv[hh] = 1.f / sum;
+    }
+    // the scores are in registers (the shuffles above consumed them): K of the warp's next item may land in the buffer
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && cached > 0 && next < p.B) issue(sK, &tm_k, bar_k, next);
+    // ---- O = P V ----------------------------------------------------------------------------------------
+    if (cached > 0) mbar_wait(bar_v, phase);
+    uint32_t packed[HW][(HD / 8 + 7) / 8];
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh) {
+    float o[HD / 8][4];
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) { o[n][0] = 0.f; o[n][1] = 0.f; o[n][2] = 0.f; o[n][3] = 0.f; }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (t * 16 < ctx) {
+        const uint32_t a[4] = {pa[hh][t][0], pa[hh][t][0], pa[hh][t][1], pa[hh][t][1]};
+#pragma unroll
+        for (int n = 0; n < HD / 8; n += 2) {
+          uint32_t b[4];
+          ldmatrix_x4_trans(b, sV + L::at(t * 16 + v_r, hh * C + n + v_c, ctx16));
+          mma_bf16_16816(o[n], a, b[0], b[1]);
+          mma_bf16_16816(o[n + 1], a, b[2], b[3]);
+        }
+      }
+    }
+    // every row group holds the same output row: group g writes n-tiles g and g + 8 (4 bytes per lane, 16 contiguous per quad)
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n)
+      if ((n & 7) == grp) packed[hh][n >> 3] = pack_bf16x2(o[n][0] * inv[hh], o[n][1] * inv[hh]);
+    }
+    // the context is in registers: V of the next item may land
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && cached > 0 && next < p.B) issue(sV, &tm_v, bar_v, next);
+    __nv_bfloat16* orow = p.out + static_cast<size_t>(seq) * p.ld_out + head * HD;
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n)
+        if ((n & 7) == grp) *reinterpret_cast<uint32_t*>(orow + hh * HD + n * 8 + quad * 2) = packed[hh][n >> 3];
   }
 }
 
@@ -666,28 +787,55 @@ template <int HD>
 static int launch_decode_attn(SmallAttnParams p, int nseq, cudaStream_t st) {
   p.B = nseq * p.num_heads;
   const int ctx = p.q_pos0 + 1;
-  const int per_warp = ((2 * ctx * (HD * 2 + 16) + HD * 2 + ((ctx + 31) & ~31) * 4) + 15) & ~15;
-  // contexts <= 128 keys: 110 KB of shared memory per CTA (two CTAs per SM); up to 256 keys: one CTA per SM
+  const int ctx16 = (ctx + 15) & ~15;
+  // contexts <= 128 keys: up to 110 KB of shared memory per CTA; up to 256 keys: one CTA per SM
   const int budget = ctx <= 128 ? 110 * 1024 : 220 * 1024;
-  if (ctx <= 256 && per_warp <= budget) {
-    int wpc = budget / per_warp;
-    if (wpc > 4) wpc = 4;
+  constexpr int HW = KvSmem<HD>::kHeads, RB = KvSmem<HD>::kRowBytes;
+  const int pw = (2 * ctx16 * RB + RB + 1023) & ~1023;                   // per warp: K | V | q, 1024-byte aligned (swizzle atoms)
+  // the TMA kernel needs 16-byte aligned caches / qkv rows; anything else takes the register kernel below
+  if (ctx <= 256 && pw + 1024 <= budget && p.num_heads % HW == 0 && (p.d_model % 8) == 0 && (p.ld_q % 8) == 0 &&
+      ((reinterpret_cast<uintptr_t>(p.k_cache) | reinterpret_cast<uintptr_t>(p.v_cache) | reinterpret_cast<uintptr_t>(p.q)) & 15) == 0) {
+    // warps per CTA: whatever packs most warps into an SM's 227 KB (1 KB per CTA is reserved by the driver); ties -> larger CTAs
+    int wpc = 1, best = 0;
+    for (int w = 1; w <= 4 && w * pw + 1024 <= budget; ++w) {
+      const int resident = (227 * 1024) / (w * pw + 2048) * w;
+      if (resident >= best) { best = resident; wpc = w; }
+    }
+    const int cached = p.append_kv ? ctx - 1 : ctx;
+    CUtensorMap tmk, tmv;
+    const uint32_t box_rows = static_cast<uint32_t>(cached > 0 ? cached : 1);
+    const uint64_t rows = static_cast<uint64_t>(nseq) * p.max_ctx;
+    int rc;
+    if (KvSmem<HD>::kSwizzled) {
+      rc = make_tmap_bf16_2d(&tmk, p.k_cache, rows, p.d_model, p.d_model, box_rows, 64);
+      if (!rc) rc = make_tmap_bf16_2d(&tmv, p.v_cache, rows, p.d_model, p.d_model, box_rows, 64);
+    } else {
+      rc = make_tmap_bf16_2d_plain(&tmk, p.k_cache, rows, p.d_model, p.d_model, box_rows, HW * HD);
+      if (!rc) rc = make_tmap_bf16_2d_plain(&tmv, p.v_cache, rows, p.d_model, p.d_model, box_rows, HW * HD);
+    }
+    if (rc) return rc;
     static bool configured_dev[64] = {};
-  bool& configured = configured_dev[device_slot()];
+    bool& configured = configured_dev[device_slot()];
     if (!configured) {
-      int rc = check_cuda(cudaFuncSetAttribute(decode_attn_smem_kernel<HD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
-                          "cudaFuncSetAttribute(decode_attn_smem)");
+      rc = check_cuda(cudaFuncSetAttribute(decode_attn_tma_kernel<HD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
+                      "cudaFuncSetAttribute(decode_attn_tma)");
       if (rc) return rc;
-      rc = check_cuda(cudaFuncSetAttribute(decode_attn_smem_kernel<HD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
-                      "cudaFuncSetAttribute(decode_attn_smem)");
+      rc = check_cuda(cudaFuncSetAttribute(decode_attn_tma_kernel<HD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+                      "cudaFuncSetAttribute(decode_attn_tma)");
       if (rc) return rc;
       configured = true;
     }
+    const size_t smem = static_cast<size_t>(wpc) * pw + 1024;
+    // persistent: as many CTAs as fit on the machine at once, every warp walks items warp, warp + W, ...
+    p.B /= HW;                                                           // items = (sequence, group of HW heads)
+    int grid = (p.B + wpc - 1) / wpc;
+    const int resident_ctas = opsg_num_sms() * (best / wpc);
+    if (grid > resident_ctas) grid = resident_ctas;
     if (ctx <= 128)
-      launch_kernel(decode_attn_smem_kernel<HD, 4>, (p.B + wpc - 1) / wpc, 128, static_cast<size_t>(wpc) * per_warp, st, p, wpc);
+      launch_kernel(decode_attn_tma_kernel<HD, 8>, grid, wpc * 32, smem, st, tmk, tmv, p, wpc, pw);
     else
-      launch_kernel(decode_attn_smem_kernel<HD, 8>, (p.B + wpc - 1) / wpc, 128, static_cast<size_t>(wpc) * per_warp, st, p, wpc);
-    OPSG_CHECK_LAUNCH("decode_attn_smem_kernel");
+      launch_kernel(decode_attn_tma_kernel<HD, 16>, grid, wpc * 32, smem, st, tmk, tmv, p, wpc, pw);
+    OPSG_CHECK_LAUNCH("decode_attn_tma_kernel");
     return OPSG_OK;
   }
   if (p.append_kv) {                         // register version reads the cache only: append with the copy kernel first

@@ -472,7 +472,7 @@ extern "C" int opsg_qformer_embed_ln(const float* query, int n_query, const int3
   return OPSG_OK;
 }
 
-// Few rows (LLM decode: 100 rows of 2560): one CTA per row instead of one warp per row -- 256 threads issue the row's
+// Few rows (LLM decode: 100 rows of 2560 per image, 800 with eight images stacked): one CTA per row instead of one warp per row -- 256 threads issue the row's
 // loads (x, gamma, beta) at once, so the kernel is one memory round trip deep instead of ten chunks per lane.
 template <int CH>                                         // CH x 256 x 8 columns max
 __global__ void __launch_bounds__(256) layernorm_row_cta_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
@@ -548,7 +548,7 @@ extern "C" int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   if (cols > 4096)
     launch_kernel(layernorm_row_cta_kernel<4>, rows, 256, 0, ST(stream), xp, gamma, beta, eps, yp, cols);
-  else if ((rows <= 512 && cols >= 1024) || cols > 256 * kMaxChunks)
+  else if ((rows <= 4096 && cols >= 1024) || cols > 256 * kMaxChunks)
     launch_kernel(layernorm_row_cta_kernel<2>, rows, 256, 0, ST(stream), xp, gamma, beta, eps, yp, cols);
   else if (cols <= 1024) launch_kernel(layernorm_bf16_kernel<4>, grid, 256, 0, ST(stream), xp, gamma, beta, eps, yp, rows, cols);
   else launch_kernel(layernorm_bf16_kernel<kMaxChunks>, grid, 256, 0, ST(stream), xp, gamma, beta, eps, yp, rows, cols);

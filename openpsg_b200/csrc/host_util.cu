@@ -44,8 +44,21 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int make_tmap_bf16_2d_sw(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle);
+
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_bf16_2d_sw(map, base, rows, cols, ld, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int make_tmap_bf16_2d_plain(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_bf16_2d_sw(map, base, rows, cols, ld, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+static int make_tmap_bf16_2d_sw(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(OPSG_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
@@ -55,7 +68,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(OPSG_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,

@@ -15,6 +15,9 @@ int check_cuda(cudaError_t e, const char* what);
 // 128-byte swizzle (box_cols * 2 bytes must be <= 128).  Out-of-bounds elements read as zero.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
+// the same without shared-memory swizzling: the box lands as dense rows of box_cols elements
+int make_tmap_bf16_2d_plain(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols);
 
 // LayerNorm-folding arguments of the CTA-pair GEMM (opsg_gemm_bf16_ln); any group may be null
 struct GemmLnFold {

@@ -118,6 +118,8 @@ class RelationTransformerHeadV4(BaseModule):
                  llm_tokenizer=None,
                  language_model=None,
                  use_cuda_graphs=True,
+                 llm_batch_images=8,
+                 last_layer_selected_rows_only=False,
                  **kwargs):
         super().__init__()
         from transformers import InstructBlipQFormerConfig, InstructBlipQFormerModel
@@ -142,6 +144,11 @@ class RelationTransformerHeadV4(BaseModule):
         self.topk_pairs = topk_pairs
         self.max_new_tokens = max_new_tokens
         self.use_cuda_graphs = bool(use_cuda_graphs) and os.environ.get("OPSG_CUDA_GRAPHS", "1") != "0"
+        # forward_batch: the selected pairs of up to this many consecutive images decode as ONE LLM batch (1 = per image)
+        self.llm_batch_images = max(1, int(llm_batch_images))
+        self.llm_batch_max_sequences = 1024
+        # last Q-Former layer only on the rows the head consumes (row 0 of every pair + the selected pairs' 33 rows)
+        self.last_layer_selected_rows_only = bool(last_layer_selected_rows_only)
         if qformer_feature_size != 768 or object_feature_size != 256:
             raise NotImplementedError("libopsg_b200 kernels are built for the reference sizes (768 / 256)")
 
@@ -276,7 +283,19 @@ class RelationTransformerHeadV4(BaseModule):
                 ev.record(copy_stream)
             return prep, ev
 
+        # LLM leg: the relation queries of up to `group` consecutive images run back to back (no host synchronisation in
+        # between), then their selected pairs decode as one batch -- every decode step streams the LLM weights once for all
+        # of them instead of once per image, and the per-image read-back of the selected pairs becomes one per group
+        with_llm = 'binary' in self.rel_cls_type and self._llm_engine is not None and is_generation
+        group = min(self.llm_batch_images, max(1, self.llm_batch_max_sequences // max(1, self.topk_pairs))) if with_llm else 1
         results = []
+        pending = []
+
+        def flush():
+            for res in self._decode_group(pending, on_result):
+                results.append(res)
+            pending.clear()
+
         nxt = prefetch(inputs_list[0]) if inputs_list else None
         for i in range(len(inputs_list)):
             prep, ev = nxt
@@ -286,9 +305,16 @@ class RelationTransformerHeadV4(BaseModule):
             cur.wait_event(ev)
             for t in prep["device"].values():
                 t.record_stream(cur)
+            if group > 1:
+                pending.append(self._run_queries(prep, keep=True))
+                if len(pending) == group:
+                    flush()
+                continue
             results.append(self._run(prep, is_generation))
             if on_result is not None:
                 on_result(self)
+        if pending:
+            flush()
         return results
 
     def _forward_test(self, image_feature, meta_info, object_info, is_generation):
@@ -337,38 +363,120 @@ class RelationTransformerHeadV4(BaseModule):
         return prep
 
     # -- stage 3: kernels ---------------------------------------------------------------------------------------------
-    def _run(self, prep, is_generation):
+    def _run_queries(self, prep, keep=False):
+        """a2-a8 of one image.  Returns None for an image without objects, else a record with the engine output and (``keep``)
+        private copies of what the LLM leg needs after the next image has overwritten the graph's static buffers."""
         from . import ops as _ops
         if prep["n"] == 0:
             self.last_output = None
-            return {'rel_pred': [], 'rel_score': []}
+            return dict(prep=prep, out=None)
         d = prep["device"]
-        n, cats = prep["n"], prep["cats"]
-        dev = self._packed.device
+        kw = dict(topk=self.topk_pairs, threshold=self.pair_selector_threshold,
+                  selected_rows_only=self.last_layer_selected_rows_only)
         if self.use_cuda_graphs and _ops._profile is None:
-            out = self._graphs.run(d["feat"], d["pan"], prep["img_hw"], prep["pad_hw"], d["obj_ids"], d["q_ids"], d["q_mask"],
-                                   topk=self.topk_pairs, threshold=self.pair_selector_threshold)
+            out = self._graphs.run(d["feat"], d["pan"], prep["img_hw"], prep["pad_hw"], d["obj_ids"], d["q_ids"], d["q_mask"], **kw)
         else:
             out = self._engine.forward(d["feat"], d["pan"], prep["img_hw"], prep["pad_hw"], d["obj_ids"], d["q_ids"],
-                                       d["q_mask"], topk=self.topk_pairs, threshold=self.pair_selector_threshold)
+                                       d["q_mask"], **kw)
         self.last_output = out
+        rec = dict(prep=prep, out=out)
+        if keep:
+            rec["rows"] = self._selected_rows(out, copy=True)
+            rec["topk"] = out.topk.clone()
+        return rec
+
+    @staticmethod
+    def _selected_rows(out, copy=False):
+        """bf16 [k, 33*768]: the 33 Q-Former rows of the selected pairs, in ``out.topk`` order (v4:215)."""
+        from . import ops as _ops
+        k = out.topk.numel()
+        width = N_QUERY * out.hidden.shape[1]
+        if out.hidden_pairs is not None:                     # last_layer_selected_rows_only: already gathered
+            rows = out.hidden.view(k, width)
+            return rows.clone() if copy else rows
+        return _ops.gather_rows(out.hidden, width, out.topk)
+
+    def _parse_relations(self, selected, n, texts):
+        """v4:315-326: generated text -> unique [subject, object, relation] triples."""
+        rel_pred: List[List[int]] = []
+        rel_score: List[float] = []
+        for si, text in zip(selected, texts):
+            parts = text.split('<s>')
+            body = (parts[1] if len(parts) > 1 else parts[0]).split('</s>')[0].strip()
+            for name in body.split('  '):
+                if name in relation_categories:
+                    trip = [si // n, si % n, relation_categories.index(name)]
+                    if trip not in rel_pred:
+                        rel_pred.append(trip)
+                        rel_score.append(1)
+        return rel_pred, rel_score
+
+    def _run(self, prep, is_generation):
+        rec = self._run_queries(prep)
+        out = rec["out"]
+        if out is None:
+            return {'rel_pred': [], 'rel_score': []}
+        n, cats = prep["n"], prep["cats"]
+        dev = self._packed.device
         rel_pred: List[List[int]] = []
         rel_score: List[float] = []
         if 'binary' in self.rel_cls_type and self._llm_engine is not None and is_generation:
             selected = out.topk.tolist()                                                # v4:236-237 (D2H sync)
             sel = np.asarray(selected, dtype=np.int64)
             l_ids, l_mask = self._llm_cache.lookup(cats[sel // n], cats[sel % n])       # v4:260-266
-            gen = self._llm_engine.generate(out.hidden, out.topk, l_ids.to(dev), l_mask.to(dev),
-                                            max_new_tokens=self.max_new_tokens)
+            if out.hidden_pairs is not None:
+                gen = self._llm_engine.generate_rows(self._selected_rows(out), l_ids.to(dev), l_mask.to(dev),
+                                                     max_new_tokens=self.max_new_tokens)
+            else:
+                gen = self._llm_engine.generate(out.hidden, out.topk, l_ids.to(dev), l_mask.to(dev),
+                                                max_new_tokens=self.max_new_tokens)
             self.last_generation = gen
             texts = self.llm_tokenizer.batch_decode(gen.tokens.cpu())                   # v4:313
-            for si, text in zip(selected, texts):                                       # v4:315-326
-                parts = text.split('<s>')
-                body = (parts[1] if len(parts) > 1 else parts[0]).split('</s>')[0].strip()
-                for name in body.split('  '):
-                    if name in relation_categories:
-                        trip = [si // n, si % n, relation_categories.index(name)]
-                        if trip not in rel_pred:
-                            rel_pred.append(trip)
-                            rel_score.append(1)
+            rel_pred, rel_score = self._parse_relations(selected, n, texts)
         return {'rel_pred': rel_pred, 'rel_score': rel_score}
+
+    def _decode_group(self, records, on_result=None):
+        """LLM leg (a9-a10) of a group of images as ONE batch of sum(k_i) sequences.  Prompts of different images are
+        left-padded to the group's longest one (padding is masked and positions are derived from the mask, v4:260-266 pads the
+        same way inside one image).  ``on_result(head)`` sees ``last_generation`` restricted to the image's own sequences;
+        ``last_output`` of all but the group's last image has been overwritten by then."""
+        from .llm import GenerationOutput
+        dev = self._packed.device
+        live = [r for r in records if r["out"] is not None]
+        results = {}
+        if live:
+            counts = [r["topk"].numel() for r in live]
+            topk_host = torch.cat([r["topk"] for r in live]).tolist()                   # one D2H sync per group (v4:236-237)
+            ids, masks, selected_lists = [], [], []
+            at = 0
+            for r, k in zip(live, counts):
+                selected = topk_host[at:at + k]
+                at += k
+                n, cats = r["prep"]["n"], r["prep"]["cats"]
+                sel = np.asarray(selected, dtype=np.int64)
+                l_ids, l_mask = self._llm_cache.lookup(cats[sel // n], cats[sel % n])
+                ids.append(l_ids); masks.append(l_mask); selected_lists.append(selected)
+            T = max(t.shape[1] for t in ids)
+            pad_id = self._llm_cache.pad_id
+            ids = torch.cat([torch.nn.functional.pad(t, (T - t.shape[1], 0), value=pad_id) for t in ids])
+            masks = torch.cat([torch.nn.functional.pad(t, (T - t.shape[1], 0), value=0) for t in masks])
+            rows = torch.cat([r["rows"] for r in live]) if len(live) > 1 else live[0]["rows"]
+            gen = self._llm_engine.generate_rows(rows, ids.to(dev), masks.to(dev), max_new_tokens=self.max_new_tokens)
+            tokens = gen.tokens.cpu()
+            texts = self.llm_tokenizer.batch_decode(tokens)                             # v4:313
+            at = 0
+            for r, k, selected in zip(live, counts, selected_lists):
+                rel_pred, rel_score = self._parse_relations(selected, r["prep"]["n"], texts[at:at + k])
+                results[id(r)] = ({'rel_pred': rel_pred, 'rel_score': rel_score}, gen.tokens[at:at + k])
+                at += k
+        out = []
+        for r in records:
+            if r["out"] is None:
+                out.append({'rel_pred': [], 'rel_score': []})
+                continue
+            res, toks = results[id(r)]
+            self.last_generation = GenerationOutput(tokens=toks)
+            if on_result is not None:
+                on_result(self)
+            out.append(res)
+        return out

@@ -199,7 +199,7 @@ class LLMDecodeEngine:
             raise ValueError(f"language_projection out_features {w_proj.shape[0]} != LLM hidden size {weights.d}")
         self.use_cuda_graphs = use_cuda_graphs
         # decode steps (rows <= 128) take the K-sliced small-M GEMM (csrc/gemm_skinny.cu); OPSG_LLM_SMALL_M=0 keeps the tiled one
-        self._graphs = GraphCache(max_entries=2)        # (hidden shape, k, T, max_new_tokens) -> captured generate()
+        self._graphs = GraphCache(max_entries=3)        # (kind, input shapes, max_new_tokens) -> captured prefill + decode loop
 
     def _norm(self, x, nw, out=None):
         w = self.w
@@ -246,42 +246,55 @@ class LLMDecodeEngine:
     def generate(self, hidden: torch.Tensor, selected: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,
                  max_new_tokens: int = 16, return_scores: bool = False,
                  forced_tokens: Optional[torch.Tensor] = None) -> GenerationOutput:
-        """Greedy relation decode for the selected pairs.  A call signature seen for the second time is captured and
-        from then on replayed as ONE CUDA graph holding the whole prefill + decode loop (~300 launches per step; the
-        loop has no host synchronisation); first sightings, ``return_scores`` / ``forced_tokens`` (parity tests) and
-        profiling runs execute eagerly."""
+        """Greedy relation decode for the selected pairs of ONE image.  A call signature seen for the second time is
+        captured and from then on replayed as ONE CUDA graph holding the whole prefill + decode loop (~300 launches per
+        step; the loop has no host synchronisation); first sightings, ``return_scores`` / ``forced_tokens`` (parity tests)
+        and profiling runs execute eagerly."""
         if not self.use_cuda_graphs or return_scores or forced_tokens is not None or ops._profile is not None:
             return self._generate(hidden, selected, llm_ids, llm_mask, max_new_tokens, return_scores, forced_tokens)
-        dev = hidden.device
-        key = (tuple(hidden.shape), tuple(llm_ids.shape), int(max_new_tokens))
+        key = ("pairs", tuple(hidden.shape), tuple(llm_ids.shape), int(max_new_tokens))
+        return self._graphed(key, dict(hidden=hidden, selected=selected, ids=llm_ids, mask=llm_mask),
+                             lambda e: self._generate(e["hidden"], e["selected"], e["ids"], e["mask"], max_new_tokens, False, None))
+
+    @torch.no_grad()
+    def generate_rows(self, rows: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor, max_new_tokens: int = 16,
+                      return_scores: bool = False, forced_tokens: Optional[torch.Tensor] = None) -> GenerationOutput:
+        """Greedy relation decode for K sequences whose Q-Former rows were already gathered: ``rows`` bf16 [K, 33*768] (row
+        0 of every pair is dropped by the prompt assembly, v4:215).  The K sequences need not come from one image:
+        ``head.forward_batch`` stacks the selected pairs of several images, so that every decode step streams the LLM
+        weights once for all of them (sequences are independent: v4:293-312 runs them one by one)."""
+        if not self.use_cuda_graphs or return_scores or forced_tokens is not None or ops._profile is not None:
+            return self._generate_rows(rows, llm_ids, llm_mask, max_new_tokens, return_scores, forced_tokens)
+        key = ("rows", tuple(rows.shape), tuple(llm_ids.shape), int(max_new_tokens))
+        return self._graphed(key, dict(rows=rows, ids=llm_ids, mask=llm_mask),
+                             lambda e: self._generate_rows(e["rows"], e["ids"], e["mask"], max_new_tokens, False, None))
+
+    def _graphed(self, key, inputs: dict, run):
+        """Replay (or, at the second sighting of ``key``, capture) ``run(static inputs)`` as one CUDA graph."""
+        dev = next(iter(inputs.values())).device
         e = self._graphs.lookup(key)
         if e is None:
             if not self._graphs.should_capture(key):
-                return self._generate(hidden, selected, llm_ids, llm_mask, max_new_tokens, False, None)
-            e = dict(hidden=torch.empty_like(hidden),
-                     selected=torch.empty(tuple(selected.shape), dtype=torch.int32, device=dev),
-                     ids=torch.empty(tuple(llm_ids.shape), dtype=torch.int32, device=dev),
-                     mask=torch.empty(tuple(llm_mask.shape), dtype=torch.int32, device=dev))
-            for name, src in (("hidden", hidden), ("selected", selected), ("ids", llm_ids), ("mask", llm_mask)):
+                return run(inputs)
+            e = {n: torch.empty(tuple(t.shape), dtype=t.dtype if t.dtype == torch.bfloat16 else torch.int32, device=dev)
+                 for n, t in inputs.items()}
+            for name, src in inputs.items():
                 e[name].copy_(src)
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                self._generate(e["hidden"], e["selected"], e["ids"], e["mask"], max_new_tokens, False, None)
+                run(e)
             cur.wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             l0 = ops.launch_count
             with torch.cuda.graph(graph):
-                out = self._generate(e["hidden"], e["selected"], e["ids"], e["mask"], max_new_tokens, False, None)
+                out = run(e)
             e.update(graph=graph, out=out, launches=ops.launch_count - l0)
             self._graphs.insert(key, e)
-        if e["hidden"].data_ptr() != hidden.data_ptr():
-            ops.copy_into(e["hidden"], hidden)
-        ops.copy_into(e["selected"], selected)
-        ops.copy_into(e["ids"], llm_ids)
-        ops.copy_into(e["mask"], llm_mask)
+        for name, src in inputs.items():
+            ops.copy_into(e[name], src)
         e["graph"].replay()
         ops._count(e["launches"])
         return e["out"]
@@ -289,24 +302,31 @@ class LLMDecodeEngine:
     def _generate(self, hidden: torch.Tensor, selected: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,
                   max_new_tokens: int = 16, return_scores: bool = False,
                   forced_tokens: Optional[torch.Tensor] = None) -> GenerationOutput:
-        # hidden bf16 [B*33, 768] (Q-Former output rows, pair-major); selected int32 [k] pair indices;
-        # llm_ids / llm_mask int32 [k, T] left-padded prompt tokens (v4:260-266).  forced_tokens int32 [k, T_new]
-        # teacher-forces the fed-back ids (parity tests: keeps our run on the oracle's trajectory).
+        # hidden bf16 [B*33, 768] (Q-Former output rows, pair-major); selected int32 [k] pair indices
+        selected = selected.to(device=hidden.device, dtype=torch.int32).contiguous()
+        rows = ops.gather_rows(hidden, N_QUERY * hidden.shape[1], selected)            # [k, 33*768]
+        return self._generate_rows(rows, llm_ids, llm_mask, max_new_tokens, return_scores, forced_tokens)
+
+    def _generate_rows(self, feat: torch.Tensor, llm_ids: torch.Tensor, llm_mask: torch.Tensor,
+                       max_new_tokens: int = 16, return_scores: bool = False,
+                       forced_tokens: Optional[torch.Tensor] = None) -> GenerationOutput:
+        # feat bf16 [k, 33*768]: the selected pairs' Q-Former rows; llm_ids / llm_mask int32 [k, T] left-padded prompt tokens
+        # (v4:260-266).  forced_tokens int32 [k, T_new] teacher-forces the fed-back ids (parity tests: keeps our run on the
+        # oracle's trajectory).
         w = self.w
-        dev = hidden.device
+        dev = feat.device
         k, T = llm_ids.shape
         d = w.d
+        d_q = feat.shape[1] // N_QUERY
         Tp = N_PREFIX + T
         max_ctx = Tp + max_new_tokens
         if max_ctx > MAX_CTX_KERNEL:
             raise ops._lib.OpsgError(ops._lib.OPSG_E_UNSUPPORTED, f"context {max_ctx} > {MAX_CTX_KERNEL} keys unsupported")
         llm_ids = llm_ids.to(device=dev, dtype=torch.int32).contiguous()
         llm_mask = llm_mask.to(device=dev, dtype=torch.int32).contiguous()
-        selected = selected.to(device=dev, dtype=torch.int32).contiguous()
 
-        # ---- a9: gather the selected pairs' 33 rows, project, assemble the embedded prompt -------------
-        feat = ops.gather_rows(hidden, N_QUERY * hidden.shape[1], selected)            # [k, 33*768]
-        proj = ops.gemm(feat.view(k * N_QUERY, hidden.shape[1]), self.w_proj, self.b_proj)      # [k*33, d]
+        # ---- a9: project the selected pairs' rows, assemble the embedded prompt -------------
+        proj = ops.gemm(feat.view(k * N_QUERY, d_q), self.w_proj, self.b_proj)         # [k*33, d]
         # positions / key mask of the prompt [1 x 32 ; left-padded text mask] and of every decode step, one small kernel:
         # OPT learned positions cumsum(mask)*mask - 1 + 2 (HF opt :64-70), Llama rotary positions cumsum(mask) - 1
         # (pads -> 0; HF generation/utils.py:707-729); generated token s sits at position n_valid + s (+2 for OPT)

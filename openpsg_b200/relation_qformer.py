@@ -117,7 +117,8 @@ class PackedQFormer:
 
 @dataclass
 class RelationQueryOutput:
-    hidden: torch.Tensor            # bf16 [B*33, d]: last_hidden_state[:, :33] stacked pair-major
+    hidden: torch.Tensor            # bf16 [B*33, d]: last_hidden_state[:, :33] stacked pair-major; with selected_rows_only
+                                    # bf16 [k*33, d]: the 33 rows of the k pairs in ``topk``, in that order (hidden_pairs = k)
     logits: torch.Tensor            # fp32 [B]
     probs: torch.Tensor             # fp32 [B]
     exist_mask: torch.Tensor        # uint8 [B]
@@ -125,6 +126,7 @@ class RelationQueryOutput:
     mask_bits: torch.Tensor         # int32 [N, words]
     image_tokens: torch.Tensor      # bf16 [L, 256]
     intermediates: Optional[dict] = None
+    hidden_pairs: Optional[int] = None   # None: ``hidden`` holds every pair; k: only the pairs of ``topk`` (selected_rows_only)
 
     def clone(self) -> "RelationQueryOutput":
         """Private copy of a result that lives in a CUDA graph's static buffers (overwritten by the next replay)."""
@@ -149,19 +151,22 @@ class GraphedRelationQuery:
     def entries(self):
         return self.cache.entries
 
-    def run(self, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, *, topk: int, threshold: float):
+    def run(self, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, *, topk: int, threshold: float,
+            selected_rows_only: bool = False):
         """A signature is replayed from its graph once it has been seen ``capture_after`` times; before that (and for
         signatures that never repeat, the common case on real PSG images) it runs eagerly through the same kernels."""
         dev = self.engine.w.device
         key = (tuple(feat.shape), tuple(pan.shape), tuple(int(x) for x in img_hw), tuple(int(x) for x in pad_hw),
-               int(obj_ids.numel()), tuple(input_ids.shape), int(topk), float(threshold))
+               int(obj_ids.numel()), tuple(input_ids.shape), int(topk), float(threshold), bool(selected_rows_only))
         e = self.cache.lookup(key)
         if e is None:
             if not self.cache.should_capture(key):
                 return self.engine.forward(self._dev(feat, torch.float32, dev), self._dev(pan, torch.int32, dev), img_hw, pad_hw,
                                            self._dev(obj_ids, torch.int32, dev), self._dev(input_ids, torch.int32, dev),
-                                           self._dev(text_mask, torch.int32, dev), topk=topk, threshold=threshold)
-            e = self._capture(key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev)
+                                           self._dev(text_mask, torch.int32, dev), topk=topk, threshold=threshold,
+                                           selected_rows_only=selected_rows_only)
+            e = self._capture(key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev,
+                              selected_rows_only)
             self.cache.insert(key, e)
         for name, src in (("feat", feat), ("pan", pan), ("obj_ids", obj_ids), ("input_ids", input_ids), ("text_mask", text_mask)):
             ops.copy_into(e[name], src)
@@ -173,7 +178,8 @@ class GraphedRelationQuery:
     def _dev(t, dtype, dev):
         return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
 
-    def _capture(self, key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev):
+    def _capture(self, key, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, dev,
+                 selected_rows_only=False):
         st = dict(
             feat=torch.empty(tuple(feat.shape), dtype=torch.float32, device=dev),
             pan=torch.empty(tuple(pan.shape), dtype=torch.int32, device=dev),
@@ -186,7 +192,7 @@ class GraphedRelationQuery:
 
         def run():
             return self.engine.forward(st["feat"], st["pan"], img_hw, pad_hw, st["obj_ids"], st["input_ids"], st["text_mask"],
-                                       topk=topk, threshold=threshold)
+                                       topk=topk, threshold=threshold, selected_rows_only=selected_rows_only)
 
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream(device=dev)
@@ -246,9 +252,16 @@ class RelationQueryTransformer:
     @torch.no_grad()
     def forward(self, feat: torch.Tensor, pan: torch.Tensor, img_hw, pad_hw, obj_ids: torch.Tensor,
                 input_ids: torch.Tensor, text_mask: torch.Tensor, *, topk: int = 20, threshold: float = 0.5,
-                pair_index: Optional[torch.Tensor] = None, keep_intermediates: bool = False) -> RelationQueryOutput:
+                pair_index: Optional[torch.Tensor] = None, keep_intermediates: bool = False,
+                selected_rows_only: bool = False) -> RelationQueryOutput:
         """feat fp32 [C,h,w]; pan int32 [Hp,Wp]; obj_ids int32 [N]; input_ids/text_mask int32 [B,T]
-        (B = N*N unless pair_index int32 [B] selects a subset of pairs)."""
+        (B = N*N unless pair_index int32 [B] selects a subset of pairs).
+
+        ``selected_rows_only``: what the reference consumes of the last layer is row 0 of every pair (existence logit,
+        v4:206-209) and rows 1..32 of the k SELECTED pairs (v4:215 gathers them for the LLM); every step after the last
+        layer's self-attention is row-wise, so the last layer then runs on B rows (row 0 of every pair) up to the top-k and
+        on k x 33 rows afterwards instead of on B x 33 rows: -34 % of the image's FLOPs.  Logits, mask, top-k and the selected
+        pairs' rows are the same values; ``hidden`` then holds only the selected pairs (see RelationQueryOutput)."""
         w = self.w
         dev = feat.device
         d = w.d
@@ -292,6 +305,8 @@ class RelationQueryTransformer:
             else:
                 qkv = ops.gemm(h, lw["w_qkv"], lw["b_qkv"])                      # [R, 3d]
                 ctx = ops.self_attn_small(qkv, text_mask, B, N_QUERY, T, NUM_HEADS, HEAD_DIM, text_queries=not last)
+            if last and selected_rows_only and inter is None:
+                return self._last_layer_selected(lw, ctx, h, kc, vt, bits_k, bits, X, N, B, L, pair_index, topk, threshold)
             rows = ctx.shape[0]                                                  # R, or B*33 on the last layer
             pre = ops.gemm(ctx, lw["w_o"], lw["b_o"], residual=h[:rows])
             h1 = ops.layernorm(pre, lw["ln_self"][0], lw["ln_self"][1], LN_EPS)
@@ -326,6 +341,42 @@ class RelationQueryTransformer:
                                                          min(topk, B))           # K8
         return RelationQueryOutput(hidden=out, logits=logits, probs=probs, exist_mask=mask, topk=top, mask_bits=bits,
                                    image_tokens=X, intermediates=inter)
+
+    def _query_rows_tail(self, lw, ctx, res, kc, vt, bits_k, N, n_pairs, n_query, L, pair_index):
+        """Everything of a layer after self-attention for a set of query rows (row-wise ops + K5): ctx / res bf16
+        [n_pairs * n_query, d] (row stride free), returns the layer output rows, contiguous."""
+        pre = ops.gemm(ctx, lw["w_o"], lw["b_o"], residual=res)
+        h1 = ops.layernorm(pre, lw["ln_self"][0], lw["ln_self"][1], LN_EPS)
+        qc = ops.gemm(h1, lw["w_cq"], lw["b_cq"])
+        # (the mask-bias tiles were built for 33 rows of every pair: these two calls take the kernel with in-kernel masks)
+        cx = ops.xattn_pairs(qc, kc, vt, bits_k, N, n_pairs, n_query, L, NUM_HEADS, HEAD_DIM, pair_index=pair_index,
+                             bias_tiles=False)
+        pre = ops.gemm(cx, lw["w_co"], lw["b_co"], residual=h1)
+        hq2 = ops.layernorm(pre, lw["ln_cross"][0], lw["ln_cross"][1], LN_EPS)
+        f = ops.gemm(hq2, lw["w_iq"], lw["b_iq"], act=ops.ACT_GELU)
+        pre = ops.gemm(f, lw["w_oq"], lw["b_oq"], residual=hq2)
+        return ops.layernorm(pre, lw["ln_q"][0], lw["ln_q"][1], LN_EPS)
+
+    def _last_layer_selected(self, lw, ctx, h, kc, vt, bits_k, bits, X, N, B, L, pair_index, topk, threshold):
+        """Last layer after its self-attention, only for the rows the reference consumes (``selected_rows_only``)."""
+        w = self.w
+        d = w.d
+        RQ = B * N_QUERY
+        # row 0 of every pair (strided views: row p of the operand = row 33 p of ctx / h) -> existence logits -> top-k
+        out0 = self._query_rows_tail(lw, ctx.view(B, N_QUERY, d)[:, 0], h[:RQ].view(B, N_QUERY, d)[:, 0], kc, vt, bits_k, N, B, 1,
+                                     L, pair_index)
+        k = min(topk, B)
+        logits, probs, mask, top = ops.exist_filter_topk(out0, d, B, d, w.exist_w, w.exist_b, threshold, k)      # K8
+        # the 33 rows of the k selected pairs
+        if k > 0:
+            ctx_sel = ops.gather_rows(ctx, N_QUERY * d, top).view(k * N_QUERY, d)
+            h_sel = ops.gather_rows(h, N_QUERY * d, top).view(k * N_QUERY, d)
+            pairs = top if pair_index is None else pair_index[top.long()].contiguous()
+            hidden = self._query_rows_tail(lw, ctx_sel, h_sel, kc, vt, bits_k, N, k, N_QUERY, L, pairs)
+        else:
+            hidden = torch.empty((0, d), dtype=torch.bfloat16, device=ctx.device)
+        return RelationQueryOutput(hidden=hidden, logits=logits, probs=probs, exist_mask=mask, topk=top, mask_bits=bits,
+                                   image_tokens=X, intermediates=None, hidden_pairs=k)
 
     # -- a3..a8 with LayerNorm folding ---------------------------------------------------------------------------------
     def _forward_folded(self, feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, pair_index, inter):

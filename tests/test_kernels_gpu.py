@@ -305,6 +305,36 @@ def test_llm_attn_static_cache(ops, hd, heads, q_len, pos0):
     assert (out.float().cpu() - ref).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("hd,heads,pos0,nseq", [(80, 32, 128, 9), (80, 32, 200, 40), (128, 8, 255, 13), (64, 12, 143, 5),
+                                                (80, 32, 64, 300), (128, 32, 15, 64), (64, 3, 0, 2)])
+def test_llm_attn_decode_long_context_many_sequences(ops, hd, heads, pos0, nseq):
+    """K10b decode kernel (mma.sync arithmetic over cp.async-staged head slices): contexts up to 256 keys (the 16-tile
+    instantiation), many sequences per launch (stacked images), random left padding.  tol 2e-2 abs (bf16 P and output)."""
+    g = torch.Generator().manual_seed(hd + pos0 + nseq)
+    max_ctx = 256
+    d = heads * hd
+    qkv = _rand_bf16((nseq, 3 * d), g)
+    kc = _rand_bf16((nseq, max_ctx, d), g)
+    vc = _rand_bf16((nseq, max_ctx, d), g)
+    pad = torch.randint(0, min(pos0, 20) + 1, (nseq,), generator=g)
+    kmask = (torch.arange(max_ctx)[None, :] >= pad[:, None]).to(torch.uint8)
+    kmask[:, pos0:] = 1
+    out = torch.zeros((nseq, d), dtype=torch.bfloat16, device="cuda")
+    kc_d, vc_d = kc.cuda(), vc.cuda()
+    ops.llm_attn_append(qkv.cuda(), kc_d, vc_d, kmask.cuda(), nseq, pos0, heads, hd, hd ** -0.5, out)
+    ctx = pos0 + 1
+    kc[:, pos0] = qkv[:, d:2 * d]
+    vc[:, pos0] = qkv[:, 2 * d:]
+    assert torch.equal(kc_d.cpu()[:, :ctx], kc[:, :ctx]) and torch.equal(vc_d.cpu()[:, :ctx], vc[:, :ctx])
+    q = qkv[:, :d].float().reshape(nseq, 1, heads, hd).permute(0, 2, 1, 3)
+    k = kc[:, :ctx].float().reshape(nseq, ctx, heads, hd).permute(0, 2, 1, 3)
+    v = vc[:, :ctx].float().reshape(nseq, ctx, heads, hd).permute(0, 2, 1, 3)
+    sc = q @ k.transpose(-1, -2) * hd ** -0.5
+    ok = kmask[:, None, None, :ctx].bool()
+    ref = (torch.softmax(sc.masked_fill(~ok, float("-inf")), -1) @ v).permute(0, 2, 1, 3).reshape(nseq, d)
+    assert (out.float().cpu() - ref).abs().max() < 2e-2
+
+
 @pytest.mark.parametrize("hd,heads,pos0", [(80, 32, 60), (64, 12, 0), (128, 8, 127)])
 def test_llm_attn_append_equals_append_then_attend(ops, hd, heads, pos0):
     """The fused decode entry (new k / v taken from the qkv row and written to the caches by the attention kernel) gives
