@@ -290,9 +290,10 @@ class RelationTransformerHeadV4(BaseModule):
         group = min(self.llm_batch_images, max(1, self.llm_batch_max_sequences // max(1, self.topk_pairs))) if with_llm else 1
         results = []
         pending = []
+        bufs = None          # group buffers of the LLM leg (selected rows, top-k indices), allocated at the first image
 
         def flush():
-            for res in self._decode_group(pending, on_result):
+            for res in self._decode_group(pending, bufs, on_result):
                 results.append(res)
             pending.clear()
 
@@ -306,7 +307,12 @@ class RelationTransformerHeadV4(BaseModule):
             for t in prep["device"].values():
                 t.record_stream(cur)
             if group > 1:
-                pending.append(self._run_queries(prep, keep=True))
+                if bufs is None:
+                    width = N_QUERY * self.qformer_feature_size
+                    bufs = (torch.empty((group * self.topk_pairs, width), dtype=torch.bfloat16, device=dev),
+                            torch.empty((group * self.topk_pairs,), dtype=torch.int32, device=dev))
+                at = sum(r["topk"].numel() for r in pending if r["out"] is not None)
+                pending.append(self._run_queries(prep, keep=(bufs[0], bufs[1], at)))
                 if len(pending) == group:
                     flush()
                 continue
@@ -380,21 +386,26 @@ class RelationTransformerHeadV4(BaseModule):
                                        d["q_mask"], **kw)
         self.last_output = out
         rec = dict(prep=prep, out=out)
-        if keep:
-            rec["rows"] = self._selected_rows(out, copy=True)
-            rec["topk"] = out.topk.clone()
+        if keep is not False:
+            # `keep` = (rows buffer bf16 [group * topk, 33*768], top-k buffer int32 [group * topk], first free slot): the next
+            # image overwrites the graph's static outputs, so what the LLM leg needs moves into the group's buffers now
+            rows_buf, topk_buf, at = keep
+            k = out.topk.numel()
+            rec["rows"] = self._selected_rows(out, into=rows_buf[at:at + k])
+            rec["topk"] = _ops.copy_into(topk_buf[at:at + k], out.topk)
+            rec["slot"] = at
         return rec
 
     @staticmethod
-    def _selected_rows(out, copy=False):
+    def _selected_rows(out, into=None):
         """bf16 [k, 33*768]: the 33 Q-Former rows of the selected pairs, in ``out.topk`` order (v4:215)."""
         from . import ops as _ops
         k = out.topk.numel()
         width = N_QUERY * out.hidden.shape[1]
         if out.hidden_pairs is not None:                     # last_layer_selected_rows_only: already gathered
             rows = out.hidden.view(k, width)
-            return rows.clone() if copy else rows
-        return _ops.gather_rows(out.hidden, width, out.topk)
+            return rows if into is None else _ops.copy_into(into, rows)
+        return _ops.gather_rows(out.hidden, width, out.topk, out=into)
 
     def _parse_relations(self, selected, n, texts):
         """v4:315-326: generated text -> unique [subject, object, relation] triples."""
@@ -435,7 +446,7 @@ class RelationTransformerHeadV4(BaseModule):
             rel_pred, rel_score = self._parse_relations(selected, n, texts)
         return {'rel_pred': rel_pred, 'rel_score': rel_score}
 
-    def _decode_group(self, records, on_result=None):
+    def _decode_group(self, records, bufs, on_result=None):
         """LLM leg (a9-a10) of a group of images as ONE batch of sum(k_i) sequences.  Prompts of different images are
         left-padded to the group's longest one (padding is masked and positions are derived from the mask, v4:260-266 pads the
         same way inside one image).  ``on_result(head)`` sees ``last_generation`` restricted to the image's own sequences;
@@ -446,7 +457,10 @@ class RelationTransformerHeadV4(BaseModule):
         results = {}
         if live:
             counts = [r["topk"].numel() for r in live]
-            topk_host = torch.cat([r["topk"] for r in live]).tolist()                   # one D2H sync per group (v4:236-237)
+            total = sum(counts)
+            # the group's records sit back to back in the group buffers (slot = running sum of the counts)
+            rows_all, topk_all = bufs[0][:total], bufs[1][:total]
+            topk_host = topk_all.tolist()                                               # one D2H sync per group (v4:236-237)
             ids, masks, selected_lists = [], [], []
             at = 0
             for r, k in zip(live, counts):
@@ -460,8 +474,7 @@ class RelationTransformerHeadV4(BaseModule):
             pad_id = self._llm_cache.pad_id
             ids = torch.cat([torch.nn.functional.pad(t, (T - t.shape[1], 0), value=pad_id) for t in ids])
             masks = torch.cat([torch.nn.functional.pad(t, (T - t.shape[1], 0), value=0) for t in masks])
-            rows = torch.cat([r["rows"] for r in live]) if len(live) > 1 else live[0]["rows"]
-            gen = self._llm_engine.generate_rows(rows, ids.to(dev), masks.to(dev), max_new_tokens=self.max_new_tokens)
+            gen = self._llm_engine.generate_rows(rows_all, ids.to(dev), masks.to(dev), max_new_tokens=self.max_new_tokens)
             tokens = gen.tokens.cpu()
             texts = self.llm_tokenizer.batch_decode(tokens)                             # v4:313
             at = 0
