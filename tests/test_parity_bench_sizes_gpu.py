@@ -16,15 +16,23 @@ def _logit_tol(ref):
     return 1e-1 + 5e-2 * ref.abs()
 
 
-def test_cfg3_llm_leg_32_layers_100_pairs_32_tokens():
-    cfg = synth.OPT_2P7B
+@pytest.fixture(scope="module")
+def cfg3_head():
+    """The head bench.py's LLM legs build: random-init OPT-2.7B (32 layers) on the device, cfg3's top-100 / 32 tokens; plus the
+    Q-Former rows of cfg3 image 0."""
     wl = synth.WORKLOADS["cfg3"]
-    head = synth.build_synthetic_head(llm=cfg, max_object_num=80, topk_pairs=wl.topk_pairs, max_new_tokens=wl.max_new_tokens,
-                                      device=DEV, llm_on_device=True)
+    head = synth.build_synthetic_head(llm=synth.OPT_2P7B, max_object_num=80, topk_pairs=wl.topk_pairs,
+                                      max_new_tokens=wl.max_new_tokens, device=DEV, llm_on_device=True)
     head.repack(DEV)
     assert head._llm_engine.w.n_layers == 32
     head(synth.inputs_to(synth.make_image_inputs(wl, 0), DEV), is_generation=False)
-    hidden = head.last_output.hidden.clone()
+    return head, head.last_output.hidden.clone()
+
+
+def test_cfg3_llm_leg_32_layers_100_pairs_32_tokens(cfg3_head):
+    cfg = synth.OPT_2P7B
+    wl = synth.WORKLOADS["cfg3"]
+    head, hidden = cfg3_head
     # the decode-only leg of bench.py (_llm_legs): same seeds, same shapes
     k, T, t_new = wl.topk_pairs, 17, wl.max_new_tokens
     g = torch.Generator().manual_seed(5)
@@ -67,3 +75,54 @@ def test_cfg3_llm_leg_32_layers_100_pairs_32_tokens():
             if not bool(decided[r, t]):
                 break
             assert int(fr[r, t]) == int(ref_toks[r, t]), (r, t)
+
+
+def test_cfg3_stacked_llm_batch_800_sequences(cfg3_head):
+    """The batch head.forward_batch / bench.py's `relation_tokens_per_sec` leg runs: the selected pairs of 8 cfg3 images stacked
+    into ONE batch of 800 sequences (decode steps on the CTA-pair GEMM at M = 800, decode attention over 25 600 (sequence, head)
+    items), 32 layers, 32 tokens.  Eager, captured and replayed runs agree bit for bit; 8 sequences spread over the batch are
+    compared with the fp32 oracle under the A.7 rule while the other 792 follow their own greedy trajectory."""
+    from openpsg_b200 import ops
+    cfg = synth.OPT_2P7B
+    wl = synth.WORKLOADS["cfg3"]
+    head, hidden = cfg3_head
+    eng = head._llm_engine
+    n_img, k, T, t_new = 8, wl.topk_pairs, 17, wl.max_new_tokens
+    K = n_img * k
+    g = torch.Generator().manual_seed(5)                     # bench.py decode_leg(8): same seeds, same shapes
+    sel = torch.cat([torch.randperm(hidden.shape[0] // 33, generator=g)[:k] for _ in range(n_img)]).to(torch.int32).to(DEV)
+    ids = torch.randint(4, cfg["vocab_size"], (K, T), generator=g).to(torch.int32).to(DEV)
+    lens = torch.randint(14, T + 1, (K, 1), generator=g)
+    mask = (torch.arange(T)[None, :] >= (T - lens)).to(torch.int32).to(DEV)
+    rows = ops.gather_rows(hidden, 33 * hidden.shape[1], sel)
+    free = eng.generate_rows(rows, ids, mask, max_new_tokens=t_new).tokens.clone()
+    free2 = eng.generate_rows(rows, ids, mask, max_new_tokens=t_new).tokens.clone()      # second sighting: captured graph
+    free3 = eng.generate_rows(rows, ids, mask, max_new_tokens=t_new).tokens.clone()      # replay
+    assert torch.equal(free, free2) and torch.equal(free, free3), "eager, captured and replayed stacked decode agree bit for bit"
+    print(f"stacked tokens_checksum (bench.py relation_tokens_per_sec.tokens_checksum) = {int(free.long().sum())}")
+
+    idx = torch.tensor([3, 117, 226, 341, 455, 569, 683, 799], device=DEV)
+    sd = {n: v.detach().float() for n, v in head.state_dict().items() if n.startswith(("language_model.", "language_projection."))}
+    feat = hidden.float().reshape(-1, 33, 768)[sel[idx].long()][:, 1:]
+    embeds, m = restated.build_llm_prefix(sd, feat, ids[idx].long(), mask[idx].long())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref_toks, ref_scores = restated.opt_greedy_decode(sd, cfg, embeds, m, t_new)
+    del sd
+    forced = free.clone()
+    forced[idx] = ref_toks.to(torch.int32)
+    gen = eng.generate_rows(rows, ids, mask, max_new_tokens=t_new, return_scores=True, forced_tokens=forced)
+    got = gen.scores[idx]
+    err = (got - ref_scores).abs()
+    tol = _logit_tol(ref_scores)
+    top2 = ref_scores.topk(2, dim=-1).values
+    decided = (top2[..., 0] - top2[..., 1]) > 2 * _logit_tol(top2[..., 0])
+    match = (gen.tokens[idx].long() == ref_toks).float().mean().item()
+    print(f"stacked depth-32 parity: max|dlogit|={err.max().item():.4f} (ref absmax {ref_scores.abs().max().item():.2f}), "
+          f"worst err/tol={(err / tol).max().item():.3f}, decided={decided.float().mean().item():.2f}, id_match={match:.3f}")
+    assert (err <= tol).all(), (err - tol).max().item()
+    assert torch.equal(gen.tokens[idx].long()[decided], ref_toks[decided])
+    # the other sequences were fed their own greedy tokens: the teacher-forced run reproduces the free run there
+    others = torch.ones(K, dtype=torch.bool, device=DEV)
+    others[idx] = False
+    assert torch.equal(gen.tokens[others], free[others])
