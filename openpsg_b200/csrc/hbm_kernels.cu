@@ -168,6 +168,111 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16
   ln_normalize_store<CHUNKS>(v, cols, gamma, beta, eps, y + static_cast<size_t>(row) * cols);
 }
 
+// LayerNorm over many rows of <= 1024 columns (the Q-Former's 8 LayerNorm passes per image: 11 % of the step).  The
+// one-row-per-warp kernel above holds its loads in registers: ~27 warps x 1.5 KB in flight per SM = 4 TB/s at HBM latency
+// (ncu: DRAM 38-45 %, issue slots 52 %).  Here the bytes in flight live in shared memory instead: a CTA walks slabs of 8
+// consecutive rows (ONE 1-D bulk copy of 12 KB each) through a 4-stage ring, warp w normalises row w of the slab out of shared
+// memory with gamma / beta held in registers (111 registers, two CTAs per SM), and stores straight from registers.  Same lane
+// <-> column assignment and reduction order as ln_normalize_store.  Measured per 32-image step: 8.4 ms against 9.4 for the
+// kernel above (4.3 against 3.9 TB/s); the variant that reloads gamma / beta per row at four CTAs per SM: 11.0 ms.  ncu
+// (profiles/r2_ncu_layernorm_ring.md): 34.5 us per launch, issue slots 55 %, DRAM 40 % -- still bound by the per-row chain.  Slabs are walked from the END of the tensor
+// (what the producing GEMM wrote last is still in L2).
+constexpr int kLnRingStages = 4, kLnRingRows = 8;
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(256, 2) layernorm_ring_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps,
+                                                                 __nv_bfloat16* __restrict__ y, int rows, int cols, int slabs_per_cta) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __shared__ __align__(8) uint64_t full[kLnRingStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_bytes = cols * 2, stage_bytes = kLnRingRows * row_bytes;
+  const int total_slabs = (rows + kLnRingRows - 1) / kLnRingRows;
+  const int j0 = blockIdx.x * slabs_per_cta;
+  const int n_slabs = min(slabs_per_cta, total_slabs - j0);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kLnRingStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  // gamma / beta of this lane's columns stay in registers for all rows of the CTA (constant inputs: loaded before the wait)
+  float g[CHUNKS][8], b[CHUNKS][8];
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
+    if (c0 < cols) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+      g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+      b[i][0] = b0.x; b[i][1] = b0.y; b[i][2] = b0.z; b[i][3] = b0.w; b[i][4] = b1.x; b[i][5] = b1.y; b[i][6] = b1.z; b[i][7] = b1.w;
+    }
+  }
+  __syncthreads();
+  pdl_wait_then_trigger();
+  if (n_slabs <= 0) return;
+  // slab j (0 = the LAST 8 rows of the tensor) covers rows [max(0, rows - 8 (j + 1)), rows - 8 j)
+  auto issue = [&](int t) {                                   // thread 0: t-th slab of this CTA into stage t % stages
+    const int j = j0 + t;
+    const int hi = rows - kLnRingRows * j, lo = max(0, hi - kLnRingRows);
+    const uint32_t bytes = static_cast<uint32_t>(hi - lo) * row_bytes;
+    uint64_t* bar = &full[t % kLnRingStages];
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(ln_smem + (t % kLnRingStages) * stage_bytes, x + static_cast<size_t>(lo) * cols, bytes, bar);
+  };
+  if (threadIdx.x == 0)
+    for (int t = 0; t < min(n_slabs, kLnRingStages); ++t) issue(t);
+  for (int t = 0; t < n_slabs; ++t) {
+    const int st = t % kLnRingStages;
+    const int j = j0 + t;
+    const int hi = rows - kLnRingRows * j, lo = max(0, hi - kLnRingRows);
+    mbar_wait(&full[st], (t / kLnRingStages) & 1);
+    if (lo + warp < hi) {
+      const uint8_t* src = ln_smem + st * stage_bytes + warp * row_bytes;
+      float v[CHUNKS][8];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c0 = (i * 32 + lane) * 8;
+        if (c0 < cols) {
+          const uint4 u = *reinterpret_cast<const uint4*>(src + c0 * 2);
+          v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
+          v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s += v[i][k];
+        }
+      }
+      const float mean = warp_sum(s) / cols;
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i)
+        if ((i * 32 + lane) * 8 < cols) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; ss += d * d; }
+        }
+      const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
+      __nv_bfloat16* yr = y + static_cast<size_t>(lo + warp) * cols;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c0 = (i * 32 + lane) * 8;
+        if (c0 < cols) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[i][k] + b[i][k];
+          uint4 u;
+          u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+          u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(yr + c0) = u;
+        }
+      }
+    }
+    if (t + kLnRingStages < n_slabs) {                        // the stage is free once every warp has read its row
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) issue(t + kLnRingStages);
+    }
+  }
+}
+
 // K7: row p*nq+q = LN(query[q]); row B*nq + p*T + t = LN(word_emb[ids[p,t]] + pos_emb[t]).  d <= 1024.
 __global__ void __launch_bounds__(256) qformer_embed_ln_kernel(const float* __restrict__ query, int nq,
                                                                const int32_t* __restrict__ ids, int B, int T,
@@ -546,6 +651,27 @@ extern "C" int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const
   const int grid = ceil_div(static_cast<long long>(rows) * 32, 256);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  // many rows of <= 1024 columns (the Q-Former): shared-memory ring fed by bulk copies
+  if (rows >= 4096 && cols <= 1024 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0) {
+    const int total_slabs = ceil_div(rows, kLnRingRows);
+    const int smem = kLnRingStages * kLnRingRows * cols * 2;
+    int spc = ceil_div(total_slabs, opsg_num_sms() * 2);      // two CTAs per SM (48 KB of ring each at 768 columns), one wave
+    if (spc < kLnRingStages) spc = kLnRingStages;
+    const int ctas = ceil_div(total_slabs, spc);
+    static bool configured_dev[64] = {};
+    bool& configured = configured_dev[device_slot()];
+    if (!configured) {
+      rc = check_cuda(cudaFuncSetAttribute(layernorm_ring_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute(layernorm_ring<3>)");
+      if (rc) return rc;
+      rc = check_cuda(cudaFuncSetAttribute(layernorm_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute(layernorm_ring<4>)");
+      if (rc) return rc;
+      configured = true;
+    }
+    if (cols <= 768) launch_kernel(layernorm_ring_kernel<3>, ctas, 256, smem, ST(stream), xp, gamma, beta, eps, yp, rows, cols, spc);
+    else launch_kernel(layernorm_ring_kernel<4>, ctas, 256, smem, ST(stream), xp, gamma, beta, eps, yp, rows, cols, spc);
+    OPSG_CHECK_LAUNCH("layernorm_ring_kernel");
+    return OPSG_OK;
+  }
   if (cols > 4096)
     launch_kernel(layernorm_row_cta_kernel<4>, rows, 256, 0, ST(stream), xp, gamma, beta, eps, yp, cols);
   else if ((rows <= 4096 && cols >= 1024) || cols > 256 * kMaxChunks)

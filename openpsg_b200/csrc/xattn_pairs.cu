@@ -87,12 +87,6 @@ __device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32
   d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
-// 1-D bulk copy global -> shared, completion on an mbarrier
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 struct XaSmem {
   static constexpr int kK = kXaKeys * 128;              // 32768: K [256 keys x 64] SW128 K-major

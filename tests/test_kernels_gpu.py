@@ -237,9 +237,13 @@ def test_qformer_embed_ln(ops):
     assert (out - ref).abs().max() < 2.5e-2       # bf16 output rounding of O(4) values
 
 
-@pytest.mark.parametrize("rows,cols", [(333, 768), (333, 320), (333, 2560), (5000, 2560), (100, 3072), (1, 1024)])
+@pytest.mark.parametrize("rows,cols", [(333, 768), (333, 320), (333, 2560), (5000, 2560), (100, 3072), (1, 1024),
+                                       # >= 4096 rows of <= 1024 columns: the shared-memory ring kernel (slabs of 8 rows, partial
+                                       # last slab, fewer slabs than ring stages per CTA, the cfg2 row counts)
+                                       (4096, 768), (4099, 768), (52800, 768), (78400, 768), (25600, 768), (5003, 1024),
+                                       (6001, 256), (40000, 328)])
 def test_layernorm(ops, rows, cols):
-    """Warp-per-row kernel (many rows) and CTA-per-row kernel (<= 512 rows of >= 1024 columns: LLM decode)."""
+    """Warp-per-row kernel, CTA-per-row kernel (<= 4096 rows of >= 1024 columns: LLM decode) and the bulk-copy ring kernel."""
     g = torch.Generator().manual_seed(3)
     x = _rand_bf16((rows, cols), g, 2.0)
     gamma = 1 + 0.1 * torch.randn(cols, generator=g)
@@ -247,6 +251,13 @@ def test_layernorm(ops, rows, cols):
     out = ops.layernorm(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5).float().cpu()
     ref = torch.nn.functional.layer_norm(x.float(), (cols,), gamma, beta, 1e-5)
     assert (out - ref).abs().max() < 3e-2
+    if rows >= 4096 and cols <= 1024:
+        # same lane <-> column assignment and reduction order as the warp-per-row kernel: a prefix of the rows through that
+        # kernel (fewer than 4096 rows) differs at most by the compiler's FMA contraction of the final scale-and-shift, i.e. by
+        # one bf16 rounding step on a handful of elements
+        head = ops.layernorm(x[:1000].cuda(), gamma.cuda(), beta.cuda(), 1e-5).float().cpu()
+        diff = (head - out[:1000]).abs()
+        assert diff.max() <= 3.2e-2 and (diff > 0).float().mean() < 1e-3, (diff.max(), (diff > 0).float().mean())
 
 
 # ----------------------------------------------------------------------------------------------
