@@ -257,10 +257,12 @@ int opsg_llm_prompt_layout(const int32_t* text_mask, int nseq, int T, int n_pref
                            void* stream);
 int opsg_copy_bytes(void* dst, const void* src, size_t nbytes, void* stream);
 /* Second half of the deterministic split-K GEMM (opsg_gemm_bf16 with out_mode OPSG_OUT_F32 and k_splits > 1 writes split s
- * to slice s of a fp32 [k_splits][M][N] buffer): out = bf16(bias + sum of the slices, in split order).  K1 PatchEmbed
- * (timm PatchEmbed, v4:410) uses it so that two runs return the same bits. */
-int opsg_splitk_reduce_bf16(const float* partials, int splits, int rows, int cols, const float* bias, opsg_bf16* out,
-                            int ld_out, void* stream);
+ * to slice s of a fp32 [k_splits][M][N] buffer): out = bf16(bias + sum of the slices, in split order (+ residual, bf16
+ * [rows, ld_res], may be NULL, may alias out)).  K1 PatchEmbed (timm PatchEmbed, v4:410) uses it so that two runs return the
+ * same bits; the LLM's out_proj / fc2 (down_proj) Linears of a stacked decode step (a few hundred rows, N = hidden size: too
+ * few output tiles for the machine; HF:opt:181,232-236 / HF llama :262,184) take it with their residual. */
+int opsg_splitk_reduce_bf16(const float* partials, int splits, int rows, int cols, const float* bias, const opsg_bf16* residual,
+                            int ld_res, opsg_bf16* out, int ld_out, void* stream);
 int opsg_transpose_i32(const int32_t* src, int rows, int cols, int32_t* dst, void* stream);
 
 /* ---- f1 / f2: the integer passes either side of the head in the reference's inference loop --------------------------

@@ -56,7 +56,7 @@ SIGNATURES = {
     "opsg_llm_prompt_layout": [P, I, I, I, I, I, P, P, P, P, P],
     "opsg_copy_bytes": [P, P, ctypes.c_size_t, P],
     "opsg_transpose_i32": [P, I, I, P, P],
-    "opsg_splitk_reduce_bf16": [P, I, I, I, P, P, I, P],
+    "opsg_splitk_reduce_bf16": [P, I, I, I, P, P, I, P, I, P],
     "opsg_pan_relabel": [P, ctypes.c_longlong, P, P, I, P, P],
     "opsg_pan_colorize": [P, ctypes.c_longlong, P, P, I, P, P],
 }

@@ -611,7 +611,8 @@ extern "C" int opsg_gemm_bf16(const opsg_bf16* A, int lda, const opsg_bf16* W, i
   const int m_tiles = (M + kBM - 1) / kBM;
   int bn = 256;
   const int sms = opsg_num_sms();
-  while (bn > 32 && (N <= bn / 2 || m_tiles * ((N + bn - 1) / bn) * k_splits < sms)) bn >>= 1;
+  // (a grid within an eighth of the machine keeps the wider tile: 140 CTAs of 128 x 256 beat 280 of 128 x 128 in two waves)
+  while (bn > 32 && (N <= bn / 2 || m_tiles * ((N + bn - 1) / bn) * k_splits < sms - sms / 8)) bn >>= 1;
 
   CUtensorMap tmA, tmB, tmD;
   rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);

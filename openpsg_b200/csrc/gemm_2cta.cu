@@ -578,7 +578,9 @@ int launch_gemm_2cta(const opsg_bf16* A, int lda, const opsg_bf16* W, int ldw, o
   const int m2_tiles = (M + 2 * kBM - 1) / (2 * kBM);
   const int n_tiles = (N + kBN - 1) / kBN;
   if ((ldd % 8) != 0 || (reinterpret_cast<uintptr_t>(D) & 15) != 0) return OPSG_E_UNSUPPORTED;
-  if (!ln && (N < kBN || m2_tiles * n_tiles < sms / 2)) return OPSG_E_UNSUPPORTED;     // small problems: 1-CTA kernel
+  // small problems: 1-CTA kernel.  From a quarter of the machine's CTA pairs on, the pair kernel's full-rate tiles win (40 tiles of
+  // 800 x 2560 x 2560: one wave at ~17 us against 24.6 us for 280 operand-bandwidth-bound 128 x 64 tiles of the 1-CTA kernel)
+  if (!ln && (N < kBN || m2_tiles * n_tiles < sms / 4)) return OPSG_E_UNSUPPORTED;
   CUtensorMap tmA, tmB, tmD, tmR;
   int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);
   if (rc) return rc;

@@ -174,11 +174,12 @@ __global__ void transpose_i32_kernel(const int32_t* __restrict__ src, int rows, 
 }
 
 
-// out[r, c] = bf16(bias[c] + sum_s partials[s][r][c]), slices summed in split order (fixed order -> bit-reproducible);
-// thread = 4 consecutive columns, 16-byte loads, `splits` independent loads in flight per thread in groups of 8.
+// out[r, c] = bf16(bias[c] + sum_s partials[s][r][c] (+ residual[r, c])), slices summed in split order (fixed order ->
+// bit-reproducible); thread = 4 consecutive columns, 16-byte loads, `splits` independent loads in flight per thread in groups
+// of 8.  residual may alias out (every thread reads its own 4 elements before it writes them).
 __global__ void __launch_bounds__(256) splitk_reduce_bf16_kernel(const float* __restrict__ partials, int splits, int rows, int cols,
-                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                                 int ld_out) {
+                                                                 const float* __restrict__ bias, const __nv_bfloat16* residual,
+                                                                 int ld_res, __nv_bfloat16* out, int ld_out) {
   pdl_wait_then_trigger();
   const int vec = cols / 4;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -199,6 +200,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_bf16_kernel(const float* __
   for (; s < splits; ++s) {
     const float4 v = __ldcs(src + (static_cast<size_t>(s) * slice) / 4);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (residual) {
+    const uint2 rv = *reinterpret_cast<const uint2*>(residual + r * ld_res + c * 4);
+    acc.x += bf16_lo(rv.x); acc.y += bf16_hi(rv.x); acc.z += bf16_lo(rv.y); acc.w += bf16_hi(rv.y);
   }
   uint2 o;
   o.x = pack_bf16x2(acc.x, acc.y);
@@ -295,15 +300,17 @@ extern "C" int opsg_transpose_i32(const int32_t* src, int rows, int cols, int32_
   return OPSG_OK;
 }
 
-extern "C" int opsg_splitk_reduce_bf16(const float* partials, int splits, int rows, int cols, const float* bias, opsg_bf16* out,
-                                       int ld_out, void* stream) {
+extern "C" int opsg_splitk_reduce_bf16(const float* partials, int splits, int rows, int cols, const float* bias,
+                                       const opsg_bf16* residual, int ld_res, opsg_bf16* out, int ld_out, void* stream) {
   int rc = opsg_device_check();
   if (rc) return rc;
   OPSG_CHECK_ARG(partials && out, "splitk_reduce: null pointer");
   OPSG_CHECK_ARG(splits > 0 && rows > 0 && cols > 0 && cols % 4 == 0 && ld_out % 4 == 0 && ld_out >= cols, "splitk_reduce: bad shape");
   OPSG_CHECK_ARG((((uintptr_t)partials | (uintptr_t)bias) & 15) == 0 && ((uintptr_t)out & 7) == 0, "splitk_reduce: bad alignment");
+  OPSG_CHECK_ARG(!residual || (ld_res % 4 == 0 && ld_res >= cols && ((uintptr_t)residual & 7) == 0), "splitk_reduce: bad residual layout");
   launch_kernel(splitk_reduce_bf16_kernel, ceil_div_ll(static_cast<long long>(rows) * (cols / 4), 256), 256, 0, ST(stream),
-                partials, splits, rows, cols, bias, reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+                partials, splits, rows, cols, bias, reinterpret_cast<const __nv_bfloat16*>(residual), ld_res,
+                reinterpret_cast<__nv_bfloat16*>(out), ld_out);
   OPSG_CHECK_LAUNCH("splitk_reduce_bf16_kernel");
   return OPSG_OK;
 }

@@ -215,7 +215,9 @@ class LLMDecodeEngine:
         # 17 / 11 / 21 / 20 us for qkv / out / fc1 / fc2 at k = 100 inside a graph against 22 / 13 / 24 / 40 us for the tiled
         # kernel (scripts/kbench.py streamk).  Tried and dropped (profiles/r2_decode_timeline.md): L2 prefetch of the next
         # GEMM's weights from a side kernel (164 ms per cfg3 image against 121), constant-weight early streaming inside the GEMM.
-        gemm = ops.gemm_small_m if h.shape[0] <= 128 else ops.gemm
+        # more rows (prefill; decode steps of a batch stacked over several images): the tiled kernels, with K split for the
+        # N = hidden-size Linears while they have too few output tiles for the machine (ops.gemm_medium_m)
+        gemm = ops.gemm_small_m if h.shape[0] <= 128 else ops.gemm_medium_m
         x = self._norm(h, lw["norm1"])
         qkv = gemm(x, lw["w_qkv"], lw["b_qkv"])                                        # [rows, 3d]
         if w.rope is not None:

@@ -526,16 +526,39 @@ def transpose_i32(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-def gemm_splitk(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k_splits: int, out: Optional[torch.Tensor] = None):
-    """Deterministic split-K GEMM for skinny-M / huge-K problems (PatchEmbed: K = 65536): every split writes its fp32
-    partial to its own slice, a second kernel sums the slices in split order and applies the bias -> bf16 [M, N]."""
+def gemm_splitk(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k_splits: int, out: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None):
+    """Deterministic split-K GEMM for problems with too few output tiles for the machine (PatchEmbed: K = 65536; the LLM's
+    out_proj / fc2 at a few hundred rows): every split writes its fp32 partial to its own slice, a second kernel sums the
+    slices in split order and applies bias (+ residual, which may alias ``out``) -> bf16 [M, N]."""
     M, K = a.shape
     N = w.shape[0]
     part = torch.empty((k_splits, M, N), dtype=torch.float32, device=a.device)
     gemm(a, w, out=part.view(k_splits * M, N)[:M], k_splits=k_splits)          # the kernel strides the slices by M rows
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    if residual is not None:
+        _cuda(residual, torch.bfloat16, "residual")
+        assert residual.shape == (M, N) and residual.stride(1) == 1
     with _timed("splitk_reduce", 0.0, 4.0 * part.numel() + 2.0 * M * N):
-        _lib.check(_lib.load().opsg_splitk_reduce_bf16(_ptr(part), k_splits, M, N, _ptr(bias), _ptr(out), out.stride(0), _stream()))
+        _lib.check(_lib.load().opsg_splitk_reduce_bf16(_ptr(part), k_splits, M, N, _ptr(bias), _ptr(residual),
+                                                      residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0),
+                                                      _stream()))
     _count()
     return out
+
+
+def gemm_medium_m(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+                  residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Linear for a few hundred rows (stacked LLM decode steps).  Wide outputs have enough 256 x 256 tiles for the CTA-pair
+    kernel; N = hidden-size outputs with a LONG K (fc2 / down_proj: 40 tiles at 800 x 2560, K = 10240) do not, so K is split
+    until the 128 x 256 tiles of the single-CTA kernel fill ONE wave, and the fixed-order reduction applies bias and residual.
+    Measured at M = 800 (OPT-2.7B, scripts/gemm_medium_m.py, profiles/r2_gemm_medium_m.md): fc2 79.9 -> 51.6 us.  The fp32
+    partial epilogue costs ~20 us, so short-K Linears (out_proj, K = 2560: 24.6 us plain, 46.7 us split) stay on the tiled path."""
+    M, K = a.shape
+    N = w.shape[0]
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    splits = min(148 // max(1, tiles), K // 512)
+    if act != ACT_NONE or K < 6144 or splits < 2 or N % 4 or (M + 255) // 256 * ((N + 255) // 256) >= 74:
+        return gemm(a, w, bias, residual=residual, act=act, out=out)
+    return gemm_splitk(a, w, bias, splits, out=out, residual=residual)

@@ -116,6 +116,33 @@ def test_gemm_split_k_atomic(ops):
     assert (acc.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max()
 
 
+@pytest.mark.parametrize("M,N,K,res,inplace", [(800, 2560, 10240, True, True), (800, 2560, 2560, True, False), (400, 2560, 2560, True, True),
+                                               (200, 2560, 10240, False, False), (777, 2560, 2560, True, True), (300, 768, 3072, True, False),
+                                               # shapes that stay on the plain tiled path (wide output / too many tiles / activation)
+                                               (800, 7680, 2560, False, False), (4900, 2560, 2560, True, True)])
+def test_gemm_medium_m_split_k(ops, M, N, K, res, inplace):
+    """ops.gemm_medium_m: N = hidden-size Linears at a few hundred rows (stacked LLM decode steps) through the deterministic
+    split-K path (fp32 partial slices + fixed-order reduction with bias and residual, in place over the residual) against
+    fp32; two runs give the same bits.  tol as test_gemm: 1.2e-2 of the output scale."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = _rand_bf16((M, K), g).cuda()
+    w = _rand_bf16((N, K), g, 1.0 / math.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    r = _rand_bf16((M, N), g).cuda() if res else None
+    ref = a.float() @ w.float().t() + bias + (r.float() if res else 0)
+    runs = []
+    for _ in range(2):
+        if inplace:
+            h = r.clone()
+            out = ops.gemm_medium_m(a, w, bias, residual=h, out=h)
+            assert out.data_ptr() == h.data_ptr()
+        else:
+            out = ops.gemm_medium_m(a, w, bias, residual=r)
+        runs.append(out.float())
+    assert torch.equal(runs[0], runs[1])
+    assert (runs[0] - ref).abs().max() <= 1.2e-2 * ref.abs().max()
+
+
 STREAMK_CASES = [
     # M, N, K, bias, residual, act, out_dtype      (LLM decode shapes: OPT-2.7B qkv / out / fc1 / fc2 / lm_head)
     (100, 7680, 2560, True, False, 0, torch.bfloat16),
