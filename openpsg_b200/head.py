@@ -408,18 +408,28 @@ class RelationTransformerHeadV4(BaseModule):
         return _ops.gather_rows(out.hidden, width, out.topk, out=into)
 
     def _parse_relations(self, selected, n, texts):
-        """v4:315-326: generated text -> unique [subject, object, relation] triples."""
+        """v4:315-326: generated text -> unique [subject, object, relation] triples, in order of first appearance (the
+        reference's `name in relation_categories` / `.index(name)` / `rel_pred not in rel_pred_list` through a dict and a
+        set: linear instead of quadratic in the number of triples)."""
+        index_of = getattr(self, "_relation_index", None)
+        if index_of is None:
+            index_of = {}
+            for i, name in enumerate(relation_categories):
+                index_of.setdefault(name, i)                  # list.index returns the first occurrence
+            self._relation_index = index_of
         rel_pred: List[List[int]] = []
         rel_score: List[float] = []
+        seen = set()
         for si, text in zip(selected, texts):
             parts = text.split('<s>')
             body = (parts[1] if len(parts) > 1 else parts[0]).split('</s>')[0].strip()
+            sub, obj = si // n, si % n
             for name in body.split('  '):
-                if name in relation_categories:
-                    trip = [si // n, si % n, relation_categories.index(name)]
-                    if trip not in rel_pred:
-                        rel_pred.append(trip)
-                        rel_score.append(1)
+                rel = index_of.get(name)
+                if rel is not None and (sub, obj, rel) not in seen:
+                    seen.add((sub, obj, rel))
+                    rel_pred.append([sub, obj, rel])
+                    rel_score.append(1)
         return rel_pred, rel_score
 
     def _run(self, prep, is_generation):

@@ -63,3 +63,36 @@ def test_workload_table():
     w = synth.WORKLOADS["cfg2"]
     assert (w.queries, w.ordered_pairs, w.image_tokens) == (1600, 1560, 256)
     assert synth.WORKLOADS["cfg5"].ordered_pairs == 6320
+
+
+def test_parse_relations_equals_the_reference_loop():
+    """head._parse_relations (dict / set) against the reference's statements v4:315-326 (list membership, list.index, list-of-lists
+    dedupe) on random generations, repeated names, unknown names and texts without the <s> marker."""
+    import numpy as np
+    from openpsg_b200.categories import relation_categories
+    from openpsg_b200.head import RelationTransformerHeadV4
+
+    def reference_loop(selected, n, texts):
+        rel_pred, rel_score = [], []
+        for si, text in zip(selected, texts):
+            parts = text.split('<s>')
+            body = (parts[1] if len(parts) > 1 else parts[0]).split('</s>')[0].strip()
+            for name in body.split('  '):
+                if name in relation_categories:
+                    trip = [si // n, si % n, relation_categories.index(name)]
+                    if trip not in rel_pred:
+                        rel_pred.append(trip)
+                        rel_score.append(1)
+        return rel_pred, rel_score
+
+    class _Holder:
+        pass
+    rng = np.random.default_rng(0)
+    texts = []
+    for _ in range(60):
+        names = [relation_categories[i] for i in rng.integers(0, len(relation_categories), 12)]
+        names.insert(int(rng.integers(0, 12)), "not a relation")
+        texts.append("<s> " + "  ".join(names) + "</s> trailing")
+    texts += ["over  over  beside</s> junk", "<s> nothing here</s>", "", "<s> on  on  in front of  on</s>"]
+    selected = [int(x) for x in rng.integers(0, 64, len(texts))]          # repeated pairs included
+    assert RelationTransformerHeadV4._parse_relations(_Holder(), selected, 8, texts) == reference_loop(selected, 8, texts)
