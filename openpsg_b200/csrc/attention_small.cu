@@ -648,29 +648,51 @@ __global__ void __launch_bounds__(128) decode_attn_tma_kernel(const __grid_const
   const int k_r = ((lane >> 4) & 1) * 8 + (lane & 7), k_c = (lane >> 3) & 1;
   const int v_r = ((lane >> 3) & 1) * 8 + (lane & 7), v_c = (lane >> 4) & 1;
   uint32_t phase = 0;
+  // The item's own small loads (query row, new token's k / v row, key-mask bytes: lane l holds keys l, l + 32, ...) are fetched
+  // ONE ITEM AHEAD into registers and consumed at the top of the next iteration: their ~1 us of global latency then runs under
+  // the current item's arithmetic instead of in front of it (ncu: long-scoreboard stalls were the largest stall class).
+  uint4 rq = make_uint4(0u, 0u, 0u, 0u), rk = rq, rv = rq;
+  uint32_t rmask[NT / 2];
+  auto prefetch = [&](int it) {
+    const int sq = it / groups, hd = (it - sq * groups) * HW;
+    const __nv_bfloat16* nk = p.q + static_cast<size_t>(sq) * p.ld_q + hd * HD;          // + d_model: k, + 2 d_model: v
+    if (lane < C * HW) {
+      rq = __ldg(reinterpret_cast<const uint4*>(nk + lane * 8));
+      if (p.append_kv) {
+        rk = __ldg(reinterpret_cast<const uint4*>(nk + p.d_model + lane * 8));
+        rv = __ldg(reinterpret_cast<const uint4*>(nk + 2 * p.d_model + lane * 8));
+      }
+    }
+    const uint8_t* km = p.key_mask + static_cast<size_t>(sq) * p.max_ctx;
+#pragma unroll
+    for (int r = 0; r < NT / 2; ++r) {
+      const int key = r * 32 + lane;
+      rmask[r] = key < ctx ? static_cast<uint32_t>(__ldg(km + key)) : 0u;
+    }
+  };
+  prefetch(first);
 
   for (int item = first; item < p.B; item += stride, phase ^= 1u) {
     const int seq = item / groups, head = (item - seq * groups) * HW;
     const int next = item + stride;
     __nv_bfloat16* kbase = const_cast<__nv_bfloat16*>(p.k_cache) + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
     __nv_bfloat16* vbase = const_cast<__nv_bfloat16*>(p.v_cache) + static_cast<size_t>(seq) * p.max_ctx * p.d_model + head * HD;
-    const uint8_t* kmask = p.key_mask + static_cast<size_t>(seq) * p.max_ctx;
-    const __nv_bfloat16* new_kv = p.q + static_cast<size_t>(seq) * p.ld_q + head * HD;    // + d_model: k, + 2 d_model: v
-    // the query row and the new token's k / v: into shared memory (rows the tensor copies do not touch) AND into the caches
-    // (replaces a kv_append launch)
+    // the query row and the new token's k / v (prefetched): into shared memory (rows the tensor copies do not touch) AND into
+    // the caches (replaces a kv_append launch)
     if (lane < C * HW) {
-      *reinterpret_cast<uint4*>(sQ + lane * 16) = __ldg(reinterpret_cast<const uint4*>(new_kv + lane * 8));
+      *reinterpret_cast<uint4*>(sQ + lane * 16) = rq;
       if (p.append_kv) {
-        const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(new_kv + p.d_model + lane * 8));
-        const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(new_kv + 2 * p.d_model + lane * 8));
-        *reinterpret_cast<uint4*>(sK + L::at(ctx - 1, lane, ctx16)) = k4;
-        *reinterpret_cast<uint4*>(sV + L::at(ctx - 1, lane, ctx16)) = v4;
+        *reinterpret_cast<uint4*>(sK + L::at(ctx - 1, lane, ctx16)) = rk;
+        *reinterpret_cast<uint4*>(sV + L::at(ctx - 1, lane, ctx16)) = rv;
         const size_t off = static_cast<size_t>(ctx - 1) * p.d_model + lane * 8;
-        *reinterpret_cast<uint4*>(kbase + off) = k4;
-        *reinterpret_cast<uint4*>(vbase + off) = v4;
+        *reinterpret_cast<uint4*>(kbase + off) = rk;
+        *reinterpret_cast<uint4*>(vbase + off) = rv;
       }
     }
-    // key validity of this lane's score columns (keys t*16 + quad*2 + {0, 1} and + 8): read while the copies are in flight
+    // key validity: 32 keys per ballot word, then this lane's score columns (keys t*16 + quad*2 + {0, 1} and + 8)
+    uint32_t vw[NT / 2];
+#pragma unroll
+    for (int r = 0; r < NT / 2; ++r) vw[r] = __ballot_sync(0xffffffffu, rmask[r] != 0u);
     uint32_t valid[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
@@ -678,11 +700,12 @@ __global__ void __launch_bounds__(128) decode_attn_tma_kernel(const __grid_const
       if (t * 16 < ctx) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int key = t * 16 + (j >> 1) * 8 + quad * 2 + (j & 1);
-          if (key < ctx && __ldg(kmask + key) != 0) valid[t] |= 1u << j;
+          const int bit = (t & 1) * 16 + (j >> 1) * 8 + quad * 2 + (j & 1);     // key = t * 16 + ... = (t >> 1) * 32 + bit
+          if ((vw[t >> 1] >> bit) & 1u) valid[t] |= 1u << j;
         }
       }
     }
+    if (next < p.B) prefetch(next);
 
     // ---- S = q K^T --------------------------------------------------------------------------------------
     __syncwarp();
@@ -699,21 +722,30 @@ __global__ void __launch_bounds__(128) decode_attn_tma_kernel(const __grid_const
     }
     float sc[NT][4];                                        // [t][0..1]: keys t*16 + quad*2 + {0,1}; [t][2..3]: the same + 8
     float mx = -INFINITY;
+    // two key tiles per step: four independent accumulator chains in flight (a lone tile leaves two chains of depth HD / 16 and
+    // the warp waits out every mma's latency).  The second tile of the last pair may lie past the context: its rows are then
+    // whatever follows in the warp's own buffer, and its scores are masked (valid bits are zero there).
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
+    for (int t = 0; t < NT; t += 2) {
       if (t * 16 < ctx) {
-        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kb = 0; kb < HD / 16; ++kb) {
-          uint32_t b[4];
+          uint32_t b[4], b2[4];
           ldmatrix_x4(b, sK + L::at(t * 16 + k_r, hh * C + kb * 2 + k_c, ctx16));
+          ldmatrix_x4(b2, sK + L::at(t * 16 + 16 + k_r, hh * C + kb * 2 + k_c, ctx16));
           const uint32_t a[4] = {qa[kb][0], qa[kb][0], qa[kb][1], qa[kb][1]};
           mma_bf16_16816(c0, a, b[0], b[1]);
           mma_bf16_16816(c1, a, b[2], b[3]);
+          mma_bf16_16816(c2, a, b2[0], b2[1]);
+          mma_bf16_16816(c3, a, b2[2], b2[3]);
         }
         sc[t][0] = (valid[t] & 1u) ? c0[0] : -INFINITY; sc[t][1] = (valid[t] & 2u) ? c0[1] : -INFINITY;
         sc[t][2] = (valid[t] & 4u) ? c1[0] : -INFINITY; sc[t][3] = (valid[t] & 8u) ? c1[1] : -INFINITY;
+        sc[t + 1][0] = (valid[t + 1] & 1u) ? c2[0] : -INFINITY; sc[t + 1][1] = (valid[t + 1] & 2u) ? c2[1] : -INFINITY;
+        sc[t + 1][2] = (valid[t + 1] & 4u) ? c3[0] : -INFINITY; sc[t + 1][3] = (valid[t + 1] & 8u) ? c3[1] : -INFINITY;
         mx = fmaxf(fmaxf(mx, fmaxf(sc[t][0], sc[t][1])), fmaxf(sc[t][2], sc[t][3]));
+        mx = fmaxf(fmaxf(mx, fmaxf(sc[t + 1][0], sc[t + 1][1])), fmaxf(sc[t + 1][2], sc[t + 1][3]));
       }
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
