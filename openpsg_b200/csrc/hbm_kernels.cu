@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16
 // (what the producing GEMM wrote last is still in L2).
 constexpr int kLnRingStages = 4, kLnRingRows = 8;
 
-template <int CHUNKS>
+template <int CHUNKS, bool FULL>                             // FULL: cols == CHUNKS * 256 exactly (768: no column guards)
 __global__ void __launch_bounds__(256, 2) layernorm_ring_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps,
                                                                  __nv_bfloat16* __restrict__ y, int rows, int cols, int slabs_per_cta) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_ring_kernel(const __nv_bfloa
 #pragma unroll
   for (int i = 0; i < CHUNKS; ++i) {
     const int c0 = (i * 32 + lane) * 8;
-    if (c0 < cols) {
+    if (FULL || c0 < cols) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
       g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_ring_kernel(const __nv_bfloa
 #pragma unroll
       for (int i = 0; i < CHUNKS; ++i) {
         const int c0 = (i * 32 + lane) * 8;
-        if (c0 < cols) {
+        if (FULL || c0 < cols) {
           const uint4 u = *reinterpret_cast<const uint4*>(src + c0 * 2);
           v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
           v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_ring_kernel(const __nv_bfloa
       float ss = 0.f;
 #pragma unroll
       for (int i = 0; i < CHUNKS; ++i)
-        if ((i * 32 + lane) * 8 < cols) {
+        if (FULL || (i * 32 + lane) * 8 < cols) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; ss += d * d; }
         }
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_ring_kernel(const __nv_bfloa
 #pragma unroll
       for (int i = 0; i < CHUNKS; ++i) {
         const int c0 = (i * 32 + lane) * 8;
-        if (c0 < cols) {
+        if (FULL || c0 < cols) {
           float o[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[i][k] + b[i][k];
@@ -661,14 +661,17 @@ extern "C" int opsg_layernorm_bf16(const opsg_bf16* x, const float* gamma, const
     static bool configured_dev[64] = {};
     bool& configured = configured_dev[device_slot()];
     if (!configured) {
-      rc = check_cuda(cudaFuncSetAttribute(layernorm_ring_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute(layernorm_ring<3>)");
+      rc = check_cuda(cudaFuncSetAttribute(layernorm_ring_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute(layernorm_ring<3, true>)");
       if (rc) return rc;
-      rc = check_cuda(cudaFuncSetAttribute(layernorm_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute(layernorm_ring<4>)");
+      rc = check_cuda(cudaFuncSetAttribute(layernorm_ring_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute(layernorm_ring<3, false>)");
+      if (rc) return rc;
+      rc = check_cuda(cudaFuncSetAttribute(layernorm_ring_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute(layernorm_ring<4, false>)");
       if (rc) return rc;
       configured = true;
     }
-    if (cols <= 768) launch_kernel(layernorm_ring_kernel<3>, ctas, 256, smem, ST(stream), xp, gamma, beta, eps, yp, rows, cols, spc);
-    else launch_kernel(layernorm_ring_kernel<4>, ctas, 256, smem, ST(stream), xp, gamma, beta, eps, yp, rows, cols, spc);
+    if (cols == 768) launch_kernel(layernorm_ring_kernel<3, true>, ctas, 256, smem, ST(stream), xp, gamma, beta, eps, yp, rows, cols, spc);
+    else if (cols < 768) launch_kernel(layernorm_ring_kernel<3, false>, ctas, 256, smem, ST(stream), xp, gamma, beta, eps, yp, rows, cols, spc);
+    else launch_kernel(layernorm_ring_kernel<4, false>, ctas, 256, smem, ST(stream), xp, gamma, beta, eps, yp, rows, cols, spc);
     OPSG_CHECK_LAUNCH("layernorm_ring_kernel");
     return OPSG_OK;
   }
