@@ -138,7 +138,9 @@ int opsg_self_attn_small(const opsg_bf16* qkv, const opsg_bf16* shared_query_qkv
  * bits: uint32 [N, words] from opsg_pair_mask_bits; pair_index int32 [B] or NULL (p -> pair p);
  * pair p = (i, j) = (pair / N, pair % N) attends keys where bits[i] | bits[j]; masked keys get the
  * reference's finfo.min bias (weight exactly 0; an all-masked pair attends uniformly to all L keys).
- * ctx_out: bf16 [B*n_query, d].  Requires head_dim == 64, L <= 256.
+ * ctx_out: bf16 [B*n_query, d].  Requires head_dim == 64.  L <= 256 image tokens run on the tcgen05 kernels (one 256-key score
+ * tile per unit in tensor memory); longer inputs (the reference has no limit, v4:408-435) take an online-softmax mma.sync kernel
+ * that reads the mask bits directly (pass bias_tiles == NULL: the operand tiles and opsg_token_order cover L <= 256 only).
  *
  * bias_tiles (optional, recommended): the pair masks pre-arranged as tensor-core operand tiles by
  * opsg_xattn_bias_tiles() into a caller-provided buffer of opsg_xattn_bias_tiles_bytes(B, n_query) bytes.

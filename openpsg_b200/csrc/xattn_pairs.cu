@@ -46,6 +46,10 @@ extern "C" int opsg_xattn_pairs_v2(const opsg_bf16* q, const opsg_bf16* k, int l
 
 namespace opsg {
 
+int launch_xattn_pairs_long(const opsg_bf16* q, const opsg_bf16* k, int ld_k, const opsg_bf16* vt, int ld_vt, const uint32_t* bits,
+                            int words, const int32_t* pair_index, int num_objects, int B, int n_query, int L, int num_heads,
+                            int head_dim, opsg_bf16* ctx_out, cudaStream_t stream);
+
 constexpr int kXaThreads = 512;
 constexpr int kXaKeys = 256;       // max keys (one N=256 MMA)
 constexpr int kXaHd = 64;
@@ -817,6 +821,10 @@ extern "C" int opsg_xattn_pairs(const opsg_bf16* q, const opsg_bf16* k, int ld_k
                                 const uint32_t* bits, int words, const int32_t* pair_index, int num_objects, int B,
                                 int n_query, int L, int num_heads, int head_dim, const void* bias_tiles,
                                 opsg_bf16* ctx_out, void* stream) {
+  // more image tokens than one 256-key score tile: the online-softmax kernel (xattn_pairs_long.cu)
+  if (L > kXaKeys)
+    return launch_xattn_pairs_long(q, k, ld_k, vt, ld_vt, bits, words, pair_index, num_objects, B, n_query, L, num_heads, head_dim,
+                                   ctx_out, reinterpret_cast<cudaStream_t>(stream));
   // without precomputed mask-bias tiles (or for shapes they do not cover) the self-contained v2 kernel runs
   if (!bias_tiles || n_query <= 0 || 127 / n_query + 2 > kXaSlots)
     return opsg_xattn_pairs_v2(q, k, ld_k, vt, ld_vt, bits, words, pair_index, num_objects, B, n_query, L, num_heads,

@@ -292,6 +292,8 @@ def xattn_pairs(q, k, vt, bits, num_objects, B, n_query, L, num_heads, head_dim,
     assert q.is_contiguous()
     if out is None:
         out = torch.empty_like(q)
+    if bias_tiles is None and L > 256:                    # the online-softmax kernel reads the mask bits directly
+        bias_tiles = False
     if bias_tiles is None:
         bias_tiles = xattn_bias_tiles(bits, num_objects, B, n_query, L, pair_index)
     elif bias_tiles is False:

@@ -26,6 +26,7 @@ from .graphs import GraphCache
 NUM_HEADS = 12
 HEAD_DIM = 64
 N_QUERY = 33
+MAX_TILE_KEYS = 256      # image tokens the tcgen05 cross-attention kernels keep in one score tile (more: online-softmax kernel)
 LN_EPS = 1e-12
 
 
@@ -277,10 +278,15 @@ class RelationQueryTransformer:
         bits = ops.pair_mask_bits(pan, img_hw, pad_hw, (th, tw), obj_ids)       # K2
         # K5 sees the image tokens sorted by owning object (attention does not depend on the key order; contiguous
         # objects make most 16-key chunks invisible to a group of pair queries, whose exponentials are then skipped)
-        perm, bits_k = ops.token_order(bits, L)
-        bias_tiles = ops.xattn_bias_tiles(bits_k, N, B, N_QUERY, L, pair_index)  # K5 mask operand tiles (both layers)
         X = self.image_tokens(feat)                                              # K1  [L,256]
-        Xk = ops.gather_rows(X, X.shape[1], perm)                                # key-order copy for the K / V projections
+        if L <= MAX_TILE_KEYS:
+            perm, bits_k = ops.token_order(bits, L)
+            bias_tiles = ops.xattn_bias_tiles(bits_k, N, B, N_QUERY, L, pair_index)  # K5 mask operand tiles (both layers)
+            Xk = ops.gather_rows(X, X.shape[1], perm)                            # key-order copy for the K / V projections
+        else:
+            # more image tokens than one tensor-memory score tile holds: K5 runs its online-softmax kernel straight from the
+            # mask bits (csrc/xattn_pairs_long.cu); no key reordering, no operand tiles
+            bits_k, bias_tiles, Xk = bits, False, X
         h = ops.qformer_embed_ln(w.query, input_ids, w.word_emb, w.pos_emb, w.emb_ln[0], w.emb_ln[1], LN_EPS)   # K7
         RQ = B * N_QUERY
         if inter is not None:

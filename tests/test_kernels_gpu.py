@@ -449,6 +449,32 @@ def test_xattn_pairs(ops, L, N, B):
     assert (last - v.float().mean(0, keepdim=True)).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("L,N,subset", [(257, 5, False), (320, 6, True), (512, 4, False), (1000, 3, True)])
+def test_xattn_pairs_more_than_256_keys(ops, L, N, subset):
+    """More image tokens than one tensor-memory score tile: the online-softmax kernel (csrc/xattn_pairs_long.cu) -- same
+    semantics (masked keys weigh 0, an all-masked pair gets the mean of V), pair_index subsets, ragged last key block."""
+    g = torch.Generator().manual_seed(L + N)
+    nq, d = 33, 768
+    pairs = torch.randperm(N * N, generator=g)[: N * N - 3].to(torch.int32) if subset else None
+    B = pairs.numel() if subset else N * N
+    q, k, v = _rand_bf16((B * nq, d), g), _rand_bf16((L, d), g), _rand_bf16((L, d), g)
+    masks = torch.rand(N, L, generator=g) < 0.1
+    masks[N - 1] = False                                  # pair (N-1, N-1) is all-masked
+    masks[0, : L // 2] = False                            # object 0 only sees the second half of the keys
+    bits = torch.from_numpy(restated.pack_mask_bits(masks.numpy()).view(np.int32))
+    Lp = (L + 7) // 8 * 8
+    vt = torch.zeros((d, Lp), dtype=torch.bfloat16)
+    vt[:, :L] = v.t()
+    out = ops.xattn_pairs(q.cuda(), k.cuda(), vt.cuda(), bits.cuda(), N, B, nq, L, 12, 64,
+                          pair_index=pairs.cuda() if subset else None, bias_tiles=False).float().cpu()
+    ref = _xattn_ref(q, k, v, masks, N, pairs.long() if subset else None, nq)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-2, err
+    if not subset:
+        last = out[(B - 1) * nq:(B - 1) * nq + 1]
+        assert (last - v.float().mean(0, keepdim=True)).abs().max() < 2e-2
+
+
 def test_xattn_pairs_without_bias_tiles(ops):
     """bias_tiles == NULL selects the self-contained kernel (per-row OR of the bit rows): same results."""
     g = torch.Generator().manual_seed(3)
@@ -545,15 +571,16 @@ def test_xattn_pairs_with_pair_index(ops):
     assert (out - ref).abs().max() < 2e-2
 
 
-def test_xattn_rejects_long_context(ops):
+def test_xattn_operand_tiles_reject_more_than_256_keys(ops):
+    """The tensor-memory kernels' helpers (key order, mask operand tiles) cover <= 256 image tokens and say so; opsg_xattn_pairs
+    itself takes longer inputs through the online-softmax kernel (test_xattn_pairs_more_than_256_keys)."""
     from openpsg_b200._lib import OPSG_E_UNSUPPORTED, OpsgError
-    z = torch.zeros((33, 768), dtype=torch.bfloat16, device="cuda")
-    k = torch.zeros((300, 768), dtype=torch.bfloat16, device="cuda")
-    vt = torch.zeros((768, 304), dtype=torch.bfloat16, device="cuda")
     bits = torch.zeros((1, 10), dtype=torch.int32, device="cuda")
     with pytest.raises(OpsgError) as e:
-        ops.xattn_pairs(z, k, vt, bits, 1, 1, 33, 300, 12, 64)
+        ops.xattn_bias_tiles(bits, 1, 1, 33, 300, None)
     assert e.value.code == OPSG_E_UNSUPPORTED
+    with pytest.raises(OpsgError):
+        ops.token_order(bits, 300)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -279,3 +279,38 @@ def test_relation_queries_80_objects_subset_vs_oracle(head):
     L = m.shape[1]
     obj = ((bits[:, np.arange(L) // 32] >> (np.arange(L) % 32).astype(np.uint32)) & 1).astype(bool)
     assert np.array_equal(obj, m.numpy())
+
+
+def test_image_with_more_than_256_tokens_vs_oracle(head):
+    """A 1024 x 1280 image = 320 image tokens (the tcgen05 cross-attention kernels hold 256): the engine takes the online-softmax
+    kernel without key reordering / operand tiles and must agree with the fp32 oracle like any other image (the reference has no
+    token limit, v4:408-435)."""
+    wl = synth.Workload("wide", 1024, 1280, 6)
+    inputs = synth.make_image_inputs(wl, 3)
+    head(synth.inputs_to(inputs, "cuda:0"), is_generation=False)
+    out = head.last_output
+    n = wl.num_objects
+    assert out.image_tokens.shape[0] == 320 and out.logits.numel() == n * n
+    sd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
+    meta, info = inputs["img_metas"][0], inputs["object_info"][0]
+    ids = [int(i) for i in info["object_id_list"]]
+    m = torch.from_numpy(restated.object_token_masks(info["pan_results"].numpy(), meta["img_shape"][:2], meta["pad_shape"][:2],
+                                                     inputs["mask_features"].shape[-2:], 16, ids))
+    tokens = restated.patch_embed(inputs["mask_features"], sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], 16)
+    from openpsg_b200.categories import object_categories
+    names = [object_categories[i % 1000] for i in ids]
+    sample = torch.arange(n * n)
+    enc = synth.SyntheticTokenizer("qformer")(
+        ['Is there a relation between {} and {}?'.format(names[p // n], names[p % n]) for p in sample.tolist()])
+    query = torch.cat([sd["rel_cls_query"], sd["relation_query"]], dim=1)[0]
+    ref = restated.qformer_forward(sd, query, enc["input_ids"], enc["attention_mask"], tokens, m, pair_index=sample)
+    got = out.hidden.float().cpu().reshape(n * n, 33, 768)
+    d = (got - ref).abs()
+    print(f"320 tokens: max|dO|={d.max():.4f} mean|dO|={d.mean():.5f}")
+    assert d.max() <= TOL_O_MAX and d.mean() <= TOL_O_MEAN, (d.max(), d.mean())
+    z_ref = restated.existence_logits(ref[:, 0], sd["binary_rel_cls_pred.weight"], sd["binary_rel_cls_pred.bias"])
+    assert (out.logits.cpu() - z_ref).abs().max() <= 4e-2
+    bits = out.mask_bits.cpu().numpy().view(np.uint32)
+    L = m.shape[1]
+    obj = ((bits[:, np.arange(L) // 32] >> (np.arange(L) % 32).astype(np.uint32)) & 1).astype(bool)
+    assert np.array_equal(obj, m.numpy())
