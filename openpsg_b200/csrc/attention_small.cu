@@ -1,12 +1,12 @@
-// K4 / K10a / K10b — small-sequence multi-head attention (Q-Former self-attention over S = 33 + T <= 64 rows per
-// pair; OPT / Llama prefill / decode attention over a static KV cache, context <= 256).
+// K4 / K10a fallbacks and K10b — small-sequence multi-head attention on warp-level mma.sync.
 //
-// These problems are tiny and independent (B * heads of them, <= 64 x 128 scores each): one CTA per
-// (sequence, head), whole K / V / Q tile in shared memory (row-major, 16-byte copies; the PV B fragments come
-// from ldmatrix.trans, so V is never transposed through memory), register-resident FlashAttention-2 style
-// softmax on warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  They carry ~1% of the path's FLOPs; the big
-// tensor-core work (GEMMs, pair cross-attention) is on tcgen05 — packing several sequences per 128-row tcgen05
-// tile with a block-diagonal mask is the planned upgrade for this kernel.
+//  * `qformer_self_attn_kernel`, `small_attn_kernel`: the FALLBACKS of the tcgen05 + TMA kernels (self_attn_pairs.cu: Q-Former
+//    self-attention over S = 33 + T <= 64 rows per pair; llm_prefill_attn.cu: LLM prefill) for the shapes those do not cover
+//    (head_dim != 64 / more than 31 text tokens; prompts longer than 64 tokens or a non-zero first position).  One CTA per
+//    (sequence, head), whole K / V / Q tile in shared memory, FlashAttention-2 style register-resident softmax.
+//  * `decode_attn_tma_kernel`: K10b, the LLM decode step (ONE query row per sequence: not a tensor-core tile; HBM-bound on the
+//    K / V cache) — TMA-staged head slices, persistent warps, 5.7 TB/s at 800 sequences (see its own header below);
+//    `decode_attn_kernel` is its register-staged fallback for unaligned operands / contexts beyond 256 keys.
 #include "common.cuh"
 #include "host_util.h"
 
