@@ -10,15 +10,16 @@ from openpsg_b200.llm import build_llm_engine
 
 dev = torch.device("cuda:0")
 n_new = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+n_img = int(sys.argv[2]) if len(sys.argv) > 2 else 1          # > 1: the stacked batch of head.forward_batch (n_img x 100 sequences)
 with torch.device(dev):
     lm = OPTForCausalLM(OPTConfig(**synth.OPT_2P7B)).eval()
     proj = torch.nn.Linear(768, 2560)
 eng = build_llm_engine(lm, proj, dev, use_cuda_graphs=False)
 del lm
-k, T = 100, 17
+k, T = 100 * n_img, 17
 g = torch.Generator().manual_seed(5)
 hidden = torch.randn((1600 * 33, 768), generator=g).to(torch.bfloat16).to(dev)
-sel = torch.randperm(1600, generator=g)[:k].to(torch.int32).to(dev)
+sel = torch.cat([torch.randperm(1600, generator=g)[:100] for _ in range(n_img)]).to(torch.int32).to(dev)
 ids = torch.randint(4, 50272, (k, T), generator=g).to(torch.int32).to(dev)
 mask = torch.ones((k, T), dtype=torch.int32, device=dev)
 eng.generate(hidden, sel, ids, mask, max_new_tokens=2)      # warm-up (first-use attribute calls)
