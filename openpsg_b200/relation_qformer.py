@@ -223,6 +223,18 @@ class RelationQueryTransformer:
         # PatchEmbed's split-K is deterministic by default (per-split partial slices + fixed-order reduction);
         # OPSG_PATCH_DETERMINISTIC=0 selects the round-1 fp32-atomics accumulation (run-to-run differences in the last bit)
         self.deterministic_patch_embed = os.environ.get("OPSG_PATCH_DETERMINISTIC", "1") != "0"
+        self._streams = {}          # device index -> (mask-chain stream, embedding stream)
+
+    def _side_streams(self, dev):
+        """Two side streams per device for the independent chains at the head of an image (see ``forward``).  Blocks they
+        allocate return to their own pools and are only reused after the next forward's ``wait_stream(current)``, i.e. after
+        everything the current stream did with them."""
+        key = torch.device(dev).index
+        st = self._streams.get(key)
+        if st is None:
+            st = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            self._streams[key] = st
+        return st
 
     # -- K1 ------------------------------------------------------------------------------------------
     def image_tokens(self, feat: torch.Tensor) -> torch.Tensor:
@@ -275,19 +287,31 @@ class RelationQueryTransformer:
             return self._forward_folded(feat, pan, img_hw, pad_hw, obj_ids, input_ids, text_mask, topk, threshold, pair_index,
                                         inter)
 
-        bits = ops.pair_mask_bits(pan, img_hw, pad_hw, (th, tw), obj_ids)       # K2
-        # K5 sees the image tokens sorted by owning object (attention does not depend on the key order; contiguous
-        # objects make most 16-key chunks invisible to a group of pair queries, whose exponentials are then skipped)
+        # The three chains at the head of an image are independent and each too small to fill the machine (40 / 1 / 413 CTAs of
+        # mask work, the PatchEmbed GEMM, 3 k CTAs of embeddings): they run as three branches -- two side streams forked off
+        # the current one and joined before their results are used (inside a CUDA graph: three parallel branches).  Serial they
+        # cost ~130 us per cfg2 image, the longest branch ~55 us.
+        cur = torch.cuda.current_stream(dev)
+        s_mask, s_embed = self._side_streams(dev)
+        s_mask.wait_stream(cur)
+        s_embed.wait_stream(cur)
+        with torch.cuda.stream(s_mask):
+            bits = ops.pair_mask_bits(pan, img_hw, pad_hw, (th, tw), obj_ids)   # K2
+            # K5 sees the image tokens sorted by owning object (attention does not depend on the key order; contiguous
+            # objects make most 16-key chunks invisible to a group of pair queries, whose exponentials are then skipped)
+            if L <= MAX_TILE_KEYS:
+                perm, bits_k = ops.token_order(bits, L)
+                bias_tiles = ops.xattn_bias_tiles(bits_k, N, B, N_QUERY, L, pair_index)  # K5 mask operand tiles (both layers)
+            else:
+                # more image tokens than one tensor-memory score tile holds: K5 runs its online-softmax kernel straight from
+                # the mask bits (csrc/xattn_pairs_long.cu); no key reordering, no operand tiles
+                perm, bits_k, bias_tiles = None, bits, False
+        with torch.cuda.stream(s_embed):
+            h = ops.qformer_embed_ln(w.query, input_ids, w.word_emb, w.pos_emb, w.emb_ln[0], w.emb_ln[1], LN_EPS)   # K7
         X = self.image_tokens(feat)                                              # K1  [L,256]
-        if L <= MAX_TILE_KEYS:
-            perm, bits_k = ops.token_order(bits, L)
-            bias_tiles = ops.xattn_bias_tiles(bits_k, N, B, N_QUERY, L, pair_index)  # K5 mask operand tiles (both layers)
-            Xk = ops.gather_rows(X, X.shape[1], perm)                            # key-order copy for the K / V projections
-        else:
-            # more image tokens than one tensor-memory score tile holds: K5 runs its online-softmax kernel straight from the
-            # mask bits (csrc/xattn_pairs_long.cu); no key reordering, no operand tiles
-            bits_k, bias_tiles, Xk = bits, False, X
-        h = ops.qformer_embed_ln(w.query, input_ids, w.word_emb, w.pos_emb, w.emb_ln[0], w.emb_ln[1], LN_EPS)   # K7
+        cur.wait_stream(s_mask)
+        Xk = X if perm is None else ops.gather_rows(X, X.shape[1], perm)         # key-order copy for the K / V projections
+        cur.wait_stream(s_embed)
         RQ = B * N_QUERY
         if inter is not None:
             inter["embeddings"] = h
