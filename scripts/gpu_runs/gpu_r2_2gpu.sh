@@ -8,6 +8,8 @@ import json
 d=json.loads([x for x in open('gpurun_out/r2_bench_2gpu.json') if x.startswith('{')][-1])
 print('N', d['n_gpus'], 'value', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'sha1', d['results']['sha1'])
 for k in ('e2e_cfg3','e2e_cfg5'):
+    if k not in d: continue
     e=d[k]; print(k, e['ms_per_step'], e['relation_tokens_per_sec'], e['llm_batch'], '| per image:', e['llm_one_image_per_batch']['ms_per_step'], e['llm_one_image_per_batch']['relation_tokens_per_sec'])
-r=d['relation_tokens_per_sec']; print('stacked', r['value'], r['ms_per_batch'], r['sequences'])
+r=d.get('relation_tokens_per_sec')
+if r: print('stacked', r['value'], r['ms_per_batch'], r['sequences'])
 P
