@@ -96,3 +96,51 @@ def test_parse_relations_equals_the_reference_loop():
     texts += ["over  over  beside</s> junk", "<s> nothing here</s>", "", "<s> on  on  in front of  on</s>"]
     selected = [int(x) for x in rng.integers(0, 64, len(texts))]          # repeated pairs included
     assert RelationTransformerHeadV4._parse_relations(_Holder(), selected, 8, texts) == reference_loop(selected, 8, texts)
+
+
+def test_decode_group_pads_prompts_and_splits_results_per_image():
+    """head._decode_group (the LLM leg of forward_batch over a group of images) on CPU with a recording stand-in for the
+    engine: prompts of different images are LEFT-padded to the group's longest one with masked pad tokens (v4:260-266 pads the
+    same way inside one image), the stacked rows / top-k reach the engine in image order, every image gets its own slice of
+    the generated tokens (on_result sees it as last_generation), images without objects yield empty results."""
+    from types import SimpleNamespace
+    from openpsg_b200.llm import GenerationOutput
+    head = build_product_head(llm=synth.OPT_TINY, topk_pairs=4, max_new_tokens=5)
+    head._packed = SimpleNamespace(device=torch.device("cpu"))
+    calls = []
+
+    class Engine:
+        def generate_rows(self, rows, ids, mask, max_new_tokens=16):
+            calls.append((rows.clone(), ids.clone(), mask.clone(), max_new_tokens))
+            k = ids.shape[0]
+            # sequence s "generates" relation class s % 56 five times (SyntheticTokenizer decodes token t to class t % 56)
+            return GenerationOutput(tokens=(torch.arange(k, dtype=torch.int32)[:, None] % 56).repeat(1, max_new_tokens))
+    head._llm_engine = Engine()
+    width = 33 * 768
+    n_a, n_b = 5, 3                                               # objects per image: 25 and 9 pair queries
+    cats_a = np.array([0, 1, 2, 3, 4]); cats_b = np.array([130, 131, 132])      # different names -> different prompt lengths
+    bufs = (torch.zeros((8, width), dtype=torch.bfloat16), torch.zeros((8,), dtype=torch.int32))
+    top_a = torch.tensor([7, 0, 24, 13], dtype=torch.int32); top_b = torch.tensor([8, 1, 4], dtype=torch.int32)   # image b: k = 3 < topk
+    bufs[1][:4] = top_a; bufs[1][4:7] = top_b
+    bufs[0][:7, 0] = torch.arange(7, dtype=torch.bfloat16)
+    rec_a = dict(prep=dict(n=n_a, cats=cats_a), out=object(), rows=bufs[0][:4], topk=bufs[1][:4], slot=0)
+    rec_empty = dict(prep=dict(n=0), out=None)
+    rec_b = dict(prep=dict(n=n_b, cats=cats_b), out=object(), rows=bufs[0][4:7], topk=bufs[1][4:7], slot=4)
+    seen = []
+    results = head._decode_group([rec_a, rec_empty, rec_b], bufs, on_result=lambda h: seen.append(h.last_generation.tokens.clone()))
+    assert len(calls) == 1 and len(results) == 3 and results[1] == {"rel_pred": [], "rel_score": []}
+    rows, ids, mask, mnt = calls[0]
+    assert mnt == 5 and rows.shape == (7, width) and torch.equal(rows[:, 0].float(), torch.arange(7.0))
+    # prompts: each image's own lookup, left-padded to the longest of the group
+    ia, ma = head._llm_cache.lookup(cats_a[top_a.numpy() // n_a], cats_a[top_a.numpy() % n_a])
+    ib, mb = head._llm_cache.lookup(cats_b[top_b.numpy() // n_b], cats_b[top_b.numpy() % n_b])
+    T = max(ia.shape[1], ib.shape[1])
+    assert ids.shape == (7, T) and mask.shape == (7, T) and ia.shape[1] != ib.shape[1]
+    for got_i, got_m, want_i, want_m in ((ids[:4], mask[:4], ia, ma), (ids[4:], mask[4:], ib, mb)):
+        pad = T - want_i.shape[1]
+        assert torch.equal(got_i[:, pad:], want_i) and torch.equal(got_m[:, pad:], want_m)
+        assert (got_m[:, :pad] == 0).all() and (got_i[:, :pad] == head._llm_cache.pad_id).all()
+    # results: sequence s of the stacked batch said "relation s % 56" -> one triple per selected pair, in top-k order
+    assert results[0]["rel_pred"] == [[7 // 5, 7 % 5, 0], [0, 0, 1], [24 // 5, 24 % 5, 2], [13 // 5, 13 % 5, 3]]
+    assert results[2]["rel_pred"] == [[8 // 3, 8 % 3, 4], [0, 1, 5], [4 // 3, 4 % 3, 6]]
+    assert [t.shape for t in seen] == [(4, 5), (3, 5)] and int(seen[1][0, 0]) == 4
